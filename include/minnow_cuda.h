@@ -1,0 +1,222 @@
+/*
+ * minnow_cuda.h -- C ABI of libminnow_b200.so: the block encode/decode hot path
+ * of phil-mansfield/minnow on one NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI today: its seam for this path is the private Go
+ * `group` interface (go/group.go:77-87) and package `bit`
+ * (go/bit/bit.go:19-206), called from Writer.Data (go/writer.go:90-104),
+ * Writer.Close (:107-141), Reader.Open (go/reader.go:28-88) and Reader.Data
+ * (:114-127).  Each entry point below names the reference code it replaces;
+ * INTEGRATION.md shows the cgo stubs that bind them behind the unchanged Go
+ * API.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Conventions
+ *  - every function returns 0 (MNW_OK) or a negative mnw_status; the message is
+ *    at mnw_last_error(ctx) (the Go glue re-panics with it, because the
+ *    reference's error convention is panic: go/writer.go:34,92; go/bit/bit.go:31).
+ *  - a context owns one CUDA stream, pinned staging and device scratch that grow
+ *    like bit.ArrayBuffer (go/bit/bit.go:188-206).  Like a minnow.Writer, a
+ *    context is NOT safe for concurrent use; use one per goroutine/thread.
+ *  - caller owns all in/out buffers for the duration of the call only.
+ *  - `_dev` variants take DEVICE pointers, enqueue on the context's stream and
+ *    do not synchronise; call mnw_sync() before reading results.
+ *  - integers are little-endian int64 like every on-disk integer of the format.
+ *  - there is no CPU fallback: without a CUDA device mnw_create fails.
+ *
+ * Results are bit-identical to the Go reference on the same inputs: packed
+ * bytes, per-block (min, bits), byte offsets, decoded int64 values, decoded
+ * pixel indices; decoded float32 values are bit-identical GIVEN the jitter
+ * stream (see mnw_jitter below).
+ */
+#ifndef MINNOW_CUDA_H
+#define MINNOW_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNW_API __attribute__((visibility("default")))
+
+typedef enum {
+    MNW_OK = 0,
+    MNW_ERR_CUDA = -1,       /* CUDA runtime error (message has the detail)  */
+    MNW_ERR_ARG = -2,        /* bad argument (where the reference panics)     */
+    MNW_ERR_CAPACITY = -3,   /* output buffer too small                       */
+    MNW_ERR_FORMAT = -4,     /* not a minnow/minh/minp file, wrong version    */
+    MNW_ERR_IO = -5,         /* file I/O failed                               */
+    MNW_ERR_TYPE = -6        /* TypeMatch failure, go/group.go:43-71          */
+} mnw_status;
+
+/* Group type codes, identical to go/group.go:11-24. */
+enum {
+    MNW_INT64_GROUP = 0, MNW_INT32_GROUP, MNW_INT16_GROUP, MNW_INT8_GROUP,
+    MNW_UINT64_GROUP, MNW_UINT32_GROUP, MNW_UINT16_GROUP, MNW_UINT8_GROUP,
+    MNW_FLOAT64_GROUP, MNW_FLOAT32_GROUP, MNW_INT_GROUP, MNW_FLOAT_GROUP
+};
+
+typedef struct mnw_ctx mnw_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+MNW_API int mnw_create(int device, mnw_ctx **out);
+MNW_API void mnw_destroy(mnw_ctx *ctx);
+MNW_API const char *mnw_last_error(const mnw_ctx *ctx); /* ctx may be NULL: last create error */
+MNW_API int mnw_sync(mnw_ctx *ctx);                     /* wait for the context's stream */
+MNW_API void *mnw_stream(mnw_ctx *ctx);                 /* the cudaStream_t, for event timing */
+MNW_API const char *mnw_version(void);
+/* Number of kernels this library has launched on ctx since creation. */
+MNW_API int64_t mnw_launch_count(const mnw_ctx *ctx);
+
+/* ---- package bit (leaf parity API) ----------------------------------------
+ * mnw_precision_needed  = bit.PrecisionNeeded  go/bit/bit.go:19-21 (Go's
+ *                         float64 log2 rounding is reproduced, including its
+ *                         under-count from max = 2^49; max = 2^64-1 returns
+ *                         MNW_ERR_ARG where Go's result is undefined).
+ * mnw_array_bytes       = bit.ArrayBytes       go/bit/bit.go:23-25
+ * mnw_pack              = bit.BufferedArray    go/bit/bit.go:84-134 (HOST ptrs;
+ *                         out holds mnw_array_bytes(bits, n); bits in 1..64)
+ * mnw_unpack            = (*Array).Slice       go/bit/bit.go:29-82  (HOST ptrs)
+ * mnw_bits              = ArrayBuffer.Bits     go/bit/bit.go:151-159 (HOST ptr)
+ */
+MNW_API int mnw_precision_needed(uint64_t max);
+MNW_API int64_t mnw_array_bytes(int bits, int64_t n);
+MNW_API int mnw_pack(mnw_ctx *ctx, int bits, const uint64_t *x, int64_t n, uint8_t *out);
+MNW_API int mnw_unpack(mnw_ctx *ctx, int bits, const uint8_t *in, int64_t n, uint64_t *out);
+MNW_API int mnw_bits(mnw_ctx *ctx, const uint64_t *x, int64_t n, int *bits);
+
+/* ---- group codecs ---------------------------------------------------------
+ * One call encodes nblocks consecutive blocks of one group; this replaces
+ * nblocks calls of intGroup.writeData (go/group.go:242-255) or
+ * floatGroup.writeData (:312-327) and the addBlock prefix sum
+ * (go/block_index.go:16-23).  Outputs, all [nblocks]:
+ *   mins[b], bits[b]  = what the reference appends to g.mins / g.bits
+ *   offsets[b]        = blockOffset(startBlock + b), go/block_index.go:25-35
+ *                       (EXCLUSIVE prefix sum of ArrayBytes(bits[b], n_b))
+ *   out[0, *out_len)  = the bytes the reference writes to the file for the
+ *                       group, blocks back to back (a block of 0 bits is empty)
+ * Blocks may be ragged: block b holds elements [starts[b], starts[b+1]) of x;
+ * pass starts = NULL for the format's usual equal-size case (block b =
+ * [b*n, (b+1)*n)); with starts given, n is ignored.
+ */
+typedef struct {
+    float low, high;      /* floatGroup.low / .high, go/group.go:271             */
+    int64_t pixels;       /* floatGroup.pixels (mnw_float_group_pixels)          */
+    uint8_t periodic;     /* floatGroup.periodic; Writer.FloatGroup passes 1     */
+    uint8_t log10;        /* minh Column.Log != 0: x <- float32(log10(float64 x)) */
+    uint8_t clamp;        /* minh processFloatGroup clamp to [low, nextafter(high)) */
+    uint8_t reserved[5];
+} mnw_float_desc;
+
+/* go/writer.go:73: pixels = int64(ceil(float64((hi - lo) / dx))) in float32 */
+MNW_API int64_t mnw_float_group_pixels(float lo, float hi, float dx);
+
+MNW_API int mnw_encode_int_group(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks,
+                                 const int64_t *starts, int64_t *mins, int64_t *bits,
+                                 int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len);
+MNW_API int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x,
+                                   int64_t n, int64_t nblocks, const int64_t *starts,
+                                   int64_t *mins, int64_t *bits, int64_t *offsets,
+                                   uint8_t *out, int64_t out_cap, int64_t *out_len);
+
+/* Decode nsel blocks of one group.  data/offsets/mins/bits describe the whole
+ * group (nblocks entries; offsets as produced above); sel lists the block ids
+ * to decode (NULL = blocks 0..nsel-1); block sel[j] lands at out + j*n.
+ * Replaces intGroup.readData (go/group.go:257-263) / floatGroup.readData
+ * (:299-310) per selected block (all blocks have n elements here).
+ *
+ * mnw_jitter: floatGroup.readData adds rand.Float64() from Go's global source
+ * (go/group.go:308), so the reference's decoded floats are not reproducible.
+ * The stream is explicit here:
+ *   mode MNW_JITTER_CENTER: u = 0.5
+ *   mode MNW_JITTER_HASH  : u = mnw_jitter_hash32(seed, block_id, i) * 2^-32,
+ *                           block_id = block_id0 + sel[j]
+ *   mode MNW_JITTER_STREAM: u = u_stream[j*n + i]   (caller's doubles in [0,1))
+ * out = dx*float32(float64(q) + u) + low in float32 without FMA, as in Go.
+ */
+enum { MNW_JITTER_CENTER = 0, MNW_JITTER_HASH = 1, MNW_JITTER_STREAM = 2 };
+typedef struct {
+    int32_t mode;
+    int32_t reserved;
+    uint64_t seed;
+    uint64_t block_id0;
+    const double *u_stream;
+} mnw_jitter;
+MNW_API uint32_t mnw_jitter_hash32(uint64_t seed, uint64_t block_id, uint64_t i);
+
+MNW_API int mnw_decode_int_blocks(mnw_ctx *ctx, const uint8_t *data, int64_t data_len,
+                                  const int64_t *offsets, const int64_t *mins, const int64_t *bits,
+                                  int64_t n, int64_t nsel, const int64_t *sel, int64_t *out);
+MNW_API int mnw_decode_float_blocks(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data,
+                                    int64_t data_len, const int64_t *offsets, const int64_t *mins,
+                                    const int64_t *bits, int64_t n, int64_t nsel, const int64_t *sel,
+                                    const mnw_jitter *jitter, float *out);
+
+/* ---- minp: fused sub-cell gather + 3-axis encode --------------------------
+ * Replaces the body of minp.Writer.Vectors (go/minp/minp.go:112-118): for each
+ * axis k and sub-cell sc, getSubCell (:246-264) + floatGroup.writeData.  aos is
+ * the [nfile^3][3]float32 Lagrangian cube of one file; desc[k] are the three
+ * FloatGroups' parameters.  Block (k, sc) is entry k*subcells^3 + sc of
+ * mins/bits/offsets (offsets restart at 0 for every axis = every group);
+ * axis k's bytes are written to out + out_axis_stride*k and its length to
+ * out_len[k].
+ * mnw_decode_vec3_subcells replaces minp.Reader.Vectors (:191-206): decode,
+ * periodic wrap (x<0 -> x+L; x>=L -> x-L when wrap_L > 0), setSubCell (:270-288).
+ * jitter block ids are block_id0 + k*subcells^3 + sc.
+ */
+MNW_API int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos,
+                                     int64_t nfile, int64_t subcells, int64_t *mins, int64_t *bits,
+                                     int64_t *offsets, uint8_t *out, int64_t out_axis_stride,
+                                     int64_t out_len[3]);
+MNW_API int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3],
+                                     const uint8_t *const data[3], const int64_t data_len[3],
+                                     const int64_t *offsets, const int64_t *mins, const int64_t *bits,
+                                     int64_t nfile, int64_t subcells, float wrap_L,
+                                     const mnw_jitter *jitter, float *aos_out);
+
+/* ---- block index ----------------------------------------------------------
+ * Exclusive prefix sum of per-block byte sizes = blockIndex.addBlock +
+ * blockOffset (go/block_index.go:16-35).  HOST pointers.  total gets the sum. */
+MNW_API int mnw_scan_offsets(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base,
+                             int64_t *offsets, int64_t *total);
+
+/* ---- device-resident variants (benchmarks, multi-GPU sharding) -------------
+ * Same semantics; every pointer is a DEVICE pointer except desc/jitter structs
+ * (host) and out_len (device int64).  Enqueued on the context's stream. */
+MNW_API int mnw_encode_int_group_dev(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks,
+                                     int64_t *mins, int64_t *bits, int64_t *offsets,
+                                     uint8_t *out, int64_t out_cap, int64_t *out_len);
+MNW_API int mnw_encode_float_group_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x,
+                                       int64_t n, int64_t nblocks, int64_t *mins, int64_t *bits,
+                                       int64_t *offsets, uint8_t *out, int64_t out_cap,
+                                       int64_t *out_len);
+MNW_API int mnw_decode_int_blocks_dev(mnw_ctx *ctx, const uint8_t *data, int64_t data_len,
+                                      const int64_t *offsets, const int64_t *mins, const int64_t *bits,
+                                      int64_t n, int64_t nsel, const int64_t *sel, int64_t *out);
+MNW_API int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data,
+                                        int64_t data_len, const int64_t *offsets, const int64_t *mins,
+                                        const int64_t *bits, int64_t n, int64_t nsel,
+                                        const int64_t *sel, const mnw_jitter *jitter, float *out);
+/* nfiles cubes back to back in aos (each nfile^3 particles); outputs are
+ * [nfiles][3*subcells^3]; file f / axis k bytes at out + (3*f + k)*out_axis_stride,
+ * lengths in out_len[3*f + k]. */
+MNW_API int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos,
+                                         int64_t nfile, int64_t subcells, int64_t nfiles,
+                                         int64_t *mins, int64_t *bits, int64_t *offsets,
+                                         uint8_t *out, int64_t out_axis_stride, int64_t *out_len);
+MNW_API int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *data,
+                                         int64_t data_axis_stride, const int64_t *offsets,
+                                         const int64_t *mins, const int64_t *bits, int64_t nfile,
+                                         int64_t subcells, int64_t nfiles, float wrap_L,
+                                         const mnw_jitter *jitter, float *aos_out);
+
+/* Which device path the last encode on ctx took: 0 = generic two-pass,
+ * 1 = fused single-read cluster kernel.  For tests and the benchmark. */
+MNW_API int mnw_last_path(const mnw_ctx *ctx);
+/* Force the generic path (testing both paths against the oracle). */
+MNW_API void mnw_force_generic(mnw_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINNOW_CUDA_H */

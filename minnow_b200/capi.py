@@ -1,0 +1,320 @@
+"""ctypes binding of include/minnow_cuda.h (libminnow_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libminnow_b200.so")
+_lib = None
+
+JITTER_CENTER, JITTER_HASH, JITTER_STREAM = 0, 1, 2
+
+
+class MinnowError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("minnow_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class FloatDesc(C.Structure):
+    """mnw_float_desc"""
+    _fields_ = [("low", C.c_float), ("high", C.c_float), ("pixels", C.c_int64), ("periodic", C.c_uint8),
+                ("log10", C.c_uint8), ("clamp", C.c_uint8), ("reserved", C.c_uint8 * 5)]
+
+    @classmethod
+    def make(cls, low, high, pixels, periodic=1, log10=0, clamp=0):
+        d = cls()
+        d.low, d.high, d.pixels = float(low), float(high), int(pixels)
+        d.periodic, d.log10, d.clamp = int(periodic), int(log10), int(clamp)
+        return d
+
+
+class Jitter(C.Structure):
+    """mnw_jitter"""
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("block_id0", C.c_uint64),
+                ("u_stream", C.c_void_p)]
+
+    @classmethod
+    def make(cls, mode=JITTER_CENTER, seed=0, block_id0=0, u_stream=None):
+        j = cls()
+        j.mode, j.seed, j.block_id0 = int(mode), int(seed), int(block_id0)
+        j.u_stream = u_stream
+        return j
+
+
+_p, _i64, _u64, _int, _f32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float
+_FD = C.POINTER(FloatDesc)
+_JT = C.POINTER(Jitter)
+
+# name -> (restype, argtypes); every symbol declared in include/minnow_cuda.h
+SIGNATURES = {
+    "mnw_create": (_int, [_int, C.POINTER(_p)]),
+    "mnw_destroy": (None, [_p]),
+    "mnw_last_error": (C.c_char_p, [_p]),
+    "mnw_sync": (_int, [_p]),
+    "mnw_stream": (_p, [_p]),
+    "mnw_version": (C.c_char_p, []),
+    "mnw_launch_count": (_i64, [_p]),
+    "mnw_precision_needed": (_int, [_u64]),
+    "mnw_array_bytes": (_i64, [_int, _i64]),
+    "mnw_pack": (_int, [_p, _int, _p, _i64, _p]),
+    "mnw_unpack": (_int, [_p, _int, _p, _i64, _p]),
+    "mnw_bits": (_int, [_p, _p, _i64, C.POINTER(_int)]),
+    "mnw_float_group_pixels": (_i64, [_f32, _f32, _f32]),
+    "mnw_encode_int_group": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_encode_float_group": (_int, [_p, _FD, _p, _i64, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_jitter_hash32": (C.c_uint32, [_u64, _u64, _u64]),
+    "mnw_decode_int_blocks": (_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p, _p]),
+    "mnw_decode_float_blocks": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _p, _JT, _p]),
+    "mnw_encode_vec3_subcells": (_int, [_p, _FD, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
+    "mnw_decode_vec3_subcells": (_int, [_p, _FD, _p, _p, _p, _p, _p, _i64, _i64, _f32, _JT, _p]),
+    "mnw_scan_offsets": (_int, [_p, _p, _i64, _i64, _p, C.POINTER(_i64)]),
+    "mnw_encode_int_group_dev": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
+    "mnw_encode_float_group_dev": (_int, [_p, _FD, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
+    "mnw_decode_int_blocks_dev": (_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p, _p]),
+    "mnw_decode_float_blocks_dev": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _p, _JT, _p]),
+    "mnw_encode_vec3_subcells_dev": (_int, [_p, _FD, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
+    "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
+    "mnw_last_path": (_int, [_p]),
+    "mnw_force_generic": (None, [_p, _int]),
+}
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Loads libminnow_b200.so.  Fails loudly when it has not been built: there
+    is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). minnow_b200 has no CPU fallback." % _LIB_PATH)
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(lib, name)
+            f.restype, f.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def precision_needed(mx):
+    r = load_library().mnw_precision_needed(int(mx) & 0xFFFFFFFFFFFFFFFF)
+    if r < 0:
+        raise MinnowError(r, "bit.PrecisionNeeded is undefined for 2^64-1")
+    return r
+
+
+def array_bytes(bits, n):
+    return int(load_library().mnw_array_bytes(bits, n))
+
+
+def float_group_pixels(lo, hi, dx):
+    return int(load_library().mnw_float_group_pixels(lo, hi, dx))
+
+
+def jitter_hash32(seed, block, i):
+    return int(load_library().mnw_jitter_hash32(seed, block, i))
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(_p)
+    if hasattr(a, "data_ptr"):      # torch tensor (device or pinned host)
+        return _p(a.data_ptr())
+    return _p(int(a))
+
+
+class Context:
+    """One mnw_ctx: a CUDA stream plus grow-only scratch.  Not thread-safe,
+    like a minnow.Writer (go/writer.go) -- use one per thread."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _p()
+        rc = self.lib.mnw_create(device, C.byref(h))
+        if rc:
+            raise MinnowError(rc, self.lib.mnw_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mnw_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise MinnowError(rc, self.lib.mnw_last_error(self.h).decode())
+
+    def sync(self):
+        self._check(self.lib.mnw_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.mnw_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mnw_launch_count(self.h))
+
+    @property
+    def last_path(self):
+        return int(self.lib.mnw_last_path(self.h))
+
+    def force_generic(self, on=True):
+        self.lib.mnw_force_generic(self.h, int(on))
+
+    # ---- package bit ---------------------------------------------------------
+    def pack(self, bits, x):
+        """bit.BufferedArray / NewArray (go/bit/bit.go:84-142)"""
+        x = _np(x, np.uint64)
+        out = np.zeros(array_bytes(bits, len(x)) if 1 <= bits <= 64 else 0, np.uint8)
+        self._check(self.lib.mnw_pack(self.h, bits, _ptr(x), len(x), _ptr(out)))
+        return out
+
+    def unpack(self, bits, data, n):
+        """(*Array).Slice (go/bit/bit.go:29-82)"""
+        data = _np(data, np.uint8)
+        out = np.zeros(n, np.uint64)
+        self._check(self.lib.mnw_unpack(self.h, bits, _ptr(data), n, _ptr(out)))
+        return out
+
+    def bits(self, x):
+        """ArrayBuffer.Bits (go/bit/bit.go:151-159)"""
+        x = _np(x, np.uint64)
+        b = _int()
+        self._check(self.lib.mnw_bits(self.h, _ptr(x), len(x), C.byref(b)))
+        return b.value
+
+    # ---- groups, host buffers --------------------------------------------------
+    def _encode_group(self, fn, pre, x, esz, n, nblocks, starts):
+        total = len(x)
+        mins, bits, offs = (np.zeros(nblocks, np.int64) for _ in range(3))
+        out = np.zeros(8 * total + 8, np.uint8)
+        ln = _i64()
+        st = _np(starts, np.int64) if starts is not None else None
+        self._check(fn(self.h, *pre, _ptr(x), n, nblocks, _ptr(st), _ptr(mins), _ptr(bits), _ptr(offs),
+                       _ptr(out), len(out), C.byref(ln)))
+        return mins, bits, offs, out[:ln.value].copy()
+
+    def encode_int_group(self, x, n=None, nblocks=None, starts=None):
+        """nblocks x intGroup.writeData (go/group.go:242-255) -> (mins, bits, offsets, bytes)"""
+        x = _np(x, np.int64).reshape(-1)
+        if starts is not None:
+            nblocks, n = len(starts) - 1, 0
+        return self._encode_group(self.lib.mnw_encode_int_group, (), x, 8, n, nblocks, starts)
+
+    def encode_float_group(self, desc, x, n=None, nblocks=None, starts=None):
+        """nblocks x floatGroup.writeData (go/group.go:312-327)"""
+        x = _np(x, np.float32).reshape(-1)
+        if starts is not None:
+            nblocks, n = len(starts) - 1, 0
+        return self._encode_group(self.lib.mnw_encode_float_group, (C.byref(desc),), x, 4, n, nblocks, starts)
+
+    def decode_int_blocks(self, data, offsets, mins, bits, n, sel=None):
+        """intGroup.readData per selected block (go/group.go:257-263)"""
+        data = _np(data, np.uint8)
+        offsets, mins, bits = _np(offsets, np.int64), _np(mins, np.int64), _np(bits, np.int64)
+        s = _np(sel, np.int64) if sel is not None else None
+        nsel = len(s) if s is not None else len(offsets)
+        out = np.zeros((nsel, n), np.int64)
+        self._check(self.lib.mnw_decode_int_blocks(self.h, _ptr(data), len(data), _ptr(offsets), _ptr(mins),
+                                                   _ptr(bits), n, nsel, _ptr(s), _ptr(out)))
+        return out
+
+    def decode_float_blocks(self, desc, data, offsets, mins, bits, n, sel=None, jitter=None, u=None):
+        """floatGroup.readData per selected block (go/group.go:299-310)"""
+        data = _np(data, np.uint8)
+        offsets, mins, bits = _np(offsets, np.int64), _np(mins, np.int64), _np(bits, np.int64)
+        s = _np(sel, np.int64) if sel is not None else None
+        nsel = len(s) if s is not None else len(offsets)
+        out = np.zeros((nsel, n), np.float32)
+        jit = jitter if jitter is not None else Jitter.make()
+        if u is not None:
+            u = _np(u, np.float64)
+            jit = Jitter.make(JITTER_STREAM, u_stream=u.ctypes.data)
+        self._check(self.lib.mnw_decode_float_blocks(self.h, C.byref(desc), _ptr(data), len(data), _ptr(offsets),
+                                                     _ptr(mins), _ptr(bits), n, nsel, _ptr(s), C.byref(jit),
+                                                     _ptr(out)))
+        return out
+
+    def scan_offsets(self, nbytes, base=0):
+        """blockIndex.addBlock / blockOffset (go/block_index.go:16-35)"""
+        nbytes = _np(nbytes, np.int64)
+        out = np.zeros(len(nbytes), np.int64)
+        tot = _i64()
+        self._check(self.lib.mnw_scan_offsets(self.h, _ptr(nbytes), len(nbytes), base, _ptr(out), C.byref(tot)))
+        return out, tot.value
+
+    # ---- minp ---------------------------------------------------------------------
+    def encode_vec3_subcells(self, descs, aos, nfile, subcells):
+        """body of minp.Writer.Vectors (go/minp/minp.go:112-118).
+        -> (mins, bits, offsets) each [3*subcells^3], [bytes_x, bytes_y, bytes_z]"""
+        aos = _np(aos, np.float32).reshape(-1)
+        assert len(aos) == 3 * nfile ** 3
+        nb = 3 * subcells ** 3
+        mins, bits, offs = (np.zeros(nb, np.int64) for _ in range(3))
+        stride = 8 * nfile ** 3 + 8
+        out = np.zeros(3 * stride, np.uint8)
+        lens = np.zeros(3, np.int64)
+        d3 = (FloatDesc * 3)(*descs)
+        self._check(self.lib.mnw_encode_vec3_subcells(self.h, d3, _ptr(aos), nfile, subcells, _ptr(mins),
+                                                      _ptr(bits), _ptr(offs), _ptr(out), stride, _ptr(lens)))
+        return mins, bits, offs, [out[k * stride:k * stride + lens[k]].copy() for k in range(3)]
+
+    def decode_vec3_subcells(self, descs, data3, offsets, mins, bits, nfile, subcells, wrap_L=0.0, jitter=None):
+        """body of minp.Reader.Vectors (go/minp/minp.go:191-206) -> [nfile^3, 3] float32"""
+        data3 = [_np(d, np.uint8) for d in data3]
+        ptrs = (C.c_void_p * 3)(*[d.ctypes.data for d in data3])
+        lens = np.array([len(d) for d in data3], np.int64)
+        offsets, mins, bits = _np(offsets, np.int64), _np(mins, np.int64), _np(bits, np.int64)
+        out = np.zeros((nfile ** 3, 3), np.float32)
+        d3 = (FloatDesc * 3)(*descs)
+        jit = jitter if jitter is not None else Jitter.make()
+        self._check(self.lib.mnw_decode_vec3_subcells(self.h, d3, ptrs, _ptr(lens), _ptr(offsets), _ptr(mins),
+                                                      _ptr(bits), nfile, subcells, wrap_L, C.byref(jit), _ptr(out)))
+        return out
+
+    # ---- device-resident variants (torch tensors or raw device addresses) ------------
+    def encode_float_group_dev(self, desc, x, n, nblocks, mins, bits, offsets, out, out_cap, out_len):
+        self._check(self.lib.mnw_encode_float_group_dev(self.h, C.byref(desc), _ptr(x), n, nblocks, _ptr(mins),
+                                                        _ptr(bits), _ptr(offsets), _ptr(out), out_cap, _ptr(out_len)))
+
+    def encode_int_group_dev(self, x, n, nblocks, mins, bits, offsets, out, out_cap, out_len):
+        self._check(self.lib.mnw_encode_int_group_dev(self.h, _ptr(x), n, nblocks, _ptr(mins), _ptr(bits),
+                                                      _ptr(offsets), _ptr(out), out_cap, _ptr(out_len)))
+
+    def decode_float_blocks_dev(self, desc, data, data_len, offsets, mins, bits, n, nsel, sel, jitter, out):
+        self._check(self.lib.mnw_decode_float_blocks_dev(self.h, C.byref(desc), _ptr(data), data_len, _ptr(offsets),
+                                                         _ptr(mins), _ptr(bits), n, nsel, _ptr(sel),
+                                                         C.byref(jitter), _ptr(out)))
+
+    def decode_int_blocks_dev(self, data, data_len, offsets, mins, bits, n, nsel, sel, out):
+        self._check(self.lib.mnw_decode_int_blocks_dev(self.h, _ptr(data), data_len, _ptr(offsets), _ptr(mins),
+                                                       _ptr(bits), n, nsel, _ptr(sel), _ptr(out)))
+
+    def encode_vec3_subcells_dev(self, descs, aos, nfile, subcells, nfiles, mins, bits, offsets, out,
+                                 out_axis_stride, out_len):
+        d3 = (FloatDesc * 3)(*descs)
+        self._check(self.lib.mnw_encode_vec3_subcells_dev(self.h, d3, _ptr(aos), nfile, subcells, nfiles,
+                                                          _ptr(mins), _ptr(bits), _ptr(offsets), _ptr(out),
+                                                          out_axis_stride, _ptr(out_len)))
+
+    def decode_vec3_subcells_dev(self, descs, data, data_axis_stride, offsets, mins, bits, nfile, subcells,
+                                 nfiles, wrap_L, jitter, aos_out):
+        d3 = (FloatDesc * 3)(*descs)
+        self._check(self.lib.mnw_decode_vec3_subcells_dev(self.h, d3, _ptr(data), data_axis_stride, _ptr(offsets),
+                                                          _ptr(mins), _ptr(bits), nfile, subcells, nfiles, wrap_L,
+                                                          C.byref(jitter), _ptr(aos_out)))

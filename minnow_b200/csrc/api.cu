@@ -1,0 +1,632 @@
+// api.cu -- the C ABI of libminnow_b200 (include/minnow_cuda.h): context,
+// device scratch management, host<->device staging, and dispatch to the
+// kernels.  There is no CPU implementation of the hot path in this library.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/minnow_cuda.h"
+#include "device_math.cuh"
+#include "engine.cuh"
+#include "launch.cuh"
+#include "fused.cuh"
+
+using namespace mnw;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {  // retry with the exact size
+            (void)cudaGetLastError();
+            want = n;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct mnw_ctx {
+    int device = 0;
+    Launcher L;
+    std::string err;
+    int last_path = 0;
+    int force_generic = 0;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws;
+    int *h_flags = nullptr;  // pinned: [slow_count, err]
+};
+
+namespace {
+
+int fail(mnw_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return fail(ctx, MNW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));   \
+    } while (0)
+
+int check_desc(mnw_ctx *ctx, const mnw_float_desc *d) {
+    if (!d) return fail(ctx, MNW_ERR_ARG, "float group descriptor is NULL");
+    // pixels <= 0 (e.g. minp's non-periodic limits of a single particle, go/minp/minp.go:92-95)
+    // is degenerate in the reference too; it is carried through the exact path unchanged.
+    return MNW_OK;
+}
+
+FloatParamsHost to_params(const mnw_float_desc &d) {
+    FloatParamsHost p;
+    p.low = d.low; p.high = d.high; p.pixels = d.pixels;
+    volatile float span = d.high - d.low;           // go/group.go:316, float32 arithmetic
+    p.dx = span / (float)d.pixels;
+    p.hi_clamp = nextafterf(d.high, -INFINITY);      // go/minh/minh.go:146
+    p.flags = (d.periodic ? F_PERIODIC : 0) | (d.log10 ? F_LOG10 : 0) | (d.clamp ? F_CLAMP : 0);
+    return p;
+}
+
+// Reserve the per-batch device records.
+int reserve_batch(mnw_ctx *ctx, int64_t nb, int64_t nchains) {
+    CU(ctx->descs.reserve(sizeof(BlockDesc) * (size_t)(nb + 1)));
+    CU(ctx->stats.reserve(sizeof(BlockStat) * (size_t)(nb + 1)));
+    CU(ctx->slow.reserve(sizeof(int64_t) * (size_t)(nb + 1)));
+    CU(ctx->flags.reserve(64));
+    CU(ctx->meta.reserve(sizeof(int64_t) * (size_t)(3 * nb + nchains + 4)));
+    return MNW_OK;
+}
+
+// After the stream has drained: surface device-side error flags.
+int check_flags(mnw_ctx *ctx) {
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    if (ctx->h_flags[1] == 1)
+        return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
+    if (ctx->h_flags[1] == 2)
+        return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
+    return MNW_OK;
+}
+
+// Device-resident group encode.  x/out/mins/bits/offsets/out_len are device
+// pointers (mins.. may be null).  Chooses the fused path when it applies.
+int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *x, int64_t n,
+                     int64_t nblocks, const int64_t *d_starts, const int64_t *d_tile0, const int64_t *d_chunk0,
+                     int64_t total_tiles, int64_t total_chunks, int64_t *mins, int64_t *bits, int64_t *offsets,
+                     uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
+    FloatParamsHost fp;
+    if (kind == KIND_F32) {
+        int rc = check_desc(ctx, desc);
+        if (rc) return rc;
+        fp = to_params(*desc);
+    }
+    int rc = reserve_batch(ctx, nblocks, 1);
+    if (rc) return rc;
+    int *d_flags = ctx->flags.as<int>();
+    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    if (nblocks == 0) {
+        if (out_len) CU(cudaMemsetAsync(out_len, 0, 8, ctx->L.stream));
+        return MNW_OK;
+    }
+    BatchShape sh = {};
+    sh.nblocks = nblocks; sh.nchains = 1; sh.blocks_per_chain = nblocks;
+    sh.uniform_n = d_starts ? 0 : n;
+    if (d_starts) {
+        sh.total_tiles = total_tiles; sh.total_chunks = total_chunks;
+    } else {
+        sh.total_tiles = nblocks * ((n + PACK_TILE - 1) / PACK_TILE);
+        sh.total_chunks = nblocks * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
+    }
+    if (sh.total_tiles >= (1LL << 31) || sh.total_chunks >= (1LL << 31))
+        return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
+
+    if (!ctx->force_generic && kind == KIND_F32 && !d_starts &&
+        fused_group_supported(fp, n, nblocks)) {
+        ctx->last_path = 1;
+        cudaError_t e = launch_fused_group(ctx->L, ctx->fused_ws.p, ctx->fused_ws.cap, fp, (const float *)x, n, nblocks,
+                                           mins, bits, offsets, out_len, out, out_cap, d_flags);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused group encode: %s", cudaGetErrorString(e));
+        return MNW_OK;
+    }
+    ctx->last_path = 0;
+    launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks);
+    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                          ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
+                          0, out_cap);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+// Host-pointer group encode: stage in, run, stage out.
+int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *x, int64_t n,
+                      int64_t nblocks, const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets,
+                      uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
+    const size_t esz = kind == KIND_I64 ? 8 : 4;
+    int64_t total = starts ? starts[nblocks] - starts[0] : n * nblocks;
+    if (starts && starts[0] != 0) return fail(ctx, MNW_ERR_ARG, "starts[0] must be 0");
+    CU(ctx->in.reserve(esz * (size_t)total + 16));
+    CU(ctx->out.reserve(8 * (size_t)total + 64));
+    int rc = reserve_batch(ctx, nblocks, 1);
+    if (rc) return rc;
+    if (total > 0) CU(cudaMemcpyAsync(ctx->in.p, x, esz * (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
+
+    const int64_t *d_starts = nullptr, *d_tile0 = nullptr, *d_chunk0 = nullptr;
+    int64_t total_tiles = 0, total_chunks = 0;
+    std::vector<int64_t> h_aux;
+    if (starts) {
+        h_aux.resize(3 * (size_t)(nblocks + 1));
+        int64_t *hs = h_aux.data(), *ht = hs + nblocks + 1, *hc = ht + nblocks + 1;
+        for (int64_t b = 0; b <= nblocks; b++) hs[b] = starts[b];
+        for (int64_t b = 0; b < nblocks; b++) {
+            int64_t nb = starts[b + 1] - starts[b];
+            if (nb < 0) return fail(ctx, MNW_ERR_ARG, "starts must be non-decreasing");
+            ht[b] = total_tiles; hc[b] = total_chunks;
+            total_tiles += (nb + PACK_TILE - 1) / PACK_TILE;
+            total_chunks += (nb + STATS_CHUNK - 1) / STATS_CHUNK;
+        }
+        ht[nblocks] = total_tiles; hc[nblocks] = total_chunks;
+        CU(ctx->aux.reserve(h_aux.size() * 8));
+        CU(cudaMemcpyAsync(ctx->aux.p, h_aux.data(), h_aux.size() * 8, cudaMemcpyHostToDevice, ctx->L.stream));
+        d_starts = ctx->aux.as<int64_t>();
+        d_tile0 = d_starts + nblocks + 1;
+        d_chunk0 = d_tile0 + nblocks + 1;
+    }
+    int64_t *d_meta = ctx->meta.as<int64_t>();
+    int64_t *d_mins = d_meta, *d_bits = d_meta + nblocks, *d_offs = d_meta + 2 * nblocks, *d_len = d_meta + 3 * nblocks;
+    rc = encode_group_dev(ctx, kind, desc, ctx->in.p, n, nblocks, d_starts, d_tile0, d_chunk0, total_tiles,
+                          total_chunks, d_mins, d_bits, d_offs, ctx->out.as<uint8_t>(), (int64_t)ctx->out.cap, d_len);
+    if (rc) return rc;
+    std::vector<int64_t> h_meta(3 * (size_t)nblocks + 1);
+    CU(cudaMemcpyAsync(h_meta.data(), d_meta, h_meta.size() * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    rc = check_flags(ctx);  // synchronises
+    if (rc) return rc;
+    int64_t len = h_meta[3 * (size_t)nblocks];
+    if (mins) memcpy(mins, h_meta.data(), 8 * (size_t)nblocks);
+    if (bits) memcpy(bits, h_meta.data() + nblocks, 8 * (size_t)nblocks);
+    if (offsets) memcpy(offsets, h_meta.data() + 2 * nblocks, 8 * (size_t)nblocks);
+    if (out_len) *out_len = len;
+    if (len > out_cap) return fail(ctx, MNW_ERR_CAPACITY, "group needs %lld bytes, buffer has %lld", (long long)len, (long long)out_cap);
+    if (len > 0) {
+        CU(cudaMemcpyAsync(out, ctx->out.p, (size_t)len, cudaMemcpyDeviceToHost, ctx->L.stream));
+        CU(cudaStreamSynchronize(ctx->L.stream));
+    }
+    return MNW_OK;
+}
+
+int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, int naxes, const mnw_jitter *jitter) {
+    for (int k = 0; k < naxes; k++) {
+        int rc = check_desc(ctx, &desc[k]);
+        if (rc) return rc;
+        FloatParamsHost p = to_params(desc[k]);
+        h.low[k] = p.low; h.dx[k] = p.dx; h.pixels[k] = p.pixels; h.periodic[k] = desc[k].periodic ? 1 : 0;
+    }
+    if (jitter) {
+        if (jitter->mode < 0 || jitter->mode > 2) return fail(ctx, MNW_ERR_ARG, "unknown jitter mode %d", jitter->mode);
+        h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0;
+    }
+    return MNW_OK;
+}
+
+// Host-pointer group decode (int or float).
+int decode_blocks_host(mnw_ctx *ctx, int mode, const mnw_float_desc *desc, const uint8_t *data, int64_t data_len,
+                       const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n, int64_t nsel,
+                       const int64_t *sel, const mnw_jitter *jitter, void *out) {
+    if (n < 0 || nsel < 0 || data_len < 0) return fail(ctx, MNW_ERR_ARG, "negative length");
+    if (nsel == 0 || n == 0) return MNW_OK;
+    DecodeHost h;
+    h.mode = mode;
+    if (mode == 1) {
+        int rc = fill_decode_float(ctx, h, desc, 1, jitter);
+        if (rc) return rc;
+    }
+    // Upload only the bytes of the selected blocks, compacted back to back.
+    std::vector<int64_t> m(3 * (size_t)nsel);
+    int64_t *c_off = m.data(), *c_min = c_off + nsel, *c_bits = c_min + nsel;
+    int64_t total = 0;
+    for (int64_t j = 0; j < nsel; j++) {
+        int64_t b = sel ? sel[j] : j;
+        if (b < 0) return fail(ctx, MNW_ERR_ARG, "negative block id");
+        if (bits[b] < 0 || bits[b] > 64) return fail(ctx, MNW_ERR_FORMAT, "block %lld has %lld bits", (long long)b, (long long)bits[b]);
+        int64_t nb = array_bytes(bits[b], n);
+        if (offsets[b] < 0 || offsets[b] + nb > data_len)
+            return fail(ctx, MNW_ERR_FORMAT, "block %lld lies outside the group's data", (long long)b);
+        c_off[j] = total; c_min[j] = mins[b]; c_bits[j] = bits[b];
+        total += nb;
+    }
+    CU(ctx->in.reserve((size_t)total + 16));
+    bool contiguous = true;
+    for (int64_t j = 0; j + 1 < nsel && contiguous; j++) {
+        int64_t b = sel ? sel[j] : j, b2 = sel ? sel[j + 1] : j + 1;
+        contiguous = offsets[b] + (c_off[j + 1] - c_off[j]) == offsets[b2];
+    }
+    if (contiguous) {
+        int64_t b = sel ? sel[0] : 0;
+        if (total > 0) CU(cudaMemcpyAsync(ctx->in.p, data + offsets[b], (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
+    } else {
+        for (int64_t j = 0; j < nsel; j++) {
+            int64_t nb = (j + 1 < nsel ? c_off[j + 1] : total) - c_off[j];
+            int64_t b = sel ? sel[j] : j;
+            if (nb > 0) CU(cudaMemcpyAsync(ctx->in.as<uint8_t>() + c_off[j], data + offsets[b], (size_t)nb,
+                                           cudaMemcpyHostToDevice, ctx->L.stream));
+        }
+    }
+    CU(ctx->meta.reserve(m.size() * 8));
+    CU(cudaMemcpyAsync(ctx->meta.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice, ctx->L.stream));
+    const size_t osz = mode == 0 ? 8 : 4;
+    CU(ctx->dec_out.reserve(osz * (size_t)(n * nsel)));
+    if (mode == 1 && h.jmode == 2) {
+        if (!jitter->u_stream) return fail(ctx, MNW_ERR_ARG, "jitter mode STREAM without u_stream");
+        CU(ctx->ustream.reserve(8 * (size_t)(n * nsel)));
+        CU(cudaMemcpyAsync(ctx->ustream.p, jitter->u_stream, 8 * (size_t)(n * nsel), cudaMemcpyHostToDevice, ctx->L.stream));
+        h.u = ctx->ustream.as<double>();
+    }
+    // jitter block ids must stay those of the ORIGINAL blocks: pass them through sel
+    // as a device array of original ids when a hash jitter is asked for.
+    h.data = ctx->in.as<uint8_t>();
+    h.stream_len = total;
+    h.offsets = ctx->meta.as<int64_t>();
+    h.mins = h.offsets + nsel;
+    h.bits = h.mins + nsel;
+    h.n = n; h.nsel = nsel; h.out = ctx->dec_out.p;
+    if (mode == 1 && h.jmode == 1 && sel) {
+        CU(ctx->aux.reserve(8 * (size_t)nsel));
+        CU(cudaMemcpyAsync(ctx->aux.p, sel, 8 * (size_t)nsel, cudaMemcpyHostToDevice, ctx->L.stream));
+        h.jitter_ids = ctx->aux.as<int64_t>();
+    }
+    launch_decode(ctx->L, h);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->dec_out.p, osz * (size_t)(n * nsel), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exported entry points
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *mnw_version(void) { return "minnow_b200 0.1 (sm_100a)"; }
+
+int mnw_create(int device, mnw_ctx **out) {
+    mnw_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, MNW_ERR_ARG, "mnw_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, MNW_ERR_CUDA, "mnw_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(nullptr, MNW_ERR_ARG, "mnw_create: device %d of %d", device, count);
+    CU(cudaSetDevice(device));
+    ctx = new mnw_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_flags, 64);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, MNW_ERR_CUDA, "mnw_create: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return MNW_OK;
+}
+
+void mnw_destroy(mnw_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->L.stream);
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws})
+        b->release();
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    cudaStreamDestroy(ctx->L.stream);
+    delete ctx;
+}
+
+const char *mnw_last_error(const mnw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mnw_sync(mnw_ctx *ctx) {
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+void *mnw_stream(mnw_ctx *ctx) { return (void *)ctx->L.stream; }
+int64_t mnw_launch_count(const mnw_ctx *ctx) { return ctx->L.count; }
+int mnw_last_path(const mnw_ctx *ctx) { return ctx->last_path; }
+void mnw_force_generic(mnw_ctx *ctx, int on) { ctx->force_generic = on; }
+
+int mnw_precision_needed(uint64_t max) {
+    int b = precision_needed(max);
+    return b < 0 ? MNW_ERR_ARG : b;
+}
+int64_t mnw_array_bytes(int bits, int64_t n) { return array_bytes(bits, n); }
+int64_t mnw_float_group_pixels(float lo, float hi, float dx) {
+    volatile float span = hi - lo;
+    volatile float r = span / dx;
+    double c = ceil((double)r);
+    if (!(c >= -9223372036854775808.0 && c < 9223372036854775808.0)) return INT64_MIN;
+    return (int64_t)c;
+}
+uint32_t mnw_jitter_hash32(uint64_t seed, uint64_t block_id, uint64_t i) { return jitter_hash32(seed, block_id, i); }
+
+int mnw_pack(mnw_ctx *ctx, int bits, const uint64_t *x, int64_t n, uint8_t *out) {
+    if (bits > 64) return fail(ctx, MNW_ERR_ARG, "Cannot pack more than 64 bits per element into a bit.Array");
+    if (bits < 1 || n < 0) return fail(ctx, MNW_ERR_ARG, "mnw_pack: bits = %d, n = %lld", bits, (long long)n);
+    if (n == 0) return MNW_OK;
+    int64_t nb = array_bytes(bits, n);
+    CU(ctx->in.reserve(8 * (size_t)n));
+    CU(ctx->out.reserve((size_t)nb + 64));
+    int rc = reserve_batch(ctx, 1, 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->in.p, x, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_raw_pack(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), ctx->in.p, n, bits, ctx->out.as<uint8_t>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->out.p, (size_t)nb, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+int mnw_unpack(mnw_ctx *ctx, int bits, const uint8_t *in, int64_t n, uint64_t *out) {
+    if (bits < 1 || bits > 64 || n < 0) return fail(ctx, MNW_ERR_ARG, "mnw_unpack: bits = %d, n = %lld", bits, (long long)n);
+    int64_t off = 0, mn = 0, bt = bits;
+    return decode_blocks_host(ctx, 0, nullptr, in, array_bytes(bits, n), &off, &mn, &bt, n, 1, nullptr, nullptr, out);
+}
+
+int mnw_bits(mnw_ctx *ctx, const uint64_t *x, int64_t n, int *bits) {
+    if (n < 0 || !bits) return fail(ctx, MNW_ERR_ARG, "mnw_bits: bad argument");
+    if (n == 0) { *bits = 0; return MNW_OK; }
+    CU(ctx->in.reserve(8 * (size_t)n));
+    CU(ctx->meta.reserve(64));
+    CU(cudaMemcpyAsync(ctx->in.p, x, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_umax(ctx->L, ctx->in.as<unsigned long long>(), n, ctx->meta.as<unsigned long long>());
+    CU(cudaGetLastError());
+    unsigned long long mx = 0;
+    CU(cudaMemcpyAsync(&mx, ctx->meta.p, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    int b = precision_needed(mx);
+    if (b < 0) return fail(ctx, MNW_ERR_ARG, "bit.PrecisionNeeded is undefined for 2^64-1");
+    *bits = b;
+    return MNW_OK;
+}
+
+int mnw_encode_int_group(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks, const int64_t *starts,
+                         int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap,
+                         int64_t *out_len) {
+    return encode_group_host(ctx, KIND_I64, nullptr, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x, int64_t n, int64_t nblocks,
+                           const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                           int64_t out_cap, int64_t *out_len) {
+    int rc = check_desc(ctx, desc);
+    if (rc) return rc;
+    return encode_group_host(ctx, KIND_F32, desc, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_decode_int_blocks(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,
+                          const int64_t *mins, const int64_t *bits, int64_t n, int64_t nsel, const int64_t *sel,
+                          int64_t *out) {
+    return decode_blocks_host(ctx, 0, nullptr, data, data_len, offsets, mins, bits, n, nsel, sel, nullptr, out);
+}
+
+int mnw_decode_float_blocks(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data, int64_t data_len,
+                            const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n,
+                            int64_t nsel, const int64_t *sel, const mnw_jitter *jitter, float *out) {
+    return decode_blocks_host(ctx, 1, desc, data, data_len, offsets, mins, bits, n, nsel, sel, jitter, out);
+}
+
+int mnw_scan_offsets(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base, int64_t *offsets,
+                     int64_t *total) {
+    if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
+    cudaError_t e = cudaSuccess;
+    CU(ctx->meta.reserve(8 * (size_t)(2 * nblocks + 2)));
+    int64_t *d_sizes = ctx->meta.as<int64_t>(), *d_off = d_sizes + nblocks, *d_total = d_off + nblocks;
+    if (nblocks) CU(cudaMemcpyAsync(d_sizes, nbytes, 8 * (size_t)nblocks, cudaMemcpyHostToDevice, ctx->L.stream));
+    e = launch_scan_sizes(ctx->L, d_sizes, nblocks, base, d_off, d_total);
+    if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
+    if (nblocks) CU(cudaMemcpyAsync(offsets, d_off, 8 * (size_t)nblocks, cudaMemcpyDeviceToHost, ctx->L.stream));
+    int64_t t = 0;
+    CU(cudaMemcpyAsync(&t, d_total, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    if (total) *total = t;
+    return MNW_OK;
+}
+
+// ---- device-resident variants ------------------------------------------------
+int mnw_encode_int_group_dev(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks, int64_t *mins,
+                             int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    return encode_group_dev(ctx, KIND_I64, nullptr, x, n, nblocks, nullptr, nullptr, nullptr, 0, 0, mins, bits,
+                            offsets, out, out_cap, out_len);
+}
+
+int mnw_encode_float_group_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x, int64_t n,
+                               int64_t nblocks, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                               int64_t out_cap, int64_t *out_len) {
+    return encode_group_dev(ctx, KIND_F32, desc, x, n, nblocks, nullptr, nullptr, nullptr, 0, 0, mins, bits,
+                            offsets, out, out_cap, out_len);
+}
+
+int mnw_decode_int_blocks_dev(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,
+                              const int64_t *mins, const int64_t *bits, int64_t n, int64_t nsel,
+                              const int64_t *sel, int64_t *out) {
+    DecodeHost h;
+    h.mode = 0; h.data = data; h.stream_len = data_len; h.offsets = offsets; h.mins = mins; h.bits = bits;
+    h.sel = sel; h.n = n; h.nsel = nsel; h.out = out;
+    launch_decode(ctx->L, h);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data, int64_t data_len,
+                                const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n,
+                                int64_t nsel, const int64_t *sel, const mnw_jitter *jitter, float *out) {
+    DecodeHost h;
+    h.mode = 1;
+    int rc = fill_decode_float(ctx, h, desc, 1, jitter);
+    if (rc) return rc;
+    if (h.jmode == 2) h.u = jitter->u_stream;  // device pointer here
+    h.data = data; h.stream_len = data_len; h.offsets = offsets; h.mins = mins; h.bits = bits;
+    h.sel = sel; h.n = n; h.nsel = nsel; h.out = out;
+    launch_decode(ctx->L, h);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
+                                 int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
+                                 int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0 || nfile > 2048)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    FloatParamsHost fp[3];
+    for (int k = 0; k < 3; k++) {
+        int rc = check_desc(ctx, &desc[k]);
+        if (rc) return rc;
+        fp[k] = to_params(desc[k]);
+    }
+    const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells, n = nsub * nsub * nsub;
+    const int64_t nb = nfiles * 3 * sc3;
+    int rc = reserve_batch(ctx, nb, 3 * nfiles);
+    if (rc) return rc;
+    int *d_flags = ctx->flags.as<int>();
+    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    if (nb == 0) return MNW_OK;
+
+    if (!ctx->force_generic && fused_vec3_supported(fp, (int)nfile, (int)subcells)) {
+        ctx->last_path = 1;
+        cudaError_t e = launch_fused_vec3(ctx->L, fp, aos, (int)nfile, (int)subcells, nfiles, mins, bits, offsets,
+                                          out_len, out, out_axis_stride, d_flags);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
+        return MNW_OK;
+    }
+    ctx->last_path = 0;
+    BatchShape sh = {};
+    sh.nblocks = nb; sh.nchains = 3 * nfiles; sh.blocks_per_chain = sc3; sh.uniform_n = n;
+    sh.total_tiles = nb * ((n + PACK_TILE - 1) / PACK_TILE);
+    sh.total_chunks = nb * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
+    if (sh.total_tiles >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
+    launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, fp);
+    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                          ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
+                          out_axis_stride, out_axis_stride);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *data,
+                                 int64_t data_axis_stride, const int64_t *offsets, const int64_t *mins,
+                                 const int64_t *bits, int64_t nfile, int64_t subcells, int64_t nfiles,
+                                 float wrap_L, const mnw_jitter *jitter, float *aos_out) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    DecodeHost h;
+    h.mode = 2;
+    int rc = fill_decode_float(ctx, h, desc, 3, jitter);
+    if (rc) return rc;
+    if (h.jmode == 2) return fail(ctx, MNW_ERR_ARG, "vec3 decode supports jitter modes CENTER and HASH");
+    const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells;
+    h.data = data; h.stream_len = data_axis_stride; h.offsets = offsets; h.mins = mins; h.bits = bits;
+    h.n = nsub * nsub * nsub; h.nsel = nfiles * 3 * sc3; h.wrap_L = wrap_L;
+    h.nfile = (int32_t)nfile; h.subcells = (int32_t)subcells; h.out = aos_out;
+    launch_decode(ctx->L, h);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+// ---- minp host-pointer entry points -------------------------------------------
+int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
+                             int64_t subcells, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                             int64_t out_axis_stride, int64_t out_len[3]) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    const int64_t np = nfile * nfile * nfile, sc3 = subcells * subcells * subcells, nb = 3 * sc3;
+    const int64_t stride = (8 * np + 255) & ~255LL;  // worst case: 64 bits per value
+    CU(ctx->in.reserve(12 * (size_t)np + 16));
+    CU(ctx->out.reserve(3 * (size_t)stride + 64));
+    int rc = reserve_batch(ctx, nb, 3);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));
+    int64_t *d_meta = ctx->meta.as<int64_t>();
+    rc = mnw_encode_vec3_subcells_dev(ctx, desc, ctx->in.as<float>(), nfile, subcells, 1, d_meta, d_meta + nb,
+                                      d_meta + 2 * nb, ctx->out.as<uint8_t>(), stride, d_meta + 3 * nb);
+    if (rc) return rc;
+    std::vector<int64_t> h_meta(3 * (size_t)nb + 3);
+    CU(cudaMemcpyAsync(h_meta.data(), d_meta, h_meta.size() * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    rc = check_flags(ctx);
+    if (rc) return rc;
+    if (mins) memcpy(mins, h_meta.data(), 8 * (size_t)nb);
+    if (bits) memcpy(bits, h_meta.data() + nb, 8 * (size_t)nb);
+    if (offsets) memcpy(offsets, h_meta.data() + 2 * nb, 8 * (size_t)nb);
+    for (int k = 0; k < 3; k++) {
+        int64_t len = h_meta[3 * (size_t)nb + k];
+        out_len[k] = len;
+        if (len > out_axis_stride)
+            return fail(ctx, MNW_ERR_CAPACITY, "axis %d needs %lld bytes, stride is %lld", k, (long long)len, (long long)out_axis_stride);
+        if (len > 0)
+            CU(cudaMemcpyAsync(out + k * out_axis_stride, ctx->out.as<uint8_t>() + k * stride, (size_t)len,
+                               cudaMemcpyDeviceToHost, ctx->L.stream));
+    }
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *const data[3],
+                             const int64_t data_len[3], const int64_t *offsets, const int64_t *mins,
+                             const int64_t *bits, int64_t nfile, int64_t subcells, float wrap_L,
+                             const mnw_jitter *jitter, float *aos_out) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    const int64_t np = nfile * nfile * nfile, sc3 = subcells * subcells * subcells, nb = 3 * sc3;
+    const int64_t nsub = nfile / subcells, n = nsub * nsub * nsub;
+    int64_t stride = 0;
+    for (int k = 0; k < 3; k++) stride = data_len[k] > stride ? data_len[k] : stride;
+    stride = (stride + 255) & ~255LL;
+    for (int64_t b = 0; b < nb; b++) {
+        if (bits[b] < 0 || bits[b] > 64) return fail(ctx, MNW_ERR_FORMAT, "block %lld has %lld bits", (long long)b, (long long)bits[b]);
+        if (offsets[b] < 0 || offsets[b] + array_bytes(bits[b], n) > data_len[b / sc3])
+            return fail(ctx, MNW_ERR_FORMAT, "block %lld lies outside its group's data", (long long)b);
+    }
+    CU(ctx->in.reserve(3 * (size_t)stride + 16));
+    CU(ctx->meta.reserve(8 * 3 * (size_t)nb));
+    CU(ctx->dec_out.reserve(12 * (size_t)np));
+    for (int k = 0; k < 3; k++)
+        if (data_len[k] > 0)
+            CU(cudaMemcpyAsync(ctx->in.as<uint8_t>() + k * stride, data[k], (size_t)data_len[k], cudaMemcpyHostToDevice, ctx->L.stream));
+    int64_t *d_meta = ctx->meta.as<int64_t>();
+    CU(cudaMemcpyAsync(d_meta, offsets, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(cudaMemcpyAsync(d_meta + nb, mins, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
+    CU(cudaMemcpyAsync(d_meta + 2 * nb, bits, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
+    int rc = mnw_decode_vec3_subcells_dev(ctx, desc, ctx->in.as<uint8_t>(), stride, d_meta, d_meta + nb, d_meta + 2 * nb,
+                                          nfile, subcells, 1, wrap_L, jitter, ctx->dec_out.as<float>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(aos_out, ctx->dec_out.p, 12 * (size_t)np, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+}  // extern "C"

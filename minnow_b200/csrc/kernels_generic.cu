@@ -1,0 +1,722 @@
+// kernels_generic.cu -- the generic (any block size, 64-bit capable, gather /
+// sub-cell capable) two-pass device path of libminnow_b200:
+//
+//   k_build_*   build BlockDesc records on the device
+//   k_init      per-block stat init + value of element 0
+//   k_stats     one read of the input: min/max and the order-independent
+//               periodic-arc statistics             (go/group.go:244-248,384-409)
+//   k_finalize  per block: periodicMin closed form, min, bits, nbytes
+//   k_slow      exact sequential periodicMin for blocks holding out-of-range
+//               pixel indices (rare), then min/max of bound()
+//   k_scan      per chain exclusive scan of nbytes   (go/block_index.go:16-35)
+//   k_pack      second read: bound, subtract min, LSB-first bit packing to a
+//               BYTE-aligned offset                  (go/bit/bit.go:84-134)
+//   k_decode    unpack + min + bound + dequantise    (go/bit/bit.go:29-82,
+//                                                     go/group.go:257-263,299-310)
+//
+// The fused single-read cluster kernels live in kernels_fused.cu; this file is
+// the fallback for blocks they do not cover and the int64 path.
+#include "engine.cuh"
+#include "device_math.cuh"
+#include "launch.cuh"
+
+namespace mnw {
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t find_block(const BlockDesc *descs, const BatchShape &sh,
+                                              int64_t unit, int64_t units_per_block, bool tiles) {
+    if (sh.uniform_n > 0) return unit / units_per_block;
+    int64_t lo = 0, hi = sh.nblocks;  // last b with start(b) <= unit
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        int64_t s = tiles ? descs[mid].tile0 : descs[mid].chunk0;
+        if (s <= unit) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// The integer the reference would hold in its int64 scratch for element i of
+// the block, BEFORE periodicMin/bound: the int64 itself, or the pixel index.
+__device__ __forceinline__ long long block_value(const BlockDesc &d, int64_t i) {
+    if (d.kind == KIND_I64) {
+        const long long *p = (const long long *)d.src;
+        return d.access == ACC_GATHER ? p[d.idx[i]] : p[i];
+    }
+    const float *p = (const float *)d.src;
+    float v;
+    if (d.access == ACC_CONTIG) {
+        v = p[i];
+    } else if (d.access == ACC_GATHER) {
+        v = p[d.idx[i]];
+    } else {  // getSubCell index arithmetic, go/minp/minp.go:252-262
+        uint32_t ii = (uint32_t)i, ns = (uint32_t)d.nsub;
+        uint32_t jx = ii % ns, t = ii / ns;
+        uint32_t jy = t % ns, jz = t / ns;
+        int64_t idx = (int64_t)(jx + d.ix0) + (int64_t)(jy + d.iy0) * d.nfile +
+                      (int64_t)(jz + d.iz0) * d.nfile * d.nfile;
+        v = p[3 * idx + d.axis];
+    }
+    v = minh_pre(v, d.flags & F_LOG10, d.flags & F_CLAMP, d.low, d.high, d.hi_clamp);
+    return quantize_exact(v, d.low, d.dx);
+}
+
+__device__ __forceinline__ long long warp_min_ll(long long v) {
+    for (int o = 16; o; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+    for (int o = 16; o; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_ull(unsigned long long v) {
+    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_ull(unsigned long long v) {
+    for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+
+// Rotation constant of the periodic-arc statistic.  With half = P/2 and
+// K = P - half - 1, w(q) = (q - q0 + K) mod P orders pixel indices by their
+// signed periodic distance to q0 (go/group.go:412-420): dist = w - K.
+__device__ __forceinline__ unsigned long long arc_rotation(long long q0, long long P) {
+    long long K = P - P / 2 - 1;
+    long long c = K - q0;
+    if (c < 0) c += P;
+    return (unsigned long long)c;
+}
+
+// ---------------------------------------------------------------------------
+// descriptor builders
+// ---------------------------------------------------------------------------
+struct FloatParams {
+    float low, high, dx, hi_clamp;
+    int64_t pixels;
+    int32_t flags;
+};
+
+__global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
+                               const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
+                               FloatParams fp, int64_t blocks_per_chain) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    BlockDesc d = {};
+    int64_t first = starts ? starts[b] : b * n;
+    int64_t cnt = starts ? starts[b + 1] - starts[b] : n;
+    d.src = kind == KIND_I64 ? (const void *)((const long long *)src + first)
+                             : (const void *)((const float *)src + first);
+    d.n = cnt;
+    d.kind = kind;
+    d.access = ACC_CONTIG;
+    d.flags = fp.flags;
+    d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
+    d.chain = (int32_t)(b / blocks_per_chain);
+    int64_t tpb = (n + PACK_TILE - 1) / PACK_TILE, cpb = (n + STATS_CHUNK - 1) / STATS_CHUNK;
+    d.tile0 = tile0 ? tile0[b] : b * tpb;
+    d.chunk0 = chunk0 ? chunk0[b] : b * cpb;
+    descs[b] = d;
+}
+
+// minp.Writer.Vectors block order: per file f, axis k, sub-cell sc (go/minp/minp.go:112-118)
+__global__ void k_build_vec3(BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
+                             int32_t subcells, FloatParams fx, FloatParams fy, FloatParams fz) {
+    int64_t sc3 = (int64_t)subcells * subcells * subcells;
+    int64_t nb = nfiles * 3 * sc3;
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    int64_t f = b / (3 * sc3);
+    int32_t k = (int32_t)((b / sc3) % 3);
+    int64_t sc = b % sc3;
+    int32_t nsub = nfile / subcells;
+    const FloatParams &fp = k == 0 ? fx : (k == 1 ? fy : fz);
+    BlockDesc d = {};
+    d.src = aos + 3 * f * (int64_t)nfile * nfile * nfile;
+    d.n = (int64_t)nsub * nsub * nsub;
+    d.kind = KIND_F32;
+    d.access = ACC_SUBCELL;
+    d.flags = fp.flags;
+    d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
+    d.chain = (int32_t)(b / sc3);
+    d.nfile = nfile; d.nsub = nsub;
+    d.ix0 = nsub * (int32_t)(sc % subcells);
+    d.iy0 = nsub * (int32_t)((sc / subcells) % subcells);
+    d.iz0 = nsub * (int32_t)(sc / ((int64_t)subcells * subcells));
+    d.axis = k;
+    int64_t tpb = (d.n + PACK_TILE - 1) / PACK_TILE, cpb = (d.n + STATS_CHUNK - 1) / STATS_CHUNK;
+    d.tile0 = b * tpb;
+    d.chunk0 = b * cpb;
+    descs[b] = d;
+}
+
+// ---------------------------------------------------------------------------
+// stats
+// ---------------------------------------------------------------------------
+__global__ void k_init(const BlockDesc *descs, BlockStat *stats, int64_t nb) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    BlockStat s = {};
+    s.wmin = ~0ULL; s.wmax = 0ULL;
+    s.qmin = LLONG_MAX; s.qmax = LLONG_MIN;
+    s.q0 = descs[b].n > 0 ? block_value(descs[b], 0) : 0;
+    stats[b] = s;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+k_stats(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh) {
+    __shared__ long long s_ll[2][STATS_THREADS / 32];
+    __shared__ unsigned long long s_ull[2][STATS_THREADS / 32];
+    __shared__ unsigned int s_oob;
+    int64_t chunk = blockIdx.x;
+    int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
+    int64_t b = find_block(descs, sh, chunk, cpb, false);
+    const BlockDesc d = descs[b];
+    int64_t first = (chunk - d.chunk0) * STATS_CHUNK;
+    int64_t end = first + STATS_CHUNK < d.n ? first + STATS_CHUNK : d.n;
+    const bool periodic = d.kind == KIND_F32 && (d.flags & F_PERIODIC);
+    const long long P = d.pixels;
+    const long long q0 = stats[b].q0;
+    const bool q0_ok = P > 0 && (unsigned long long)q0 < (unsigned long long)P;
+    const unsigned long long C = (periodic && q0_ok) ? arc_rotation(q0, P) : 0ULL;
+    if (threadIdx.x == 0) s_oob = 0;
+
+    unsigned long long wmin = ~0ULL, wmax = 0ULL;
+    long long qmin = LLONG_MAX, qmax = LLONG_MIN;
+    unsigned int oob = 0;
+    for (int64_t i = first + threadIdx.x; i < end; i += STATS_THREADS) {
+        long long q = block_value(d, i);
+        qmin = q < qmin ? q : qmin;
+        qmax = q > qmax ? q : qmax;
+        if (periodic) {
+            if (!q0_ok || (unsigned long long)q >= (unsigned long long)P) {
+                oob = 1;
+            } else {
+                unsigned long long w = (unsigned long long)q + C;
+                if (w >= (unsigned long long)P) w -= (unsigned long long)P;
+                wmin = w < wmin ? w : wmin;
+                wmax = w > wmax ? w : wmax;
+            }
+        }
+    }
+    qmin = warp_min_ll(qmin); qmax = warp_max_ll(qmax);
+    wmin = warp_min_ull(wmin); wmax = warp_max_ull(wmax);
+    oob = __any_sync(0xffffffffu, oob);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) {
+        s_ll[0][w] = qmin; s_ll[1][w] = qmax; s_ull[0][w] = wmin; s_ull[1][w] = wmax;
+        if (oob) atomicOr(&s_oob, 1u);
+    }
+    __syncthreads();
+    if (w == 0) {
+        constexpr int NW = STATS_THREADS / 32;
+        qmin = l < NW ? s_ll[0][l] : LLONG_MAX;
+        qmax = l < NW ? s_ll[1][l] : LLONG_MIN;
+        wmin = l < NW ? s_ull[0][l] : ~0ULL;
+        wmax = l < NW ? s_ull[1][l] : 0ULL;
+        qmin = warp_min_ll(qmin); qmax = warp_max_ll(qmax);
+        wmin = warp_min_ull(wmin); wmax = warp_max_ull(wmax);
+        if (l == 0) {
+            BlockStat *s = &stats[b];
+            atomicMin(&s->qmin, qmin);
+            atomicMax(&s->qmax, qmax);
+            if (periodic) {
+                atomicMin(&s->wmin, wmin);
+                atomicMax(&s->wmax, wmax);
+                if (s_oob || !q0_ok) atomicOr(&s->oob, 1u);
+            }
+        }
+    }
+}
+
+// bits / nbytes from (min, max offset); flags an error where Go is undefined.
+__device__ __forceinline__ void finish_stat(BlockStat &s, int64_t n, unsigned long long maxoff, int *err) {
+    int bits = precision_needed(maxoff);
+    if (bits < 0) { bits = 64; atomicExch(err, 1); }
+    s.bits = bits;
+    s.nbytes = array_bytes(bits, n);
+}
+
+__global__ void k_finalize(const BlockDesc *descs, BlockStat *stats, int64_t nb, int64_t *slow_list,
+                           int *slow_count, int *err) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const BlockDesc &d = descs[b];
+    BlockStat s = stats[b];
+    s.do_bound = 0; s.slow = 0; s.pmin = 0; s.out_off = 0;
+    if (d.n == 0) {  // int64Min / Bits / periodicMin of an empty slice are all 0
+        s.min = 0; s.bits = 0; s.nbytes = 0;
+    } else if (d.kind == KIND_I64 || !(d.flags & F_PERIODIC)) {
+        s.min = s.qmin;
+        finish_stat(s, d.n, (unsigned long long)s.qmax - (unsigned long long)s.qmin, err);
+    } else if (s.oob) {
+        s.slow = 1;
+        slow_list[atomicAdd(slow_count, 1)] = b;
+    } else {
+        // Order-independent form of periodicMin (go/group.go:384-409), valid for
+        // pixel indices in [0, pixels): the arc is [q0 + dmin, q0 + dmax] with
+        // d = signed periodic distance to q0; too wide an arc returns 0.
+        const long long P = d.pixels, half = P / 2, K = P - half - 1;
+        unsigned long long spread = s.wmax - s.wmin + 1ULL;
+        s.do_bound = 1;
+        if (spread > (unsigned long long)half) {
+            s.pmin = 0;
+            s.min = s.qmin;
+            finish_stat(s, d.n, (unsigned long long)s.qmax - (unsigned long long)s.qmin, err);
+        } else {
+            long long m = s.q0 + ((long long)s.wmin - K);
+            if (m < 0) m += P;
+            s.pmin = m;
+            s.min = m;
+            finish_stat(s, d.n, spread - 1ULL, err);
+        }
+    }
+    stats[b] = s;
+}
+
+// Exact periodicMin for blocks with out-of-range pixel indices.  One CTA per
+// slow block.  Warp 0 walks the block in the reference's order; lanes whose
+// element lies strictly inside the current arc (`continue` at go/group.go:395)
+// are skipped 32 at a time with a ballot, every other element updates the arc
+// exactly as the Go loop does.
+__global__ void __launch_bounds__(256)
+k_slow(const BlockDesc *descs, BlockStat *stats, const int64_t *slow_list, const int *slow_count, int *err) {
+    __shared__ long long s_pmin;
+    __shared__ long long s_red[2][8];
+    const int nslow = *slow_count;
+    for (int si = blockIdx.x; si < nslow; si += gridDim.x) {
+        const int64_t b = slow_list[si];
+        const BlockDesc d = descs[b];
+        const long long P = d.pixels;
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            long long x0 = block_value(d, 0), width = 1;
+            bool returned_zero = false;
+            for (int64_t base = 0; base < d.n && !returned_zero; base += 32) {
+                int64_t i = base + lane;
+                bool valid = i < d.n;
+                long long q = valid ? block_value(d, i) : 0;
+                unsigned pending = __ballot_sync(0xffffffffu, valid);
+                while (pending) {
+                    long long x1 = (long long)((unsigned long long)x0 + (unsigned long long)width - 1ULL);
+                    if (x1 >= P) x1 = (long long)((unsigned long long)x1 - (unsigned long long)P);
+                    long long d0 = periodic_distance(q, x0, P);
+                    long long d1 = periodic_distance(q, x1, P);
+                    bool inside = d0 > 0 && d1 < 0;
+                    unsigned act = __ballot_sync(0xffffffffu, !inside) & pending;
+                    if (!act) break;
+                    int j = __ffs(act) - 1;
+                    long long e0 = __shfl_sync(0xffffffffu, d0, j);
+                    long long e1 = __shfl_sync(0xffffffffu, d1, j);
+                    if (e1 > (long long)(0ULL - (unsigned long long)e0)) {
+                        width = (long long)((unsigned long long)width + (unsigned long long)e1);
+                    } else {
+                        x0 = (long long)((unsigned long long)x0 + (unsigned long long)e0);
+                        if (x0 < 0) x0 = (long long)((unsigned long long)x0 + (unsigned long long)P);
+                        width = (long long)((unsigned long long)width - (unsigned long long)e0);
+                    }
+                    if (width > P / 2) { returned_zero = true; break; }
+                    pending &= ~((2u << j) - 1u);  // elements up to j are done
+                }
+            }
+            if (lane == 0) s_pmin = returned_zero ? 0 : x0;
+        }
+        __syncthreads();
+        const long long pmin = s_pmin;
+        long long mn = LLONG_MAX, mx = LLONG_MIN;
+        for (int64_t i = threadIdx.x; i < d.n; i += blockDim.x) {
+            long long q = bound1(block_value(d, i), pmin, P);
+            mn = q < mn ? q : mn;
+            mx = q > mx ? q : mx;
+        }
+        mn = warp_min_ll(mn); mx = warp_max_ll(mx);
+        if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = mn; s_red[1][threadIdx.x >> 5] = mx; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; k++) {
+                mn = s_red[0][k] < mn ? s_red[0][k] : mn;
+                mx = s_red[1][k] > mx ? s_red[1][k] : mx;
+            }
+            BlockStat s = stats[b];
+            s.pmin = pmin; s.do_bound = 1; s.min = mn;
+            finish_stat(s, d.n, (unsigned long long)mx - (unsigned long long)mn, err);
+            stats[b] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// scan: one CTA per chain (= minnow group); exclusive prefix of nbytes
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_scan(BlockStat *stats, BatchShape sh, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int64_t chain = blockIdx.x;
+    const int64_t b0 = chain * sh.blocks_per_chain;
+    const int64_t b1 = b0 + sh.blocks_per_chain < sh.nblocks ? b0 + sh.blocks_per_chain : sh.nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = b0; base < b1; base += 1024) {
+        int64_t b = base + threadIdx.x;
+        long long v = b < b1 ? stats[b].nbytes : 0;
+        long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+            long long wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        long long carry = s_carry;
+        long long excl = carry + s_warp[warp] + incl - v;
+        if (b < b1) {
+            stats[b].out_off = excl;
+            if (offsets) offsets[b] = excl;
+            if (mins) mins[b] = stats[b].min;
+            if (bits) bits[b] = stats[b].bits;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && out_len) out_len[chain] = s_carry;
+}
+
+// ---------------------------------------------------------------------------
+// byte-aligned stream store: write nbytes of the little-endian word stream s[]
+// to dst, which may have any byte alignment.  Interior words are written as
+// aligned 32-bit stores; the first/last partial word as single bytes, because
+// neighbouring blocks own the other bytes of those words.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_stream(uint8_t *dst, const uint32_t *s, int64_t nbytes, int tid, int nthreads) {
+    const uintptr_t A = (uintptr_t)dst;
+    const int a = (int)(A & 3);
+    uint32_t *base = (uint32_t *)(A - a);
+    const int64_t nwords = (a + nbytes + 3) >> 2;
+    for (int64_t j = tid; j < nwords; j += nthreads) {
+        uint32_t lo = j > 0 ? s[j - 1] : 0u;
+        uint32_t hi = 4 * j < nbytes ? s[j] : 0u;
+        uint32_t w = __funnelshift_rc(lo, hi, 32 - 8 * a);
+        int64_t t0 = 4 * j - a;  // stream index of this word's byte 0
+        if (t0 >= 0 && t0 + 4 <= nbytes) {
+            base[j] = w;
+        } else {
+            uint8_t *bp = (uint8_t *)(base + j);
+            for (int k = 0; k < 4; k++) {
+                int64_t t = t0 + k;
+                if (t >= 0 && t < nbytes) bp[k] = (uint8_t)(w >> (8 * k));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PACK_THREADS)
+k_pack(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats, BatchShape sh,
+       uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err) {
+    __shared__ uint32_t s_out[PACK_THREADS * 64 + 4];
+    const int64_t tile = blockIdx.x;
+    const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
+    const int64_t b = find_block(descs, sh, tile, tpb, true);
+    const BlockStat st = stats[b];
+    const int bits = st.bits;
+    if (bits == 0) return;  // ArrayBuffer.Write returns at once, go/bit/bit.go:162
+    if (st.out_off + st.nbytes > chain_cap) {  // never write past the caller's buffer
+        if (threadIdx.x == 0) atomicExch(err, 2);
+        return;
+    }
+    const BlockDesc d = descs[b];
+    const int64_t first = (tile - d.tile0) * PACK_TILE;
+    const int64_t count = first + PACK_TILE <= d.n ? PACK_TILE : d.n - first;
+    const unsigned long long mask = bits >= 64 ? ~0ULL : ((1ULL << bits) - 1ULL);  // go/bit/bit.go:104
+    const long long P = d.pixels;
+
+    const int g = threadIdx.x;
+    int64_t i0 = first + 32 * (int64_t)g;
+    if (32 * g < count) {
+        unsigned long long acc_lo = 0, acc_hi = 0;
+        int pos = 0, w = g * bits;
+#pragma unroll 4
+        for (int k = 0; k < 32; k++) {
+            int64_t i = i0 + k;
+            unsigned long long v = 0;
+            if (i < d.n) {
+                long long q = block_value(d, i);
+                if (st.do_bound) q = bound1(q, st.pmin, P);
+                v = ((unsigned long long)q - (unsigned long long)st.min) & mask;
+            }
+            acc_lo |= v << pos;
+            if (pos) acc_hi |= v >> (64 - pos);
+            pos += bits;
+            while (pos >= 32) {
+                s_out[w++] = (uint32_t)acc_lo;
+                acc_lo = (acc_lo >> 32) | (acc_hi << 32);
+                acc_hi >>= 32;
+                pos -= 32;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t nbytes = (count * bits + 7) >> 3;
+    uint8_t *dst = out + (int64_t)d.chain * chain_stride + st.out_off + ((first * bits) >> 3);
+    store_stream(dst, s_out, nbytes, threadIdx.x, PACK_THREADS);
+}
+
+// ---------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long extract_bits(const uint8_t *stream, int64_t stream_len,
+                                                           int64_t byte_off, int64_t i, int bits) {
+    const uintptr_t S = (uintptr_t)stream;
+    const int a = (int)(S & 3);
+    const uint32_t *base = (const uint32_t *)(S - a);
+    const int64_t limit = (a + stream_len + 3) >> 2;
+    unsigned long long bitpos = ((unsigned long long)byte_off + a) * 8ULL + (unsigned long long)i * bits;
+    int64_t wi = (int64_t)(bitpos >> 5);
+    int sh = (int)(bitpos & 31);
+    uint32_t w0 = wi < limit ? __ldg(base + wi) : 0u;
+    uint32_t w1 = (sh + bits > 32 && wi + 1 < limit) ? __ldg(base + wi + 1) : 0u;
+    unsigned long long v = (((unsigned long long)w1 << 32) | w0) >> sh;
+    if (sh + bits > 64) {
+        uint32_t w2 = wi + 2 < limit ? __ldg(base + wi + 2) : 0u;
+        v |= (unsigned long long)w2 << (64 - sh);
+    }
+    if (bits < 64) v &= (1ULL << bits) - 1ULL;
+    return v;
+}
+
+struct DecodeArgs {
+    int mode;                 // 0: int group, 1: float group, 2: vec3 sub-cells
+    const uint8_t *data;
+    int64_t stream_len;       // bytes per stream (group: data_len; vec3: axis stride)
+    const int64_t *offsets, *mins, *bits, *sel, *jitter_ids;
+    int64_t n, nsel;
+    float low[3], dx[3];
+    int64_t pixels[3];
+    int periodic[3];
+    float wrap_L;
+    int jmode;
+    unsigned long long seed, block_id0;
+    const double *u;
+    int32_t nfile, nsub, subcells;
+    int64_t sc3;
+    void *out;
+};
+
+__global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
+    const int64_t cpb = (A.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    const int64_t j = blockIdx.x / cpb;          // which selected block
+    const int64_t c = blockIdx.x - j * cpb;
+    const int64_t b = A.sel ? A.sel[j] : j;      // block id within the group / batch
+    const long long mn = A.mins[b];
+    const int bits = (int)A.bits[b];
+    const int64_t off = A.offsets[b];
+    const uint8_t *stream = A.data;
+    int k = 0;
+    int64_t f = 0, sc = 0;
+    if (A.mode == 2) {
+        f = b / (3 * A.sc3);
+        k = (int)((b / A.sc3) % 3);
+        sc = b % A.sc3;
+        stream += (b / A.sc3) * A.stream_len;    // stream (3f + k)
+    }
+    const long long P = A.pixels[k];
+    const float low = A.low[k], dx = A.dx[k];
+    const int64_t end = (c + 1) * DEC_CHUNK < A.n ? (c + 1) * DEC_CHUNK : A.n;
+    for (int64_t i = c * DEC_CHUNK + threadIdx.x; i < end; i += DEC_THREADS) {
+        unsigned long long v = bits ? extract_bits(stream, A.stream_len, off, i, bits) : 0ULL;
+        long long q = (long long)((unsigned long long)mn + v);  // go/group.go:262
+        if (A.mode == 0) {
+            ((long long *)A.out)[j * A.n + i] = q;
+            continue;
+        }
+        if (A.periodic[k]) q = bound1(q, 0, P);              // go/group.go:303
+        double u = 0.5;
+        if (A.jmode == 1) u = (double)jitter_hash32(A.seed, A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b), (unsigned long long)i) * 0x1p-32;
+        else if (A.jmode == 2) u = A.u[j * A.n + i];
+        float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));  // go/group.go:308
+        float o = __fadd_rn(__fmul_rn(dx, t), low);
+        if (A.mode == 1) {
+            ((float *)A.out)[j * A.n + i] = o;
+        } else {
+            if (A.wrap_L > 0.0f) {                               // go/minp/minp.go:195-203
+                if (o < 0.0f) o = __fadd_rn(o, A.wrap_L);
+                else if (o >= A.wrap_L) o = __fsub_rn(o, A.wrap_L);
+            }
+            uint32_t ii = (uint32_t)i, ns = (uint32_t)A.nsub;   // setSubCell, go/minp/minp.go:270-288
+            uint32_t jx = ii % ns, tt = ii / ns;
+            uint32_t jy = tt % ns, jz = tt / ns;
+            int32_t ix0 = A.nsub * (int32_t)(sc % A.subcells);
+            int32_t iy0 = A.nsub * (int32_t)((sc / A.subcells) % A.subcells);
+            int32_t iz0 = A.nsub * (int32_t)(sc / ((int64_t)A.subcells * A.subcells));
+            int64_t idx = (int64_t)(jx + ix0) + (int64_t)(jy + iy0) * A.nfile + (int64_t)(jz + iz0) * A.nfile * A.nfile;
+            float *cube = (float *)A.out + 3 * f * (int64_t)A.nfile * A.nfile * A.nfile;
+            cube[3 * idx + k] = o;
+        }
+    }
+}
+
+// max of uint64 (ArrayBuffer.Bits, go/bit/bit.go:151-159)
+__global__ void __launch_bounds__(256) k_umax(const unsigned long long *x, int64_t n, unsigned long long *out) {
+    unsigned long long m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = x[i] > m ? x[i] : m;
+    m = warp_max_ull(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// raw pack of caller-supplied uint64 values with caller-supplied bits
+// (bit.BufferedArray): presets the stat so that k_pack does the work.
+__global__ void k_preset_raw(BlockDesc *descs, BlockStat *stats, const void *src, int64_t n, int bits) {
+    BlockDesc d = {};
+    d.src = src; d.n = n; d.kind = KIND_I64; d.access = ACC_CONTIG;
+    d.tile0 = 0; d.chunk0 = 0;
+    descs[0] = d;
+    BlockStat s = {};
+    s.min = 0; s.bits = bits; s.nbytes = array_bytes(bits, n); s.out_off = 0; s.do_bound = 0;
+    stats[0] = s;
+}
+
+// blockIndex.addBlock/blockOffset over a plain size array (go/block_index.go:16-35)
+__global__ void __launch_bounds__(1024)
+k_scan_sizes(const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets, int64_t *total) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = base;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < n; b0 += 1024) {
+        int64_t b = b0 + threadIdx.x;
+        long long v = b < n ? sizes[b] : 0, incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        long long excl = s_carry + s_warp[warp] + incl - v;
+        if (b < n) offsets[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry - base;
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
+                         const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
+                         const FloatParamsHost &fp, int64_t blocks_per_chain) {
+    if (nb == 0) return;
+    FloatParams p = {fp.low, fp.high, fp.dx, fp.hi_clamp, fp.pixels, fp.flags};
+    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, p, blocks_per_chain);
+    L.count++;
+}
+
+void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
+                       int32_t subcells, const FloatParamsHost fp[3]) {
+    int64_t nb = nfiles * 3 * (int64_t)subcells * subcells * subcells;
+    if (nb == 0) return;
+    FloatParams p[3];
+    for (int k = 0; k < 3; k++) p[k] = {fp[k].low, fp[k].high, fp[k].dx, fp[k].hi_clamp, fp[k].pixels, fp[k].flags};
+    k_build_vec3<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nfiles, aos, nfile, subcells, p[0], p[1], p[2]);
+    L.count++;
+}
+
+void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
+                           int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
+                           int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
+                           int64_t chain_cap) {
+    if (sh.nblocks == 0) return;
+    cudaMemsetAsync(slow_count, 0, sizeof(int), L.stream);
+    k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks);
+    L.count++;
+    if (sh.total_chunks > 0) {
+        k_stats<<<(unsigned)sh.total_chunks, STATS_THREADS, 0, L.stream>>>(descs, stats, sh);
+        L.count++;
+    }
+    k_finalize<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, slow_list, slow_count, err);
+    L.count++;
+    unsigned slow_grid = (unsigned)(sh.nblocks < 296 ? sh.nblocks : 296);
+    k_slow<<<slow_grid, 256, 0, L.stream>>>(descs, stats, slow_list, slow_count, err);
+    L.count++;
+    k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len);
+    L.count++;
+    if (sh.total_tiles > 0) {
+        k_pack<<<(unsigned)sh.total_tiles, PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err);
+        L.count++;
+    }
+}
+
+void launch_raw_pack(Launcher &L, BlockDesc *descs, BlockStat *stats, const void *src, int64_t n, int bits,
+                     uint8_t *out) {
+    if (n == 0) return;
+    k_preset_raw<<<1, 1, 0, L.stream>>>(descs, stats, src, n, bits);
+    L.count++;
+    BatchShape sh = {1, 1, 1, n, (n + PACK_TILE - 1) / PACK_TILE, 0};
+    k_pack<<<(unsigned)sh.total_tiles, PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, 0, (int64_t)1 << 62, nullptr);
+    L.count++;
+}
+
+void launch_umax(Launcher &L, const unsigned long long *x, int64_t n, unsigned long long *out) {
+    cudaMemsetAsync(out, 0, 8, L.stream);
+    if (n == 0) return;
+    unsigned g = grid_for(n, 256);
+    if (g > 1184) g = 1184;
+    k_umax<<<g, 256, 0, L.stream>>>(x, n, out);
+    L.count++;
+}
+
+cudaError_t launch_scan_sizes(Launcher &L, const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets,
+                              int64_t *total) {
+    k_scan_sizes<<<1, 1024, 0, L.stream>>>(sizes, n, base, offsets, total);
+    L.count++;
+    return cudaGetLastError();
+}
+
+void launch_decode(Launcher &L, const DecodeHost &h) {
+    if (h.nsel == 0 || h.n == 0) return;
+    DecodeArgs A = {};
+    A.mode = h.mode; A.data = h.data; A.stream_len = h.stream_len;
+    A.offsets = h.offsets; A.mins = h.mins; A.bits = h.bits; A.sel = h.sel; A.jitter_ids = h.jitter_ids;
+    A.n = h.n; A.nsel = h.nsel;
+    for (int k = 0; k < 3; k++) { A.low[k] = h.low[k]; A.dx[k] = h.dx[k]; A.pixels[k] = h.pixels[k]; A.periodic[k] = h.periodic[k]; }
+    A.wrap_L = h.wrap_L; A.jmode = h.jmode; A.seed = h.seed; A.block_id0 = h.block_id0; A.u = h.u;
+    A.nfile = h.nfile; A.nsub = h.subcells ? h.nfile / h.subcells : 0; A.subcells = h.subcells;
+    A.sc3 = (int64_t)h.subcells * h.subcells * h.subcells;
+    A.out = h.out;
+    int64_t cpb = (h.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    k_decode<<<(unsigned)(h.nsel * cpb), DEC_THREADS, 0, L.stream>>>(A);
+    L.count++;
+}
+
+}  // namespace mnw
