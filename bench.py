@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- encode & decode GB/s (uncompressed) of the minnow block hot path.
+
+Workload (BASELINE.json configs[1]): a minp particle snapshot of 1024^3
+particles, positions + velocities, as 64 files of 256^3 (FileCells = 4), each
+file split into 4^3 sub-cells of 64^3 (SubCells = 4): 3 FloatGroups x 64 blocks
+per file and field.  Positions: periodic [0, 1000) Mpc/h, dx = 0.005 (200 000
+pixels).  Velocities: per-file limits [min, nextafter(max)], dv = 1 km/s.
+One step = encode(x) + encode(v) + decode(x) + decode(v) of the whole snapshot
+on every rank (weak scaling: each rank holds its own 1024^3 block range).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]      (N>1: under torchrun)
+  python bench.py --impl reference ...                     CPU oracle on host cores
+
+Prints ONE JSON line (see the contract in DESIGN.md, "Measurement").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encode+decode GB/s (uncompressed)"
+L_BOX, DX_POS, DV = 1000.0, 0.005, 1.0
+NSIDE, FILE_CELLS, SUB_CELLS = 1024, 4, 4
+NFILE = NSIDE // FILE_CELLS            # 256
+NFILES = FILE_CELLS ** 3               # 64
+SC3 = SUB_CELLS ** 3                   # 64
+NSUB3 = (NFILE // SUB_CELLS) ** 3      # 262144
+NP_FILE = NFILE ** 3
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "minp 1024^3 positions+velocities: 64 files x 256^3 (FileCells=4), SubCells=4 -> "
+                       "3x64 blocks of 64^3 per file and field; x periodic [0,1000) dx=0.005 (200000 px), "
+                       "v per-file limits dv=1; one step = encode(x,v) + decode(x,v)",
+           "particles_per_gpu": NSIDE ** 3, "uncompressed_bytes_per_step_per_gpu": 4 * 12 * NSIDE ** 3,
+           "cache": "inputs (25.8 GB per GPU) are far larger than L2 (126 MB); no flush needed",
+           "jitter": "hash (one random sub-pixel offset per decoded value, as the reference draws rand.Float64)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def gen_file(torch, f, seed, device):
+    """Synthetic Lagrangian file f: positions = grid + Irwin-Hall(4) displacement
+    (sigma 2 Mpc/h) wrapped into [0, L); velocities = 300 km/s x Irwin-Hall(4)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 100003 + f)
+    fx, fy, fz = f % FILE_CELLS, (f // FILE_CELLS) % FILE_CELLS, f // (FILE_CELLS * FILE_CELLS)
+    j = torch.arange(NFILE, device=device, dtype=torch.float32)
+    cell = L_BOX / NSIDE
+    gx = ((fx * NFILE + j) * cell).view(1, 1, NFILE).expand(NFILE, NFILE, NFILE)
+    gy = ((fy * NFILE + j) * cell).view(1, NFILE, 1).expand(NFILE, NFILE, NFILE)
+    gz = ((fz * NFILE + j) * cell).view(NFILE, 1, 1).expand(NFILE, NFILE, NFILE)
+    grid = torch.stack([gx, gy, gz], dim=-1).reshape(NP_FILE, 3)
+
+    def irwin_hall():
+        u = torch.rand((4, NP_FILE, 3), generator=g, device=device, dtype=torch.float32)
+        return (u.sum(0) - 2.0) * (1.0 / 0.5773502691896257)   # unit variance
+
+    pos = torch.remainder(grid + 2.0 * irwin_hall(), L_BOX)
+    pos = torch.where(pos >= L_BOX, torch.zeros_like(pos), pos).contiguous()
+    vel = (300.0 * irwin_hall()).contiguous()
+    return pos, vel
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons = index, period, [], set()
+        self.stop_flag = threading.Event()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (oracle = port of the reference; test infrastructure, only ever the thing timed
+# here as the BASELINE, never as the product)
+# ---------------------------------------------------------------------------------------
+def cpu_descs(orc, vel_np):
+    lo, hi = orc.minp_limits(vel_np, False, L_BOX)
+    vpx = [orc.float_group_pixels(float(lo[k]), float(hi[k]), np.float32(DV)) for k in range(3)]
+    ppx = orc.float_group_pixels(0.0, np.float32(L_BOX), np.float32(DX_POS))
+    return ([0.0] * 3, [L_BOX] * 3, [ppx] * 3), (lo.tolist(), hi.tolist(), vpx)
+
+
+def cpu_step(orc, pos_np, vel_np, threads):
+    """encode + decode of ONE file (positions and velocities) with the oracle."""
+    pd, vd = cpu_descs(orc, vel_np)
+    for arr, (lo, hi, px), per in ((pos_np, pd, True), (vel_np, vd, False)):
+        mins, bits, nbytes, packed, stride, total = orc.bench_minp_encode(arr, NFILE, SUB_CELLS, lo, hi, px, threads)
+        orc.bench_minp_decode(packed, stride, NFILE, SUB_CELLS, lo, hi, px, mins, bits, per, L_BOX, 1, 7, threads)
+    return 4 * 12 * NP_FILE   # uncompressed bytes through encode + decode
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Go is not in
+    this image) on all host cores, bounded sample = one file per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as orc
+    orc.lib()
+    threads = orc.max_threads()
+    pos, vel = gen_file(torch, 0, 2, "cpu")
+    pos_np, vel_np = pos.numpy(), vel.numpy()
+    for _ in range(args.warmup):
+        cpu_step(orc, pos_np, vel_np, threads)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(args.steps):
+        nbytes += cpu_step(orc, pos_np, vel_np, threads)
+    dt = time.perf_counter() - t0
+    val = nbytes / dt / 1e9
+    sample = "1 of 64 files (256^3 particles, x and v) per step, encode+decode, OpenMP over blocks"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->i64 (f64 floor)",
+           "data": "synthetic", "config": workload_config(),
+           "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import minnow_b200 as mb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = mb.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---- synthetic snapshot, resident in HBM -------------------------------------------
+    pos = torch.empty((NFILES, NP_FILE, 3), dtype=torch.float32, device=dev)
+    vel = torch.empty((NFILES, NP_FILE, 3), dtype=torch.float32, device=dev)
+    for f in range(NFILES):
+        p, v = gen_file(torch, f, 2 + rank, dev)
+        pos[f].copy_(p)
+        vel[f].copy_(v)
+        del p, v
+    torch.cuda.synchronize()
+
+    nb = NFILES * 3 * SC3                  # blocks per field
+    stride = 4 * NFILE ** 3 + 256          # bytes reserved per (file, axis) stream (<= 32 bits/value)
+    i64 = dict(dtype=torch.int64, device=dev)
+    meta = {k: [torch.zeros(nb, **i64) for _ in range(3)] for k in ("x", "v")}     # mins, bits, offsets
+    out_len = {k: torch.zeros(3 * NFILES, **i64) for k in ("x", "v")}
+    packed = {k: torch.empty(3 * NFILES * stride, dtype=torch.uint8, device=dev) for k in ("x", "v")}
+    decoded = torch.empty((NFILES, NP_FILE, 3), dtype=torch.float32, device=dev)
+    sizes_all = torch.zeros(world * 2 * nb, **i64)
+    offs_all = torch.zeros(world * 2 * nb, **i64)
+    total_all = torch.zeros(1, **i64)
+
+    ppx = mb.float_group_pixels(0.0, L_BOX, DX_POS)
+    pdescs = [mb.FloatDesc.make(0.0, L_BOX, ppx) for _ in range(3)]
+    jit = mb.Jitter.make(mb.JITTER_HASH, 7)
+    state = {}
+
+    def vel_descs():
+        lo, hi = ctx.vec3_limits(vel, NFILES, dev=True)       # bounds() of minp.Writer.Vectors; synchronises
+        return [mb.FloatDesc.make(lo[f, k], hi[f, k], mb.float_group_pixels(lo[f, k], hi[f, k], DV))
+                for f in range(NFILES) for k in range(3)]
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = []
+
+    def step(record=False):
+        with torch.cuda.stream(stream):
+            e = [ev() for _ in range(5)] if record else None
+            if record: e[0].record(stream)
+            vd = vel_descs()
+            state["vd"] = vd
+            ctx.encode_vec3_subcells_dev(pdescs, pos, NFILE, SUB_CELLS, NFILES, *meta["x"], packed["x"], stride, out_len["x"])
+            if record: e[1].record(stream)
+            ctx.encode_vec3_subcells_dev(vd, vel, NFILE, SUB_CELLS, NFILES, *meta["v"], packed["v"], stride, out_len["v"])
+            if record: e[2].record(stream)
+            if world > 1:
+                # the one exchange of the sharded path: all-gather per-block packed sizes, then every
+                # rank scans them to the global byte offsets
+                local = torch.cat([(meta[k][1] * NSUB3 + 7) >> 3 for k in ("x", "v")])
+                dist.all_gather_into_tensor(sizes_all, local)
+                ctx.scan_offsets_dev(sizes_all, sizes_all.numel(), 0, offs_all, total_all)
+            ctx.decode_vec3_subcells_dev(pdescs, packed["x"], stride, meta["x"][2], meta["x"][0], meta["x"][1],
+                                         NFILE, SUB_CELLS, NFILES, L_BOX, jit, decoded)
+            if record: e[3].record(stream)
+            ctx.decode_vec3_subcells_dev(vd, packed["v"], stride, meta["v"][2], meta["v"][0], meta["v"][1],
+                                         NFILE, SUB_CELLS, NFILES, 0.0, jit, decoded)
+            if record: e[4].record(stream)
+            if record: marks.append(e)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = ctx.launch_count
+    ctx.profile(True)
+    start, stop = ev(), ev()
+    start.record(stream)
+    for _ in range(args.steps):
+        step(record=True)
+    stop.record(stream)
+    barrier()
+    ctx.profile(False)
+    clocks = sampler.result()
+    launches = ctx.launch_count - launches0
+    ms_total = start.elapsed_time(stop)
+    prof = ctx.profile_summary()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    bytes_step = 4 * 12 * NSIDE ** 3                      # per GPU: encode in (x, v) + decode out (x, v)
+    value = world * bytes_step / (ms_step * 1e-3) / 1e9
+
+    # per-phase times (rank 0), device events on the launching stream
+    ph = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks]).mean(0)
+    field_bytes = 12 * NSIDE ** 3
+    mean_bits = {k: float(meta[k][1].double().mean().item()) for k in ("x", "v")}
+    packed_bytes = {k: int(out_len[k].sum().item()) for k in ("x", "v")}
+    phases = {"encode_x_ms": ph[0], "encode_v_ms": ph[1], "decode_x_ms": ph[2], "decode_v_ms": ph[3],
+              "encode_gbs": 2 * field_bytes / ((ph[0] + ph[1]) * 1e-3) / 1e9,
+              "decode_gbs": 2 * field_bytes / ((ph[2] + ph[3]) * 1e-3) / 1e9,
+              "mean_bits_x": mean_bits["x"], "mean_bits_v": mean_bits["v"],
+              "packed_bytes_x": packed_bytes["x"], "packed_bytes_v": packed_bytes["v"],
+              "encode_path": "fused" if ctx.last_path == 1 else "generic-two-pass"}
+
+    # ---- roofline of the dominant kernel -------------------------------------------------
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = {"hbm_gbs": float(json.load(f)["hbm_gbs"]), "src": "measured"}
+    except Exception:
+        pass
+    pk_total = packed_bytes["x"] + packed_bytes["v"]
+    algo = {  # algorithmic bytes per step, summed over both fields (DESIGN.md "Kernels")
+        "k_stats": 2 * field_bytes, "k_pack": 2 * field_bytes + pk_total,
+        "k_fused_vec3": 2 * field_bytes + pk_total, "k_decode": pk_total + 2 * field_bytes}
+    roof = None
+    if prof:
+        top = max(prof, key=lambda r: r["ms"])
+        per_launch_ms = top["ms"] / top["launches"]
+        launches_per_step = top["launches"] / args.steps
+        a = algo.get(top["kernel"], 0) / launches_per_step / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": a / peaks["hbm_gbs"], "peak_source": peaks["src"] + " (MEASURED_PEAKS.json copy bandwidth)",
+                "traffic": None, "ms_per_launch": per_launch_ms,
+                "algorithmic_bytes_per_launch": algo.get(top["kernel"], 0) / launches_per_step,
+                "kernels": [dict(r, share=r["ms"] / (ms_total)) for r in prof]}
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ------
+    e2e = run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev)
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on the host cores ----------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.lib()
+        threads = orc.max_threads()
+        p0, v0 = pos[0].cpu().numpy(), vel[0].cpu().numpy()
+        cpu_step(orc, p0, v0, threads)
+        t0 = time.perf_counter()
+        reps, nby = 0, 0
+        while reps < 2 or time.perf_counter() - t0 < 4.0:
+            nby += cpu_step(orc, p0, v0, threads)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": nby / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": "file 0 of 64 (256^3 particles, x and v), encode+decode, %d repetitions, OpenMP over blocks" % reps}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32->i64 (f64 floor, as the reference)", "data": "synthetic",
+               "config": workload_config({"sharding": "block ranges per GPU; NCCL all-gather of per-block sizes + "
+                                          "offset scan" if world > 1 else "single GPU"}),
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "phases": phases,
+               "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
+    """The same step through mnw_encode_vec3_subcells / mnw_decode_vec3_subcells with
+    HOST buffers: every file's particles come from pinned host memory, packed bytes
+    and metadata go back to the host, are sent down again and decoded to host memory."""
+    import psutil
+    budget = 0.35 * psutil.virtual_memory().available / max(world, 1)
+    per_file = 2 * 12 * NP_FILE
+    nfiles = int(max(1, min(NFILES, budget // per_file)))
+    hpos = torch.empty((nfiles, NP_FILE, 3), dtype=torch.float32).pin_memory()
+    hvel = torch.empty((nfiles, NP_FILE, 3), dtype=torch.float32).pin_memory()
+    hpos.copy_(pos[:nfiles])
+    hvel.copy_(vel[:nfiles])
+    stride = 4 * NP_FILE + 256
+    hout = torch.empty(3 * stride, dtype=torch.uint8).pin_memory()
+    hdec = torch.empty((NP_FILE, 3), dtype=torch.float32).pin_memory()
+    nbk = 3 * SC3
+    mins, bits, offs = (np.zeros(nbk, np.int64) for _ in range(3))
+    lens = np.zeros(3, np.int64)
+    import ctypes as C
+    lib, h = ctx.lib, ctx.h
+    jit = mb.Jitter.make(mb.JITTER_HASH, 7)
+    P = lambda a: C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
+    h2d = d2h = 0
+
+    def one(field, f, count):
+        nonlocal h2d, d2h
+        src = hpos[f] if field == "x" else hvel[f]
+        if field == "x":
+            d3 = (mb.FloatDesc * 3)(*pdescs)
+            wrap = L_BOX
+        else:
+            lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+            ctx._check(lib.mnw_vec3_limits(h, P(src), NP_FILE, 1, P(lo), P(hi)))
+            d3 = (mb.FloatDesc * 3)(*[mb.FloatDesc.make(lo[k], hi[k], mb.float_group_pixels(lo[k], hi[k], DV)) for k in range(3)])
+            wrap = 0.0
+            if count: h2d += 12 * NP_FILE
+        ctx._check(lib.mnw_encode_vec3_subcells(h, d3, P(src), NFILE, SUB_CELLS, P(mins), P(bits), P(offs), P(hout), stride, P(lens)))
+        ptrs = (C.c_void_p * 3)(*[hout.data_ptr() + k * stride for k in range(3)])
+        ctx._check(lib.mnw_decode_vec3_subcells(h, d3, ptrs, P(lens), P(offs), P(mins), P(bits), NFILE, SUB_CELLS, wrap,
+                                                C.byref(jit), P(hdec)))
+        if count:
+            pk = int(lens.sum())
+            h2d += 12 * NP_FILE + pk + 3 * 8 * nbk
+            d2h += pk + 3 * 8 * nbk + 12 * NP_FILE
+
+    one("x", 0, False); one("v", 0, False)     # warm-up (buffers grow once)
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for f in range(nfiles):
+            one("x", f, True)
+            one("v", f, True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    nbytes = steps * nfiles * 4 * 12 * NP_FILE
+    scale = NFILES / nfiles                       # bytes per full step, as counted from the copies made
+    return {"value": world * nbytes / dt / 1e9, "unit": "GB/s",
+            "h2d_bytes_per_step": int(h2d / steps * scale), "d2h_bytes_per_step": int(d2h / steps * scale),
+            "files_timed_per_step": nfiles, "steps": steps,
+            "api": "mnw_vec3_limits + mnw_encode_vec3_subcells + mnw_decode_vec3_subcells, one file per call, "
+                   "pinned host buffers, synchronous"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -199,16 +199,38 @@ MNW_API int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc
                                         const int64_t *sel, const mnw_jitter *jitter, float *out);
 /* nfiles cubes back to back in aos (each nfile^3 particles); outputs are
  * [nfiles][3*subcells^3]; file f / axis k bytes at out + (3*f + k)*out_axis_stride,
- * lengths in out_len[3*f + k]. */
-MNW_API int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos,
-                                         int64_t nfile, int64_t subcells, int64_t nfiles,
+ * lengths in out_len[3*f + k].  desc (HOST) holds 3 entries shared by all files
+ * (desc_per_file = 0; periodic positions) or 3 per file (desc_per_file = 1;
+ * non-periodic fields get their own limits per file, go/minp/minp.go:92-95). */
+MNW_API int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file,
+                                         const float *aos, int64_t nfile, int64_t subcells, int64_t nfiles,
                                          int64_t *mins, int64_t *bits, int64_t *offsets,
                                          uint8_t *out, int64_t out_axis_stride, int64_t *out_len);
-MNW_API int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *data,
-                                         int64_t data_axis_stride, const int64_t *offsets,
+MNW_API int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file,
+                                         const uint8_t *data, int64_t data_axis_stride, const int64_t *offsets,
                                          const int64_t *mins, const int64_t *bits, int64_t nfile,
                                          int64_t subcells, int64_t nfiles, float wrap_L,
                                          const mnw_jitter *jitter, float *aos_out);
+
+/* minp.Writer.Vectors limits for NON-periodic fields (go/minp/minp.go:92-95):
+ * lo = min over particles, hi = Nextafter32(max, 2*max), per axis.  aos holds
+ * nfiles cubes of np particles each; lo/hi are HOST arrays [nfiles][3].  The
+ * _dev variant takes a DEVICE aos pointer (it synchronises to return lo/hi).
+ * NaNs are ignored; if both -0 and +0 are extreme values the sign of the
+ * returned zero may differ from Go's first-seen rule. */
+MNW_API int mnw_vec3_limits(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi);
+MNW_API int mnw_vec3_limits_dev(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi);
+
+/* Device-pointer form of mnw_scan_offsets (sizes, offsets [nblocks], total [1]). */
+MNW_API int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base,
+                                 int64_t *offsets, int64_t *total);
+
+/* Per-kernel timing with CUDA events on the context's stream.  mnw_profile(ctx, 1)
+ * starts recording the library's bandwidth-carrying kernels, mnw_profile(ctx, 0)
+ * stops; mnw_profile_summary synchronises and writes a JSON array
+ * [{"kernel": name, "launches": n, "ms": total}, ...] into buf and clears the log. */
+MNW_API int mnw_profile(mnw_ctx *ctx, int on);
+MNW_API int mnw_profile_summary(mnw_ctx *ctx, char *buf, int64_t cap);
 
 /* Which device path the last encode on ctx took: 0 = generic two-pass,
  * 1 = fused single-read cluster kernel.  For tests and the benchmark. */

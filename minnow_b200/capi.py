@@ -74,8 +74,13 @@ SIGNATURES = {
     "mnw_encode_float_group_dev": (_int, [_p, _FD, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
     "mnw_decode_int_blocks_dev": (_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p, _p]),
     "mnw_decode_float_blocks_dev": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _p, _JT, _p]),
-    "mnw_encode_vec3_subcells_dev": (_int, [_p, _FD, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
-    "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
+    "mnw_encode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
+    "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
+    "mnw_vec3_limits": (_int, [_p, _p, _i64, _i64, _p, _p]),
+    "mnw_vec3_limits_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
+    "mnw_scan_offsets_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
+    "mnw_profile": (_int, [_p, _int]),
+    "mnw_profile_summary": (_int, [_p, C.c_char_p, _i64]),
     "mnw_last_path": (_int, [_p]),
     "mnw_force_generic": (None, [_p, _int]),
 }
@@ -172,6 +177,18 @@ class Context:
     @property
     def last_path(self):
         return int(self.lib.mnw_last_path(self.h))
+
+    def profile(self, on=True):
+        self._check(self.lib.mnw_profile(self.h, int(on)))
+
+    def profile_summary(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.mnw_profile_summary(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
+    def scan_offsets_dev(self, nbytes, nblocks, base, offsets, total):
+        self._check(self.lib.mnw_scan_offsets_dev(self.h, _ptr(nbytes), nblocks, base, _ptr(offsets), _ptr(total)))
 
     def force_generic(self, on=True):
         self.lib.mnw_force_generic(self.h, int(on))
@@ -305,16 +322,29 @@ class Context:
         self._check(self.lib.mnw_decode_int_blocks_dev(self.h, _ptr(data), data_len, _ptr(offsets), _ptr(mins),
                                                        _ptr(bits), n, nsel, _ptr(sel), _ptr(out)))
 
+    def vec3_limits(self, aos, nfiles=1, dev=False):
+        """minp.Writer.Vectors limits of non-periodic fields (go/minp/minp.go:92-95) -> lo, hi [nfiles, 3]"""
+        lo, hi = np.zeros((nfiles, 3), np.float32), np.zeros((nfiles, 3), np.float32)
+        if dev:
+            npart = aos.numel() // (3 * nfiles)
+            self._check(self.lib.mnw_vec3_limits_dev(self.h, _ptr(aos), npart, nfiles, _ptr(lo), _ptr(hi)))
+        else:
+            aos = _np(aos, np.float32).reshape(-1)
+            npart = len(aos) // (3 * nfiles)
+            self._check(self.lib.mnw_vec3_limits(self.h, _ptr(aos), npart, nfiles, _ptr(lo), _ptr(hi)))
+        return lo, hi
+
     def encode_vec3_subcells_dev(self, descs, aos, nfile, subcells, nfiles, mins, bits, offsets, out,
                                  out_axis_stride, out_len):
-        d3 = (FloatDesc * 3)(*descs)
-        self._check(self.lib.mnw_encode_vec3_subcells_dev(self.h, d3, _ptr(aos), nfile, subcells, nfiles,
+        """descs: 3 FloatDesc (shared) or 3*nfiles (per file)"""
+        d3 = (FloatDesc * len(descs))(*descs)
+        self._check(self.lib.mnw_encode_vec3_subcells_dev(self.h, d3, int(len(descs) != 3), _ptr(aos), nfile, subcells, nfiles,
                                                           _ptr(mins), _ptr(bits), _ptr(offsets), _ptr(out),
                                                           out_axis_stride, _ptr(out_len)))
 
     def decode_vec3_subcells_dev(self, descs, data, data_axis_stride, offsets, mins, bits, nfile, subcells,
                                  nfiles, wrap_L, jitter, aos_out):
-        d3 = (FloatDesc * 3)(*descs)
-        self._check(self.lib.mnw_decode_vec3_subcells_dev(self.h, d3, _ptr(data), data_axis_stride, _ptr(offsets),
+        d3 = (FloatDesc * len(descs))(*descs)
+        self._check(self.lib.mnw_decode_vec3_subcells_dev(self.h, d3, int(len(descs) != 3), _ptr(data), data_axis_stride, _ptr(offsets),
                                                           _ptr(mins), _ptr(bits), nfile, subcells, nfiles, wrap_L,
                                                           C.byref(jitter), _ptr(aos_out)))

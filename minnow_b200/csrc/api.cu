@@ -49,7 +49,7 @@ struct mnw_ctx {
     std::string err;
     int last_path = 0;
     int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
 };
 
@@ -80,13 +80,26 @@ int check_desc(mnw_ctx *ctx, const mnw_float_desc *d) {
 }
 
 FloatParamsHost to_params(const mnw_float_desc &d) {
-    FloatParamsHost p;
+    FloatParamsHost p = {};
     p.low = d.low; p.high = d.high; p.pixels = d.pixels;
     volatile float span = d.high - d.low;           // go/group.go:316, float32 arithmetic
     p.dx = span / (float)d.pixels;
     p.hi_clamp = nextafterf(d.high, -INFINITY);      // go/minh/minh.go:146
     p.flags = (d.periodic ? F_PERIODIC : 0) | (d.log10 ? F_LOG10 : 0) | (d.clamp ? F_CLAMP : 0);
     return p;
+}
+
+// Upload a table of group parameters; returns the device pointer through *tab.
+int upload_params(mnw_ctx *ctx, const mnw_float_desc *desc, int64_t count, std::vector<FloatParams> &host,
+                  const FloatParams **tab) {
+    host.resize((size_t)count);
+    for (int64_t i = 0; i < count; i++) host[(size_t)i] = to_params(desc[i]);
+    CU(ctx->params.reserve(sizeof(FloatParams) * (size_t)count));
+    // pageable source: the runtime stages it before returning, so `host` may die after the call
+    CU(cudaMemcpyAsync(ctx->params.p, host.data(), sizeof(FloatParams) * (size_t)count, cudaMemcpyHostToDevice,
+                       ctx->L.stream));
+    *tab = ctx->params.as<FloatParams>();
+    return MNW_OK;
 }
 
 // Reserve the per-batch device records.
@@ -117,7 +130,7 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
                      int64_t total_tiles, int64_t total_chunks, int64_t *mins, int64_t *bits, int64_t *offsets,
                      uint8_t *out, int64_t out_cap, int64_t *out_len) {
     if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
-    FloatParamsHost fp;
+    FloatParamsHost fp = {};
     if (kind == KIND_F32) {
         int rc = check_desc(ctx, desc);
         if (rc) return rc;
@@ -217,13 +230,12 @@ int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const 
     return MNW_OK;
 }
 
-int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, int naxes, const mnw_jitter *jitter) {
-    for (int k = 0; k < naxes; k++) {
-        int rc = check_desc(ctx, &desc[k]);
-        if (rc) return rc;
-        FloatParamsHost p = to_params(desc[k]);
-        h.low[k] = p.low; h.dx[k] = p.dx; h.pixels[k] = p.pixels; h.periodic[k] = desc[k].periodic ? 1 : 0;
-    }
+int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, int64_t ndesc, const mnw_jitter *jitter) {
+    int rc = check_desc(ctx, desc);
+    if (rc) return rc;
+    std::vector<FloatParams> host;
+    rc = upload_params(ctx, desc, ndesc, host, &h.tab);
+    if (rc) return rc;
     if (jitter) {
         if (jitter->mode < 0 || jitter->mode > 2) return fail(ctx, MNW_ERR_ARG, "unknown jitter mode %d", jitter->mode);
         h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0;
@@ -342,7 +354,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws})
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     cudaStreamDestroy(ctx->L.stream);
@@ -498,17 +510,18 @@ int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const 
     return MNW_OK;
 }
 
-int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
-                                 int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
+int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file, const float *aos,
+                                 int64_t nfile, int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
                                  int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0 || nfile > 2048)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
-    FloatParamsHost fp[3];
-    for (int k = 0; k < 3; k++) {
-        int rc = check_desc(ctx, &desc[k]);
-        if (rc) return rc;
-        fp[k] = to_params(desc[k]);
-    }
+    int rc0 = check_desc(ctx, desc);
+    if (rc0) return rc0;
+    const int64_t ndesc = desc_per_file ? 3 * nfiles : 3;
+    std::vector<FloatParams> fp;
+    const FloatParams *tab = nullptr;
+    rc0 = upload_params(ctx, desc, ndesc, fp, &tab);
+    if (rc0) return rc0;
     const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells, n = nsub * nsub * nsub;
     const int64_t nb = nfiles * 3 * sc3;
     int rc = reserve_batch(ctx, nb, 3 * nfiles);
@@ -517,10 +530,10 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], con
     CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
     if (nb == 0) return MNW_OK;
 
-    if (!ctx->force_generic && fused_vec3_supported(fp, (int)nfile, (int)subcells)) {
+    if (!ctx->force_generic && fused_vec3_supported(fp.data(), ndesc, (int)nfile, (int)subcells)) {
         ctx->last_path = 1;
-        cudaError_t e = launch_fused_vec3(ctx->L, fp, aos, (int)nfile, (int)subcells, nfiles, mins, bits, offsets,
-                                          out_len, out, out_axis_stride, d_flags);
+        cudaError_t e = launch_fused_vec3(ctx->L, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles, mins,
+                                          bits, offsets, out_len, out, out_axis_stride, d_flags);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
         return MNW_OK;
     }
@@ -530,7 +543,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], con
     sh.total_tiles = nb * ((n + PACK_TILE - 1) / PACK_TILE);
     sh.total_chunks = nb * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
     if (sh.total_tiles >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
-    launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, fp);
+    launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, tab, desc_per_file);
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
                           out_axis_stride, out_axis_stride);
@@ -538,7 +551,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], con
     return MNW_OK;
 }
 
-int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *data,
+int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file, const uint8_t *data,
                                  int64_t data_axis_stride, const int64_t *offsets, const int64_t *mins,
                                  const int64_t *bits, int64_t nfile, int64_t subcells, int64_t nfiles,
                                  float wrap_L, const mnw_jitter *jitter, float *aos_out) {
@@ -546,7 +559,8 @@ int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc desc[3], con
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     DecodeHost h;
     h.mode = 2;
-    int rc = fill_decode_float(ctx, h, desc, 3, jitter);
+    h.tab_per_file = desc_per_file;
+    int rc = fill_decode_float(ctx, h, desc, desc_per_file ? 3 * nfiles : 3, jitter);
     if (rc) return rc;
     if (h.jmode == 2) return fail(ctx, MNW_ERR_ARG, "vec3 decode supports jitter modes CENTER and HASH");
     const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells;
@@ -572,7 +586,7 @@ int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const f
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));
     int64_t *d_meta = ctx->meta.as<int64_t>();
-    rc = mnw_encode_vec3_subcells_dev(ctx, desc, ctx->in.as<float>(), nfile, subcells, 1, d_meta, d_meta + nb,
+    rc = mnw_encode_vec3_subcells_dev(ctx, desc, 0, ctx->in.as<float>(), nfile, subcells, 1, d_meta, d_meta + nb,
                                       d_meta + 2 * nb, ctx->out.as<uint8_t>(), stride, d_meta + 3 * nb);
     if (rc) return rc;
     std::vector<int64_t> h_meta(3 * (size_t)nb + 3);
@@ -621,12 +635,83 @@ int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const u
     CU(cudaMemcpyAsync(d_meta, offsets, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
     CU(cudaMemcpyAsync(d_meta + nb, mins, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
     CU(cudaMemcpyAsync(d_meta + 2 * nb, bits, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
-    int rc = mnw_decode_vec3_subcells_dev(ctx, desc, ctx->in.as<uint8_t>(), stride, d_meta, d_meta + nb, d_meta + 2 * nb,
+    int rc = mnw_decode_vec3_subcells_dev(ctx, desc, 0, ctx->in.as<uint8_t>(), stride, d_meta, d_meta + nb, d_meta + 2 * nb,
                                           nfile, subcells, 1, wrap_L, jitter, ctx->dec_out.as<float>());
     if (rc) return rc;
     CU(cudaMemcpyAsync(aos_out, ctx->dec_out.p, 12 * (size_t)np, cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(cudaStreamSynchronize(ctx->L.stream));
     return MNW_OK;
+}
+
+int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base, int64_t *offsets,
+                         int64_t *total) {
+    if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
+    cudaError_t e = launch_scan_sizes(ctx->L, nbytes, nblocks, base, offsets, total);
+    if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
+    return MNW_OK;
+}
+
+int mnw_profile(mnw_ctx *ctx, int on) {
+    ctx->L.prof = on != 0;
+    return MNW_OK;
+}
+
+int mnw_profile_summary(mnw_ctx *ctx, char *buf, int64_t cap) {
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    struct Agg { const char *name; int64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (ProfRec &r : ctx->L.recs) {
+        float ms = 0;
+        if (r.a && r.b && cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        bool found = false;
+        for (Agg &a : agg) if (!strcmp(a.name, r.name)) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({r.name, 1, (double)ms});
+    }
+    ctx->L.recs.clear();
+    std::string s = "[";
+    for (size_t i = 0; i < agg.size(); i++) {
+        char line[256];
+        snprintf(line, sizeof line, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f}", i ? ", " : "",
+                 agg[i].name, (long long)agg[i].n, agg[i].ms);
+        s += line;
+    }
+    s += "]";
+    if ((int64_t)s.size() + 1 > cap) return fail(ctx, MNW_ERR_CAPACITY, "profile summary needs %zu bytes", s.size() + 1);
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return MNW_OK;
+}
+
+static inline float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int mnw_vec3_limits_dev(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi) {
+    if (np <= 0 || nfiles < 0) return fail(ctx, MNW_ERR_ARG, "vec3 limits of an empty cube (the reference indexes vec[0])");
+    if ((np + 32767) / 32768 >= 65536LL * 32768 || nfiles > 65535) return fail(ctx, MNW_ERR_ARG, "too many files in one call");
+    CU(ctx->aux.reserve(24 * (size_t)nfiles + 64));
+    launch_vec3_limits(ctx->L, aos, np, nfiles, ctx->aux.as<uint32_t>());
+    CU(cudaGetLastError());
+    std::vector<uint32_t> keys(6 * (size_t)nfiles);
+    CU(cudaMemcpyAsync(keys.data(), ctx->aux.p, 24 * (size_t)nfiles, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    for (int64_t f = 0; f < nfiles; f++)
+        for (int k = 0; k < 3; k++) {
+            float mn = key_to_float(keys[6 * f + k]), mx = key_to_float(keys[6 * f + 3 + k]);
+            lo[3 * f + k] = mn;
+            hi[3 * f + k] = nextafterf(mx, 2 * mx);  // go/minp/minp.go:94
+        }
+    return MNW_OK;
+}
+
+int mnw_vec3_limits(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi) {
+    if (np <= 0 || nfiles < 0) return fail(ctx, MNW_ERR_ARG, "vec3 limits of an empty cube (the reference indexes vec[0])");
+    CU(ctx->in.reserve(12 * (size_t)(np * nfiles) + 16));
+    CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)(np * nfiles), cudaMemcpyHostToDevice, ctx->L.stream));
+    return mnw_vec3_limits_dev(ctx, ctx->in.as<float>(), np, nfiles, lo, hi);
 }
 
 }  // extern "C"

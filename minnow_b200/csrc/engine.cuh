@@ -46,6 +46,14 @@ struct __align__(16) BlockStat {
     int bits;                       // what the reference appends to g.bits
 };
 
+// Parameters of one FloatGroup as the kernels use them (device table entry).
+struct FloatParams {
+    float low, high, dx, hi_clamp;
+    int64_t pixels;
+    int32_t flags;
+    int32_t pad;
+};
+
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_CHUNK = 16384;   // elements per k_stats CTA
 constexpr int PACK_THREADS = 128;

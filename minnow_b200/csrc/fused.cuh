@@ -14,8 +14,8 @@ cudaError_t launch_fused_group(Launcher &L, void *ws, size_t ws_cap, const Float
                                int64_t *out_len, uint8_t *out, int64_t out_cap, int *flags);
 
 // minp sub-cell gather + 3-axis encode.
-bool fused_vec3_supported(const FloatParamsHost fp[3], int nfile, int subcells);
-cudaError_t launch_fused_vec3(Launcher &L, const FloatParamsHost fp[3], const float *aos, int nfile, int subcells,
+bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile, int subcells);
+cudaError_t launch_fused_vec3(Launcher &L, const FloatParams *tab, int tab_per_file, const float *aos, int nfile, int subcells,
                               int64_t nfiles, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
                               uint8_t *out, int64_t out_axis_stride, int *flags);
 

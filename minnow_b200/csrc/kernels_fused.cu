@@ -8,8 +8,8 @@ cudaError_t launch_fused_group(Launcher &, void *, size_t, const FloatParamsHost
                                int64_t *, int64_t *, int64_t *, int64_t *, uint8_t *, int64_t, int *) {
     return cudaErrorNotSupported;
 }
-bool fused_vec3_supported(const FloatParamsHost[3], int, int) { return false; }
-cudaError_t launch_fused_vec3(Launcher &, const FloatParamsHost[3], const float *, int, int, int64_t, int64_t *,
+bool fused_vec3_supported(const FloatParamsHost *, int64_t, int, int) { return false; }
+cudaError_t launch_fused_vec3(Launcher &, const FloatParams *, int, const float *, int, int, int64_t, int64_t *,
                               int64_t *, int64_t *, int64_t *, uint8_t *, int64_t, int *) {
     return cudaErrorNotSupported;
 }

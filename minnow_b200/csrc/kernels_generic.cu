@@ -92,12 +92,6 @@ __device__ __forceinline__ unsigned long long arc_rotation(long long q0, long lo
 // ---------------------------------------------------------------------------
 // descriptor builders
 // ---------------------------------------------------------------------------
-struct FloatParams {
-    float low, high, dx, hi_clamp;
-    int64_t pixels;
-    int32_t flags;
-};
-
 __global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                                const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
                                FloatParams fp, int64_t blocks_per_chain) {
@@ -122,7 +116,7 @@ __global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const
 
 // minp.Writer.Vectors block order: per file f, axis k, sub-cell sc (go/minp/minp.go:112-118)
 __global__ void k_build_vec3(BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
-                             int32_t subcells, FloatParams fx, FloatParams fy, FloatParams fz) {
+                             int32_t subcells, const FloatParams *tab, int tab_per_file) {
     int64_t sc3 = (int64_t)subcells * subcells * subcells;
     int64_t nb = nfiles * 3 * sc3;
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -131,7 +125,7 @@ __global__ void k_build_vec3(BlockDesc *descs, int64_t nfiles, const float *aos,
     int32_t k = (int32_t)((b / sc3) % 3);
     int64_t sc = b % sc3;
     int32_t nsub = nfile / subcells;
-    const FloatParams &fp = k == 0 ? fx : (k == 1 ? fy : fz);
+    const FloatParams fp = tab[(tab_per_file ? 3 * f : 0) + k];
     BlockDesc d = {};
     d.src = aos + 3 * f * (int64_t)nfile * nfile * nfile;
     d.n = (int64_t)nsub * nsub * nsub;
@@ -349,6 +343,56 @@ k_slow(const BlockDesc *descs, BlockStat *stats, const int64_t *slow_list, const
 }
 
 // ---------------------------------------------------------------------------
+// bounds() of minp.Writer.Vectors for non-periodic fields, go/minp/minp.go:291-300.
+// float min/max through order-preserving uint32 keys and 32-bit atomics.
+// ---------------------------------------------------------------------------
+constexpr int LIMITS_CHUNK = 32768;  // particles per CTA
+__device__ __forceinline__ uint32_t float_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void k_limits_init(uint32_t *keys, int64_t nfiles) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nfiles * 6) keys[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+__global__ void __launch_bounds__(256) k_vec3_limits(const float *__restrict__ aos, int64_t np, uint32_t *keys) {
+    const int64_t f = blockIdx.y;
+    const float *base = aos + 3 * f * np;
+    int64_t p0 = (int64_t)blockIdx.x * LIMITS_CHUNK;
+    int64_t p1 = p0 + LIMITS_CHUNK < np ? p0 + LIMITS_CHUNK : np;
+    uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    // thread t reads floats t, t+256, ...; component = index % 3
+    for (int64_t i = 3 * p0 + threadIdx.x; i < 3 * p1; i += 256 * 3) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            int64_t ii = i + 256 * j;
+            if (ii < 3 * p1) {
+                float v = base[ii];
+                if (v == v) {  // NaN never wins a comparison in bounds()
+                    uint32_t key = float_key(v);
+                    int c = (int)(ii % 3);
+                    if (c == 0) { mn[0] = min(mn[0], key); mx[0] = max(mx[0], key); }
+                    else if (c == 1) { mn[1] = min(mn[1], key); mx[1] = max(mx[1], key); }
+                    else { mn[2] = min(mn[2], key); mx[2] = max(mx[2], key); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        mn[c] = __reduce_min_sync(0xffffffffu, mn[c]);
+        mx[c] = __reduce_max_sync(0xffffffffu, mx[c]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            atomicMin(&keys[f * 6 + c], mn[c]);
+            atomicMax(&keys[f * 6 + 3 + c], mx[c]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // scan: one CTA per chain (= minnow group); exclusive prefix of nbytes
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -507,9 +551,8 @@ struct DecodeArgs {
     int64_t stream_len;       // bytes per stream (group: data_len; vec3: axis stride)
     const int64_t *offsets, *mins, *bits, *sel, *jitter_ids;
     int64_t n, nsel;
-    float low[3], dx[3];
-    int64_t pixels[3];
-    int periodic[3];
+    const FloatParams *tab;
+    int tab_per_file;
     float wrap_L;
     int jmode;
     unsigned long long seed, block_id0;
@@ -536,8 +579,13 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
         sc = b % A.sc3;
         stream += (b / A.sc3) * A.stream_len;    // stream (3f + k)
     }
-    const long long P = A.pixels[k];
-    const float low = A.low[k], dx = A.dx[k];
+    long long P = 0;
+    float low = 0.f, dx = 0.f;
+    bool periodic = false;
+    if (A.mode != 0) {
+        const FloatParams fp = A.tab[(A.tab_per_file ? 3 * f : 0) + k];
+        P = fp.pixels; low = fp.low; dx = fp.dx; periodic = fp.flags & F_PERIODIC;
+    }
     const int64_t end = (c + 1) * DEC_CHUNK < A.n ? (c + 1) * DEC_CHUNK : A.n;
     for (int64_t i = c * DEC_CHUNK + threadIdx.x; i < end; i += DEC_THREADS) {
         unsigned long long v = bits ? extract_bits(stream, A.stream_len, off, i, bits) : 0ULL;
@@ -546,7 +594,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
             ((long long *)A.out)[j * A.n + i] = q;
             continue;
         }
-        if (A.periodic[k]) q = bound1(q, 0, P);              // go/group.go:303
+        if (periodic) q = bound1(q, 0, P);              // go/group.go:303
         double u = 0.5;
         if (A.jmode == 1) u = (double)jitter_hash32(A.seed, A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b), (unsigned long long)i) * 0x1p-32;
         else if (A.jmode == 2) u = A.u[j * A.n + i];
@@ -637,18 +685,26 @@ void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
                          const FloatParamsHost &fp, int64_t blocks_per_chain) {
     if (nb == 0) return;
-    FloatParams p = {fp.low, fp.high, fp.dx, fp.hi_clamp, fp.pixels, fp.flags};
-    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, p, blocks_per_chain);
+    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, fp, blocks_per_chain);
     L.count++;
 }
 
 void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
-                       int32_t subcells, const FloatParamsHost fp[3]) {
+                       int32_t subcells, const FloatParams *tab, int tab_per_file) {
     int64_t nb = nfiles * 3 * (int64_t)subcells * subcells * subcells;
     if (nb == 0) return;
-    FloatParams p[3];
-    for (int k = 0; k < 3; k++) p[k] = {fp[k].low, fp[k].high, fp[k].dx, fp[k].hi_clamp, fp[k].pixels, fp[k].flags};
-    k_build_vec3<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nfiles, aos, nfile, subcells, p[0], p[1], p[2]);
+    k_build_vec3<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nfiles, aos, nfile, subcells, tab, tab_per_file);
+    L.count++;
+}
+
+void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int64_t nfiles, uint32_t *keys) {
+    if (nfiles == 0) return;
+    k_limits_init<<<grid_for(nfiles * 6, 256), 256, 0, L.stream>>>(keys, nfiles);
+    L.count++;
+    if (np_per_file == 0) return;
+    int64_t chunks = (np_per_file + LIMITS_CHUNK - 1) / LIMITS_CHUNK;
+    dim3 grid((unsigned)chunks, (unsigned)nfiles);
+    k_vec3_limits<<<grid, 256, 0, L.stream>>>(aos, np_per_file, keys);
     L.count++;
 }
 
@@ -661,7 +717,9 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks);
     L.count++;
     if (sh.total_chunks > 0) {
+        L.begin("k_stats");
         k_stats<<<(unsigned)sh.total_chunks, STATS_THREADS, 0, L.stream>>>(descs, stats, sh);
+        L.end();
         L.count++;
     }
     k_finalize<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, slow_list, slow_count, err);
@@ -672,7 +730,9 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len);
     L.count++;
     if (sh.total_tiles > 0) {
+        L.begin("k_pack");
         k_pack<<<(unsigned)sh.total_tiles, PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err);
+        L.end();
         L.count++;
     }
 }
@@ -709,13 +769,15 @@ void launch_decode(Launcher &L, const DecodeHost &h) {
     A.mode = h.mode; A.data = h.data; A.stream_len = h.stream_len;
     A.offsets = h.offsets; A.mins = h.mins; A.bits = h.bits; A.sel = h.sel; A.jitter_ids = h.jitter_ids;
     A.n = h.n; A.nsel = h.nsel;
-    for (int k = 0; k < 3; k++) { A.low[k] = h.low[k]; A.dx[k] = h.dx[k]; A.pixels[k] = h.pixels[k]; A.periodic[k] = h.periodic[k]; }
+    A.tab = h.tab; A.tab_per_file = h.tab_per_file;
     A.wrap_L = h.wrap_L; A.jmode = h.jmode; A.seed = h.seed; A.block_id0 = h.block_id0; A.u = h.u;
     A.nfile = h.nfile; A.nsub = h.subcells ? h.nfile / h.subcells : 0; A.subcells = h.subcells;
     A.sc3 = (int64_t)h.subcells * h.subcells * h.subcells;
     A.out = h.out;
     int64_t cpb = (h.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    L.begin("k_decode");
     k_decode<<<(unsigned)(h.nsel * cpb), DEC_THREADS, 0, L.stream>>>(A);
+    L.end();
     L.count++;
 }
 

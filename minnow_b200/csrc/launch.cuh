@@ -2,21 +2,39 @@
 // translation units.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 #include "engine.cuh"
 
 namespace mnw {
 
+// Optional per-kernel timing with CUDA events on the launching stream
+// (mnw_profile): the roofline figure of bench.py is read from here.
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+
 struct Launcher {
     cudaStream_t stream = nullptr;
     int64_t count = 0;  // kernels launched (reported by mnw_launch_count)
+    bool prof = false;
+    std::vector<ProfRec> recs;
+    void begin(const char *name) {
+        if (!prof) return;
+        ProfRec r = {name, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        recs.push_back(r);
+    }
+    void end() {
+        if (!prof) return;
+        cudaEventRecord(recs.back().b, stream);
+    }
 };
 
-struct FloatParamsHost {
-    float low = 0, high = 0, dx = 0, hi_clamp = 0;
-    int64_t pixels = 0;
-    int32_t flags = 0;
-};
+using FloatParamsHost = FloatParams;
 
 struct DecodeHost {
     int mode = 0;
@@ -25,9 +43,8 @@ struct DecodeHost {
     const int64_t *offsets = nullptr, *mins = nullptr, *bits = nullptr, *sel = nullptr;
     const int64_t *jitter_ids = nullptr;  // original block ids for the hash jitter when sel was compacted away
     int64_t n = 0, nsel = 0;
-    float low[3] = {0, 0, 0}, dx[3] = {0, 0, 0};
-    int64_t pixels[3] = {0, 0, 0};
-    int periodic[3] = {0, 0, 0};
+    const FloatParams *tab = nullptr;  // device table: 1 entry (group), 3 (vec3) or 3*nfiles (vec3, per file)
+    int tab_per_file = 0;
     float wrap_L = 0;
     int jmode = 0;
     unsigned long long seed = 0, block_id0 = 0;
@@ -41,7 +58,10 @@ void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
                          const FloatParamsHost &fp, int64_t blocks_per_chain);
 void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
-                       int32_t subcells, const FloatParamsHost fp[3]);
+                       int32_t subcells, const FloatParams *tab, int tab_per_file);
+// bounds() of minp.Writer.Vectors (go/minp/minp.go:291-300): keys[f*6 + k] = min, [f*6 + 3 + k] = max,
+// as order-preserving uint32 keys (decode with key_to_float on the host).
+void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int64_t nfiles, uint32_t *keys);
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
