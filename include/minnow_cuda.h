@@ -129,8 +129,9 @@ MNW_API int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, con
  * (go/group.go:308), so the reference's decoded floats are not reproducible.
  * The stream is explicit here:
  *   mode MNW_JITTER_CENTER: u = 0.5
- *   mode MNW_JITTER_HASH  : u = mnw_jitter_hash32(seed, block_id, i) * 2^-32,
- *                           block_id = block_id0 + sel[j]
+ *   mode MNW_JITTER_HASH  : u = (mnw_jitter_hash32(seed, block_id, i) >> 8) * 2^-24,
+ *                           block_id = block_id0 + sel[j]  (24 bits: u is exact in
+ *                           float32 and float64(q) + u is exact for q < 2^29)
  *   mode MNW_JITTER_STREAM: u = u_stream[j*n + i]   (caller's doubles in [0,1))
  * out = dx*float32(float64(q) + u) + low in float32 without FMA, as in Go.
  */
@@ -231,6 +232,14 @@ MNW_API int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nb
  * [{"kernel": name, "launches": n, "ms": total}, ...] into buf and clears the log. */
 MNW_API int mnw_profile(mnw_ctx *ctx, int on);
 MNW_API int mnw_profile_summary(mnw_ctx *ctx, char *buf, int64_t cap);
+
+/* Diagnostic: the fused kernels replace the IEEE float32 divide of go/group.go:319 by a
+ * multiply with RN(1/dx) and two FMA corrections, and use the result only when the pixel
+ * index lands in [1, pixels).  This runs both on every float32 bit pattern in
+ * [first_bits, first_bits + count) and reports how many accepted results differ from the
+ * divide (must be 0) and how many were accepted. */
+MNW_API int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t first_bits, uint64_t count,
+                                 uint64_t *mismatches, uint64_t *accepted);
 
 /* Which device path the last encode on ctx took: 0 = generic two-pass,
  * 1 = fused single-read cluster kernel.  For tests and the benchmark. */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mnw_stream": (_p, [_p]),
     "mnw_version": (C.c_char_p, []),
     "mnw_launch_count": (_i64, [_p]),
+    "mnw_selftest_fastdiv": (_int, [_p, _FD, C.c_uint32, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
     "mnw_pack": (_int, [_p, _int, _p, _i64, _p]),
@@ -189,6 +190,12 @@ class Context:
 
     def scan_offsets_dev(self, nbytes, nblocks, base, offsets, total):
         self._check(self.lib.mnw_scan_offsets_dev(self.h, _ptr(nbytes), nblocks, base, _ptr(offsets), _ptr(total)))
+
+    def selftest_fastdiv(self, desc, first_bits=0, count=1 << 32):
+        """-> (mismatches, accepted) of the fast quantiser against the IEEE divide"""
+        bad, acc = _u64(0), _u64(0)
+        self._check(self.lib.mnw_selftest_fastdiv(self.h, C.byref(desc), first_bits, count, C.byref(bad), C.byref(acc)))
+        return bad.value, acc.value
 
     def force_generic(self, on=True):
         self.lib.mnw_force_generic(self.h, int(on))

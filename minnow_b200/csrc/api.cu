@@ -86,6 +86,10 @@ FloatParamsHost to_params(const mnw_float_desc &d) {
     p.dx = span / (float)d.pixels;
     p.hi_clamp = nextafterf(d.high, -INFINITY);      // go/minh/minh.go:146
     p.flags = (d.periodic ? F_PERIODIC : 0) | (d.log10 ? F_LOG10 : 0) | (d.clamp ? F_CLAMP : 0);
+    volatile float rcp = 1.0f / p.dx;                // correctly rounded reciprocal (quantize_fast)
+    p.rcp = rcp;
+    if (std::isnormal(p.dx) && std::isnormal(p.rcp) && p.dx > 0x1p-60f && p.dx < 0x1p60f && d.pixels >= 2)
+        p.flags |= F_FASTDIV;
     return p;
 }
 
@@ -156,14 +160,6 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
     if (sh.total_tiles >= (1LL << 31) || sh.total_chunks >= (1LL << 31))
         return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
 
-    if (!ctx->force_generic && kind == KIND_F32 && !d_starts &&
-        fused_group_supported(fp, n, nblocks)) {
-        ctx->last_path = 1;
-        cudaError_t e = launch_fused_group(ctx->L, ctx->fused_ws.p, ctx->fused_ws.cap, fp, (const float *)x, n, nblocks,
-                                           mins, bits, offsets, out_len, out, out_cap, d_flags);
-        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused group encode: %s", cudaGetErrorString(e));
-        return MNW_OK;
-    }
     ctx->last_path = 0;
     launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks);
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
@@ -530,20 +526,35 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
     CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
     if (nb == 0) return MNW_OK;
 
-    if (!ctx->force_generic && fused_vec3_supported(fp.data(), ndesc, (int)nfile, (int)subcells)) {
-        ctx->last_path = 1;
-        cudaError_t e = launch_fused_vec3(ctx->L, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles, mins,
-                                          bits, offsets, out_len, out, out_axis_stride, d_flags);
-        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
-        return MNW_OK;
-    }
-    ctx->last_path = 0;
     BatchShape sh = {};
     sh.nblocks = nb; sh.nchains = 3 * nfiles; sh.blocks_per_chain = sc3; sh.uniform_n = n;
     sh.total_tiles = nb * ((n + PACK_TILE - 1) / PACK_TILE);
     sh.total_chunks = nb * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
     if (sh.total_tiles >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
     launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, tab, desc_per_file);
+
+    if (!ctx->force_generic && fused_vec3_supported(fp.data(), ndesc, (int)nfile, (int)subcells, aos)) {
+        ctx->last_path = 1;
+        CU(ctx->fused_ws.reserve(fused_work_bytes(nb)));
+        FusedWork W = {};
+        W.pub = ctx->fused_ws.as<unsigned long long>();
+        W.repack_list = (int64_t *)(W.pub + nb);
+        W.err = d_flags + 1; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
+        CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
+        cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
+                                          ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
+        // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
+        launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,
+                         out, out_axis_stride, out_axis_stride, d_flags + 1);
+        // blocks that need the exact sequential periodicMin: the whole call again, generically
+        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                              ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
+                              out_axis_stride, out_axis_stride, W.abort_flag);
+        CU(cudaGetLastError());
+        return MNW_OK;
+    }
+    ctx->last_path = 0;
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
                           out_axis_stride, out_axis_stride);
@@ -567,6 +578,11 @@ int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
     h.data = data; h.stream_len = data_axis_stride; h.offsets = offsets; h.mins = mins; h.bits = bits;
     h.n = nsub * nsub * nsub; h.nsel = nfiles * 3 * sc3; h.wrap_L = wrap_L;
     h.nfile = (int32_t)nfile; h.subcells = (int32_t)subcells; h.out = aos_out;
+    if (!ctx->force_generic && fused_decode_vec3_supported((int)nfile, (int)subcells, aos_out)) {
+        cudaError_t e = launch_fused_decode_vec3(ctx->L, h, nfiles);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 decode: %s", cudaGetErrorString(e));
+        return MNW_OK;
+    }
     launch_decode(ctx->L, h);
     CU(cudaGetLastError());
     return MNW_OK;
@@ -648,6 +664,22 @@ int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, i
     if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
     cudaError_t e = launch_scan_sizes(ctx->L, nbytes, nblocks, base, offsets, total);
     if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
+    return MNW_OK;
+}
+
+int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t first_bits, uint64_t count,
+                         uint64_t *mismatches, uint64_t *accepted) {
+    int rc = check_desc(ctx, desc);
+    if (rc) return rc;
+    if ((uint64_t)first_bits + count > (1ULL << 32)) return fail(ctx, MNW_ERR_ARG, "bit pattern range exceeds 2^32");
+    CU(ctx->meta.reserve(64));
+    launch_selftest_fastdiv(ctx->L, to_params(*desc), first_bits, count, ctx->meta.as<unsigned long long>());
+    CU(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, ctx->meta.p, 16, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    if (mismatches) *mismatches = h[0];
+    if (accepted) *accepted = h[1];
     return MNW_OK;
 }
 

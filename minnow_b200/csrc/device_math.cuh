@@ -105,6 +105,23 @@ MNW_D long long quantize_exact(float v, float low, float dx) {
     return go_float_to_i64(floorf(r));
 }
 
+// The same pixel index without the IEEE divide, for dx flagged F_FASTDIV (normal,
+// 2^-60 < dx < 2^60): y = t * r with r = RN(1/dx), then two Markstein corrections
+// y <- RN(y + RN(t - dx*y) * r); the residual is exact in an FMA, the first
+// correction makes y a faithful quotient and the second one the correctly rounded
+// quotient, which is what __fdiv_rn returns.  Callers accept the result only when
+// it lands in [1, pixels) -- tiny, negative, huge and NaN quotients take
+// quantize_exact -- and tests/test_gpu_parity.py checks it against __fdiv_rn.
+MNW_D int quantize_fast(float v, float low, float rcp, float ndx /* = -dx */) {
+    float t = __fsub_rn(v, low);
+    float y = __fmul_rn(t, rcp);
+    float e = __fmaf_rn(ndx, y, t);
+    y = __fmaf_rn(e, rcp, y);
+    e = __fmaf_rn(ndx, y, t);
+    y = __fmaf_rn(e, rcp, y);
+    return __float2int_rd(y);
+}
+
 // minh processFloatGroup, go/minh/minh.go:141-149 (hi_clamp = Nextafter32(High, -Inf)).
 MNW_D float minh_pre(float v, bool is_log, bool clamp, float low, float high, float hi_clamp) {
     if (is_log) v = __double2float_rn(go_log10((double)v));
@@ -129,6 +146,16 @@ MNW_HD long long periodic_distance(long long x, long long x0, long long pixels) 
     return d;
 }
 
+// Rotation constant of the periodic-arc statistic.  With half = P/2 and
+// K = P - half - 1, w(q) = (q - q0 + K) mod P orders pixel indices by their
+// signed periodic distance to q0 (go/group.go:412-420): dist = w - K.
+MNW_HD unsigned long long arc_rotation(long long q0, long long P) {
+    long long K = P - P / 2 - 1;
+    long long c = K - q0;
+    if (c < 0) c += P;
+    return (unsigned long long)c;
+}
+
 // go/group.go:374-382 bound, one element.
 MNW_HD long long bound1(long long x, long long mn, long long pixels) {
     if (x < mn) return (long long)((unsigned long long)x + (unsigned long long)pixels);
@@ -144,10 +171,16 @@ MNW_HD uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
     return x;
 }
+// key: once per block; hash: one lowbias32 round over a Weyl sequence in i.
+MNW_HD uint32_t jitter_key(unsigned long long seed, unsigned long long block) {
+    uint32_t k = mix32((uint32_t)(seed >> 32));
+    k = mix32((uint32_t)seed ^ k);
+    k = mix32((uint32_t)(block >> 32) ^ k);
+    return mix32((uint32_t)block ^ k);
+}
+MNW_HD uint32_t jitter_hash_keyed(uint32_t key, uint32_t i) { return mix32(i * 0x9E3779B1U + key); }
 MNW_HD uint32_t jitter_hash32(unsigned long long seed, unsigned long long block, unsigned long long i) {
-    uint32_t x = mix32((uint32_t)i ^ (uint32_t)seed);
-    x += (uint32_t)block * 0x9E3779B9U + (uint32_t)(seed >> 32);
-    return mix32(x);
+    return jitter_hash_keyed(jitter_key(seed, block), (uint32_t)i);
 }
 
 }  // namespace mnw

@@ -14,7 +14,7 @@ namespace mnw {
 
 enum : int32_t { KIND_I64 = 0, KIND_F32 = 1 };
 enum : int32_t { ACC_CONTIG = 0, ACC_GATHER = 1, ACC_SUBCELL = 2 };
-enum : int32_t { F_PERIODIC = 1, F_LOG10 = 2, F_CLAMP = 4 };
+enum : int32_t { F_PERIODIC = 1, F_LOG10 = 2, F_CLAMP = 4, F_FASTDIV = 8 };
 
 struct __align__(16) BlockDesc {
     const void *src;      // CONTIG: first element; GATHER: column base; SUBCELL: AoS cube base
@@ -50,8 +50,8 @@ struct __align__(16) BlockStat {
 struct FloatParams {
     float low, high, dx, hi_clamp;
     int64_t pixels;
-    int32_t flags;
-    int32_t pad;
+    int32_t flags;   // F_* bits; F_FASTDIV: rcp may replace the IEEE divide (device_math.cuh quantize_fast)
+    float rcp;       // RN(1 / dx)
 };
 
 constexpr int STATS_THREADS = 256;

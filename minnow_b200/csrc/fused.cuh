@@ -1,4 +1,12 @@
-// fused.cuh -- single-read fused encode kernels (kernels_fused.cu).
+// fused.cuh -- single-read fused kernels (kernels_fused.cu).
+//
+// Encode: one thread-block cluster per minp sub-cell reads the sub-cell's AoS
+// rows ONCE, quantises all three axes, keeps the 16-bit rotated pixel indices in
+// (distributed) shared memory, reduces the per-block statistics across the
+// cluster, obtains the block byte offsets by decoupled look-back over the
+// sub-cells of the file, and packs straight from shared memory.
+// Decode: one CTA per slab of a sub-cell unpacks all three axes and writes whole
+// AoS rows.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -7,16 +15,32 @@
 
 namespace mnw {
 
-// One FloatGroup of nblocks equal blocks of n contiguous float32.
-bool fused_group_supported(const FloatParamsHost &fp, int64_t n, int64_t nblocks);
-cudaError_t launch_fused_group(Launcher &L, void *ws, size_t ws_cap, const FloatParamsHost &fp, const float *x,
-                               int64_t n, int64_t nblocks, int64_t *mins, int64_t *bits, int64_t *offsets,
-                               int64_t *out_len, uint8_t *out, int64_t out_cap, int *flags);
+// Device workspace of one fused encode launch (zeroed before the launch).
+struct FusedWork {
+    unsigned long long *pub;   // [nblocks] look-back words: flag (2 bits) | bytes (62 bits)
+    unsigned int *ticket;      // next unit to claim
+    int64_t *repack_list;      // blocks whose bits > 16: packed afterwards from global memory
+    int *repack_count;
+    int *abort_flag;           // some block needs the exact sequential periodicMin: rerun generically
+    int *err;
+};
 
-// minp sub-cell gather + 3-axis encode.
-bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile, int subcells);
-cudaError_t launch_fused_vec3(Launcher &L, const FloatParams *tab, int tab_per_file, const float *aos, int nfile, int subcells,
-                              int64_t nfiles, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
-                              uint8_t *out, int64_t out_axis_stride, int *flags);
+// minp sub-cell gather + 3-axis encode.  Supported when nfile/subcells is 16, 32
+// or 64, every group is periodic without minh pre-transform, and pixels < 2^30.
+bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile, int subcells, const void *aos);
+size_t fused_work_bytes(int64_t nblocks);
+cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams *tab, int tab_per_file,
+                              const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
+                              int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
+                              int64_t out_axis_stride);
+
+// 3-axis decode + periodic wrap + sub-cell scatter.
+bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out);
+cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t nfiles);
+
+// quantize_fast vs __fdiv_rn over float bit patterns [first, first + count):
+// d_out2[0] = mismatches among accepted fast results, d_out2[1] = accepted results.
+void launch_selftest_fastdiv(Launcher &L, const FloatParamsHost &fp, unsigned long long first,
+                             unsigned long long count, unsigned long long *d_out2);
 
 }  // namespace mnw

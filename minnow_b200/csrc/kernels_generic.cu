@@ -79,16 +79,6 @@ __device__ __forceinline__ unsigned long long warp_max_ull(unsigned long long v)
     return v;
 }
 
-// Rotation constant of the periodic-arc statistic.  With half = P/2 and
-// K = P - half - 1, w(q) = (q - q0 + K) mod P orders pixel indices by their
-// signed periodic distance to q0 (go/group.go:412-420): dist = w - K.
-__device__ __forceinline__ unsigned long long arc_rotation(long long q0, long long P) {
-    long long K = P - P / 2 - 1;
-    long long c = K - q0;
-    if (c < 0) c += P;
-    return (unsigned long long)c;
-}
-
 // ---------------------------------------------------------------------------
 // descriptor builders
 // ---------------------------------------------------------------------------
@@ -148,7 +138,10 @@ __global__ void k_build_vec3(BlockDesc *descs, int64_t nfiles, const float *aos,
 // ---------------------------------------------------------------------------
 // stats
 // ---------------------------------------------------------------------------
-__global__ void k_init(const BlockDesc *descs, BlockStat *stats, int64_t nb) {
+// `run_if` (may be null): the kernels of the generic encode do nothing unless *run_if != 0.
+// The fused path enqueues them behind itself as the exact redo for inputs it refuses.
+__global__ void k_init(const BlockDesc *descs, BlockStat *stats, int64_t nb, const int *run_if) {
+    if (run_if && *run_if == 0) return;
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= nb) return;
     BlockStat s = {};
@@ -159,11 +152,12 @@ __global__ void k_init(const BlockDesc *descs, BlockStat *stats, int64_t nb) {
 }
 
 __global__ void __launch_bounds__(STATS_THREADS)
-k_stats(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh) {
+k_stats(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh, const int *run_if) {
     __shared__ long long s_ll[2][STATS_THREADS / 32];
     __shared__ unsigned long long s_ull[2][STATS_THREADS / 32];
     __shared__ unsigned int s_oob;
-    int64_t chunk = blockIdx.x;
+    if (run_if && *run_if == 0) return;
+    for (int64_t chunk = blockIdx.x; chunk < sh.total_chunks; chunk += gridDim.x) {
     int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
     int64_t b = find_block(descs, sh, chunk, cpb, false);
     const BlockDesc d = descs[b];
@@ -181,6 +175,10 @@ k_stats(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh) {
     unsigned int oob = 0;
     for (int64_t i = first + threadIdx.x; i < end; i += STATS_THREADS) {
         long long q = block_value(d, i);
+        // A pixel index equal to `pixels` (x within half an ulp of `high`) behaves
+        // exactly like index 0 in periodicDistance, periodicMin and bound
+        // (go/group.go:374-420) as long as x[0] itself is in range: fold it.
+        if (periodic && q0_ok && q == P) q = 0;
         qmin = q < qmin ? q : qmin;
         qmax = q > qmax ? q : qmax;
         if (periodic) {
@@ -223,6 +221,8 @@ k_stats(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh) {
             }
         }
     }
+    __syncthreads();   // shared scratch is reused by the next chunk
+    }
 }
 
 // bits / nbytes from (min, max offset); flags an error where Go is undefined.
@@ -234,7 +234,8 @@ __device__ __forceinline__ void finish_stat(BlockStat &s, int64_t n, unsigned lo
 }
 
 __global__ void k_finalize(const BlockDesc *descs, BlockStat *stats, int64_t nb, int64_t *slow_list,
-                           int *slow_count, int *err) {
+                           int *slow_count, int *err, const int *run_if) {
+    if (run_if && *run_if == 0) return;
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const BlockDesc &d = descs[b];
@@ -276,9 +277,11 @@ __global__ void k_finalize(const BlockDesc *descs, BlockStat *stats, int64_t nb,
 // are skipped 32 at a time with a ballot, every other element updates the arc
 // exactly as the Go loop does.
 __global__ void __launch_bounds__(256)
-k_slow(const BlockDesc *descs, BlockStat *stats, const int64_t *slow_list, const int *slow_count, int *err) {
+k_slow(const BlockDesc *descs, BlockStat *stats, const int64_t *slow_list, const int *slow_count, int *err,
+       const int *run_if) {
     __shared__ long long s_pmin;
     __shared__ long long s_red[2][8];
+    if (run_if && *run_if == 0) return;
     const int nslow = *slow_count;
     for (int si = blockIdx.x; si < nslow; si += gridDim.x) {
         const int64_t b = slow_list[si];
@@ -396,9 +399,11 @@ __global__ void __launch_bounds__(256) k_vec3_limits(const float *__restrict__ a
 // scan: one CTA per chain (= minnow group); exclusive prefix of nbytes
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-k_scan(BlockStat *stats, BatchShape sh, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len) {
+k_scan(BlockStat *stats, BatchShape sh, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
+       const int *run_if) {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
+    if (run_if && *run_if == 0) return;
     const int64_t chain = blockIdx.x;
     const int64_t b0 = chain * sh.blocks_per_chain;
     const int64_t b1 = b0 + sh.blocks_per_chain < sh.nblocks ? b0 + sh.blocks_per_chain : sh.nblocks;
@@ -471,55 +476,69 @@ __device__ __forceinline__ void store_stream(uint8_t *dst, const uint32_t *s, in
 // ---------------------------------------------------------------------------
 // pack
 // ---------------------------------------------------------------------------
+// Tiles are walked grid-stride.  With `list` given only the listed blocks are packed
+// (*list_count of them; the fused path's blocks wider than 16 bits), else all of them.
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats, BatchShape sh,
-       uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err) {
+       uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err, const int *run_if,
+       const int64_t *list, const int *list_count) {
     __shared__ uint32_t s_out[PACK_THREADS * 64 + 4];
-    const int64_t tile = blockIdx.x;
+    if (run_if && *run_if == 0) return;
     const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
-    const int64_t b = find_block(descs, sh, tile, tpb, true);
-    const BlockStat st = stats[b];
-    const int bits = st.bits;
-    if (bits == 0) return;  // ArrayBuffer.Write returns at once, go/bit/bit.go:162
-    if (st.out_off + st.nbytes > chain_cap) {  // never write past the caller's buffer
-        if (threadIdx.x == 0) atomicExch(err, 2);
-        return;
-    }
-    const BlockDesc d = descs[b];
-    const int64_t first = (tile - d.tile0) * PACK_TILE;
-    const int64_t count = first + PACK_TILE <= d.n ? PACK_TILE : d.n - first;
-    const unsigned long long mask = bits >= 64 ? ~0ULL : ((1ULL << bits) - 1ULL);  // go/bit/bit.go:104
-    const long long P = d.pixels;
+    const int64_t total = list ? (int64_t)*list_count * tpb : sh.total_tiles;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int64_t b, tile_in_block;
+        if (list) {
+            b = list[tile / tpb];
+            tile_in_block = tile % tpb;
+        } else {
+            b = find_block(descs, sh, tile, tpb, true);
+            tile_in_block = tile - descs[b].tile0;
+        }
+        const BlockStat st = stats[b];
+        const int bits = st.bits;
+        if (bits == 0) continue;  // ArrayBuffer.Write returns at once, go/bit/bit.go:162
+        if (st.out_off + st.nbytes > chain_cap) {  // never write past the caller's buffer
+            if (threadIdx.x == 0) atomicExch(err, 2);
+            continue;
+        }
+        const BlockDesc d = descs[b];
+        const int64_t first = tile_in_block * PACK_TILE;
+        const int64_t count = first + PACK_TILE <= d.n ? PACK_TILE : d.n - first;
+        const unsigned long long mask = bits >= 64 ? ~0ULL : ((1ULL << bits) - 1ULL);  // go/bit/bit.go:104
+        const long long P = d.pixels;
 
-    const int g = threadIdx.x;
-    int64_t i0 = first + 32 * (int64_t)g;
-    if (32 * g < count) {
-        unsigned long long acc_lo = 0, acc_hi = 0;
-        int pos = 0, w = g * bits;
+        const int g = threadIdx.x;
+        int64_t i0 = first + 32 * (int64_t)g;
+        if (32 * g < count) {
+            unsigned long long acc_lo = 0, acc_hi = 0;
+            int pos = 0, w = g * bits;
 #pragma unroll 4
-        for (int k = 0; k < 32; k++) {
-            int64_t i = i0 + k;
-            unsigned long long v = 0;
-            if (i < d.n) {
-                long long q = block_value(d, i);
-                if (st.do_bound) q = bound1(q, st.pmin, P);
-                v = ((unsigned long long)q - (unsigned long long)st.min) & mask;
-            }
-            acc_lo |= v << pos;
-            if (pos) acc_hi |= v >> (64 - pos);
-            pos += bits;
-            while (pos >= 32) {
-                s_out[w++] = (uint32_t)acc_lo;
-                acc_lo = (acc_lo >> 32) | (acc_hi << 32);
-                acc_hi >>= 32;
-                pos -= 32;
+            for (int k = 0; k < 32; k++) {
+                int64_t i = i0 + k;
+                unsigned long long v = 0;
+                if (i < d.n) {
+                    long long q = block_value(d, i);
+                    if (st.do_bound) q = bound1(q, st.pmin, P);
+                    v = ((unsigned long long)q - (unsigned long long)st.min) & mask;
+                }
+                acc_lo |= v << pos;
+                if (pos) acc_hi |= v >> (64 - pos);
+                pos += bits;
+                while (pos >= 32) {
+                    s_out[w++] = (uint32_t)acc_lo;
+                    acc_lo = (acc_lo >> 32) | (acc_hi << 32);
+                    acc_hi >>= 32;
+                    pos -= 32;
+                }
             }
         }
+        __syncthreads();
+        const int64_t nbytes = (count * bits + 7) >> 3;
+        uint8_t *dst = out + (int64_t)d.chain * chain_stride + st.out_off + ((first * bits) >> 3);
+        store_stream(dst, s_out, nbytes, threadIdx.x, PACK_THREADS);
+        __syncthreads();   // s_out is reused by the next tile
     }
-    __syncthreads();
-    const int64_t nbytes = (count * bits + 7) >> 3;
-    uint8_t *dst = out + (int64_t)d.chain * chain_stride + st.out_off + ((first * bits) >> 3);
-    store_stream(dst, s_out, nbytes, threadIdx.x, PACK_THREADS);
 }
 
 // ---------------------------------------------------------------------------
@@ -596,7 +615,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
         }
         if (periodic) q = bound1(q, 0, P);              // go/group.go:303
         double u = 0.5;
-        if (A.jmode == 1) u = (double)jitter_hash32(A.seed, A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b), (unsigned long long)i) * 0x1p-32;
+        if (A.jmode == 1) u = (double)(jitter_hash32(A.seed, A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b), (unsigned long long)i) >> 8) * 0x1p-24;
         else if (A.jmode == 2) u = A.u[j * A.n + i];
         float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));  // go/group.go:308
         float o = __fadd_rn(__fmul_rn(dx, t), low);
@@ -708,33 +727,50 @@ void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int6
     L.count++;
 }
 
+// CTAs of the grid-stride kernels: enough to fill the chip, few enough to vanish when skipped.
+static inline unsigned persistent_grid(int64_t units, int per_sm) {
+    int64_t cap = 148LL * per_sm;
+    return (unsigned)(units < cap ? (units > 0 ? units : 1) : cap);
+}
+
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
-                           int64_t chain_cap) {
+                           int64_t chain_cap, const int *run_if) {
     if (sh.nblocks == 0) return;
     cudaMemsetAsync(slow_count, 0, sizeof(int), L.stream);
-    k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks);
+    k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, run_if);
     L.count++;
     if (sh.total_chunks > 0) {
-        L.begin("k_stats");
-        k_stats<<<(unsigned)sh.total_chunks, STATS_THREADS, 0, L.stream>>>(descs, stats, sh);
-        L.end();
+        if (!run_if) L.begin("k_stats");
+        k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        if (!run_if) L.end();
         L.count++;
     }
-    k_finalize<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, slow_list, slow_count, err);
+    k_finalize<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, slow_list, slow_count, err, run_if);
     L.count++;
     unsigned slow_grid = (unsigned)(sh.nblocks < 296 ? sh.nblocks : 296);
-    k_slow<<<slow_grid, 256, 0, L.stream>>>(descs, stats, slow_list, slow_count, err);
+    k_slow<<<slow_grid, 256, 0, L.stream>>>(descs, stats, slow_list, slow_count, err, run_if);
     L.count++;
-    k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len);
+    k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len, run_if);
     L.count++;
     if (sh.total_tiles > 0) {
-        L.begin("k_pack");
-        k_pack<<<(unsigned)sh.total_tiles, PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err);
-        L.end();
+        if (!run_if) L.begin("k_pack");
+        k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
+                                                                                   run_if, nullptr, nullptr);
+        if (!run_if) L.end();
         L.count++;
     }
+}
+
+// Pack only the listed blocks (uniform block size), from global memory.
+void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
+                      const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,
+                      int64_t chain_cap, int *err) {
+    if (sh.nblocks == 0 || sh.uniform_n <= 0) return;
+    k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
+                                                                               nullptr, list, list_count);
+    L.count++;
 }
 
 void launch_raw_pack(Launcher &L, BlockDesc *descs, BlockStat *stats, const void *src, int64_t n, int bits,
@@ -743,7 +779,8 @@ void launch_raw_pack(Launcher &L, BlockDesc *descs, BlockStat *stats, const void
     k_preset_raw<<<1, 1, 0, L.stream>>>(descs, stats, src, n, bits);
     L.count++;
     BatchShape sh = {1, 1, 1, n, (n + PACK_TILE - 1) / PACK_TILE, 0};
-    k_pack<<<(unsigned)sh.total_tiles, PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, 0, (int64_t)1 << 62, nullptr);
+    k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, 0, (int64_t)1 << 62, nullptr,
+                                                                               nullptr, nullptr, nullptr);
     L.count++;
 }
 

@@ -65,7 +65,10 @@ void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int6
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
-                           int64_t chain_cap);
+                           int64_t chain_cap, const int *run_if = nullptr);
+void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
+                      const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,
+                      int64_t chain_cap, int *err);
 cudaError_t launch_scan_sizes(Launcher &L, const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets,
                               int64_t *total);
 void launch_raw_pack(Launcher &L, BlockDesc *descs, BlockStat *stats, const void *src, int64_t n, int bits,
