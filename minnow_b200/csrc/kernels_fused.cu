@@ -33,6 +33,7 @@
 #include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_math.cuh"
 #include "engine.cuh"
@@ -69,6 +70,7 @@ struct FusedArgs {
     int64_t *mins, *bits, *offsets, *out_len;
     uint8_t *out;
     long long axis_stride;
+    int prefetch;   // pull the next unit's rows into L2 during the pack phase
     FusedWork W;
 };
 
@@ -118,7 +120,8 @@ __device__ __noinline__ int quantize_rare(float x, float low, float dx, int P, u
     return 0;
 }
 
-// 32 values of B bits -> B words, all shifts resolved at compile time.
+// 32 values of B bits -> B words, all shifts resolved at compile time.  The fields do
+// not overlap, so + is | and (v << sh) + o is a single LEA / IMAD.
 template <int B>
 __device__ __forceinline__ void pack32(const unsigned (&v)[32], unsigned (&o)[16]) {
 #pragma unroll
@@ -126,35 +129,58 @@ __device__ __forceinline__ void pack32(const unsigned (&v)[32], unsigned (&o)[16
 #pragma unroll
     for (int i = 0; i < 32; i++) {
         const int bit = i * B, wd = bit >> 5, sh = bit & 31;
-        o[wd] |= v[i] << sh;
-        if (sh + B > 32) o[wd + 1] |= v[i] >> (32 - sh);
+        o[wd] += v[i] << sh;
+        if (sh + B > 32) o[wd + 1] = v[i] >> (32 - sh);
     }
 }
 
-// Write `nbytes` of the little-endian word stream to dst (any byte alignment) with one
-// warp; word j of the stream is ld(j).  Interior words go out as aligned 32-bit stores,
-// the first/last partial word as single bytes (the neighbours own the other bytes).
-template <class Ld>
-__device__ __forceinline__ void warp_store_stream(uint8_t *dst, long long nbytes, int lane, Ld ld) {
-    const uintptr_t A = (uintptr_t)dst;
-    const int a = (int)(A & 3);
-    uint32_t *base = (uint32_t *)(A - a);
-    const long long nwords = (a + nbytes + 3) >> 2;
-    const int nsrc = (int)((nbytes + 3) >> 2);
-    for (long long j = lane; j < nwords; j += 32) {
-        uint32_t lo = (j > 0 && j - 1 < nsrc) ? ld((int)j - 1) : 0u;
-        uint32_t hi = j < nsrc ? ld((int)j) : 0u;
-        uint32_t w = __funnelshift_rc(lo, hi, 32 - 8 * a);
-        long long t0 = 4 * j - a;
-        if (t0 >= 0 && t0 + 4 <= nbytes) {
-            base[j] = w;
-        } else {
-            uint8_t *bp = (uint8_t *)(base + j);
-            for (int k = 0; k < 4; k++) {
-                long long t = t0 + k;
-                if (t >= 0 && t < nbytes) bp[k] = (uint8_t)(w >> (8 * k));
-            }
+// One pack group = 1024 consecutive elements of one block = 32 lanes x 32 values ->
+// 32*B words.  The words are transposed in place through the group's own 2 KiB of
+// staging (XOR swizzle: conflict-free both ways) so that the warp can write them out in
+// stream order, 128 bytes per store instruction.
+template <int B>
+__device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane) {
+    unsigned o[16];
+    pack32<B>(v, o);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        const int W = lane * B + j;
+        region[W ^ (W >> 5)] = o[j];
+    }
+    __syncwarp();
+}
+
+// Write the group's nwords = 32*bits stream words to dst (any byte alignment).  Interior
+// words go out as aligned 32-bit stores; the bytes of the first and last partial word are
+// stored one by one, because the neighbouring groups own the rest of those words.
+__device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region, int bits, int lane) {
+    const int a = (int)((uintptr_t)dst & 3);
+    uint32_t *base = (uint32_t *)(dst - a);
+    const int nsrc = 32 * bits;
+    if (a == 0) {
+#pragma unroll 2
+        for (int j = lane; j < nsrc; j += 32) base[j] = region[j ^ (j >> 5)];
+        return;
+    }
+    const int sh = 32 - 8 * a;
+    // aligned word j (1 <= j < nsrc) = stream words j-1 and j, funnel-shifted
+#pragma unroll 2
+    for (int j = lane; j < nsrc; j += 32) {
+        if (j > 0) {
+            const unsigned lo = region[(j - 1) ^ ((j - 1) >> 5)], hi = region[j ^ (j >> 5)];
+            base[j] = __funnelshift_r(lo, hi, sh);
         }
+    }
+    if (lane == 0) {          // head: bytes a..3 of aligned word 0 = low bytes of stream word 0
+        const unsigned w = region[0];
+        uint8_t *bp = (uint8_t *)base;
+        for (int k = a; k < 4; k++) bp[k] = (uint8_t)(w >> (8 * (k - a)));
+    } else if (lane == 1) {   // tail: bytes 0..a-1 of aligned word nsrc = high bytes of the last stream word
+        const int l = nsrc - 1;
+        const unsigned w = region[l ^ (l >> 5)];
+        uint8_t *bp = (uint8_t *)(base + nsrc);
+        for (int k = 0; k < a; k++) bp[k] = (uint8_t)(w >> (8 * (4 - a + k)));
     }
 }
 
@@ -163,6 +189,16 @@ __device__ __forceinline__ void cluster_sync_all() {
     if constexpr (CS > 1) cg::this_cluster().sync();
     else __syncthreads();
 }
+
+// Batch-local statistics of phase 1, in the thread's relative axis order.
+struct LocalStat {
+    unsigned wmin[3], wmax[3];
+    int qmin[3], qmax[3];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { wmin[j] = ~0u; wmax[j] = 0u; qmin[j] = INT_MAX; qmax[j] = INT_MIN; }
+    }
+};
 
 }  // namespace
 
@@ -182,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
     static_assert(NT % R4 == 0 && ROWS % RPP == 0, "threads tile the rows exactly");
     static_assert((RPP * NSUB) % 512 == 0, "swizzle term must be a per-thread constant");
     static_assert(CHUNK % 1024 == 0 && N % CS == 0, "whole pack groups per CTA");
-    static_assert(PASSES % UNROLL == 0, "unroll divides the passes");
+    static_assert(PASSES % UNROLL == 0 && UNROLL % 2 == 0, "batches of float4 pairs");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *stage = (unsigned short *)smem_raw;   // [3][CHUNK], swizzled
@@ -206,6 +242,8 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
         const int e = rsub * NSUB + (4 * col4 + c) / 3;
         soff[c] = ax * CHUNK + (e ^ (((e >> 6) & 7) << 3));
     }
+    const int S = A.subcells, nfile = A.nfile;
+    const unsigned row4 = 3u * (unsigned)nfile / 4u, plane4 = row4 * (unsigned)nfile;   // float4 units
 
     int par = 0;
     if (rank == 0 && tid == 0) {
@@ -218,20 +256,21 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
     }
     cluster_sync_all<CS>();
 
-    for (long long unit = s_unit[0]; unit < A.nunits; unit = s_unit[par], (void)0) {
+    for (long long unit = s_unit[0]; unit < A.nunits; unit = s_unit[par]) {
         const long long f = unit / A.sc3, sc = unit - f * A.sc3;
-        const int S = A.subcells, nfile = A.nfile;
         const int ix0 = NSUB * (int)(sc % S), iy0 = NSUB * (int)((sc / S) % S), iz0 = NSUB * (int)(sc / ((long long)S * S));
         const float *cube = A.aos + 3 * f * (long long)nfile * nfile * nfile;
         const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
+        // first float4 of this thread's column in row 0 of the sub-cell
+        const float4 *pbase = (const float4 *)cube + ((unsigned)(3 * ix0) / 4u + (unsigned)iy0 * row4 + (unsigned)iz0 * plane4) + col4;
 
         // ---- per-axis parameters in this thread's axis order (relative axis j = actual (a0+j)%3) ----
         float low[3], rcp[3], ndx[3];
         int P[3];
         unsigned Pm1[3], C[3];
         unsigned oob = 0;
-        long long q0[3];
         {
+            long long q0[3];
             const long long idx0 = ix0 + (long long)iy0 * nfile + (long long)iz0 * nfile * nfile;
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -245,40 +284,74 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
                 C[j] = ok ? (unsigned)arc_rotation(q0[j], P[j]) : 0u;
                 if (!ok) oob = 1;   // periodicMin starting outside [0, pixels): exact path only
             }
+            if (tid == 0) { s_q0[0] = q0[0]; s_q0[1] = q0[1]; s_q0[2] = q0[2]; }   // a0 == 0 here: actual order
         }
-        if (tid == 0) { s_q0[0] = q0[0]; s_q0[1] = q0[1]; s_q0[2] = q0[2]; }   // a0 == 0 here: actual order
 
-        unsigned wmin[3] = {~0u, ~0u, ~0u}, wmax[3] = {0u, 0u, 0u};
-        int qmin[3] = {INT_MAX, INT_MAX, INT_MAX}, qmax[3] = {INT_MIN, INT_MIN, INT_MIN};
+        LocalStat run;
+        run.reset();
 
         __syncthreads();   // the previous unit's pack phase has released the staging area
 
         // ---- phase 1: one read of the sub-cell rows ----
-        const long long plane = (long long)nfile * nfile;
-#pragma unroll 1
-        for (int p0 = 0; p0 < PASSES; p0 += UNROLL) {
+        // A batch = UNROLL float4 per thread.  The fast quantiser is trusted only for pixel
+        // indices in [1, pixels): the batch minimum and maximum tell whether every element
+        // qualified; if not (rare) the batch is redone with the IEEE divide.
+        auto batch = [&](auto exact_tag, int p0, LocalStat &ls) {
+            constexpr bool EXACT = decltype(exact_tag)::value;
             float4 v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                const int rowg = (int)rank * ROWS + rsub + RPP * (p0 + u);
-                const int jz = rowg / NSUB, jy = rowg % NSUB;
-                const long long idx = ix0 + (long long)(jy + iy0) * nfile + (long long)(jz + iz0) * plane;
-                v[u] = __ldcs((const float4 *)(cube + 3 * idx) + col4);
+                const unsigned rowg = rank * ROWS + rsub + RPP * (p0 + u);
+                v[u] = __ldcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4));
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            for (int u = 0; u < UNROLL; u += 2) {
+                int q[2][4];
+                unsigned w[2][4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int j = c % 3;
-                    int qi = quantize_fast(x[c], low[j], rcp[j], ndx[j]);
-                    if ((unsigned)(qi - 1) >= Pm1[j]) qi = quantize_rare(x[c], low[j], -ndx[j], P[j], oob);
-                    unsigned w = (unsigned)qi + C[j];
-                    w = min(w, w - (unsigned)P[j]);
-                    wmin[j] = min(wmin[j], w); wmax[j] = max(wmax[j], w);
-                    qmin[j] = min(qmin[j], qi); qmax[j] = max(qmax[j], qi);
-                    stage[soff[c] + (p0 + u) * (RPP * NSUB)] = (unsigned short)w;
+                for (int h = 0; h < 2; h++) {
+                    const float x[4] = {v[u + h].x, v[u + h].y, v[u + h].z, v[u + h].w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int j = c % 3;
+                        if constexpr (EXACT) q[h][c] = quantize_rare(x[c], low[j], -ndx[j], P[j], oob);
+                        else q[h][c] = quantize_fast(x[c], low[j], rcp[j], ndx[j]);
+                        const unsigned t = (unsigned)q[h][c] + C[j];
+                        w[h][c] = min(t, t - (unsigned)P[j]);
+                        stage[soff[c] + (p0 + u + h) * (RPP * NSUB)] = (unsigned short)w[h][c];
+                    }
                 }
+                // relative axis 0 owns floats 0 and 3 of each float4, axes 1 and 2 one float each
+                ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[0][0], q[0][3]); ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[1][0], q[1][3]);
+                ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[0][0], q[0][3]); ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[1][0], q[1][3]);
+                ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[0][0], w[0][3]); ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[1][0], w[1][3]);
+                ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[0][0], w[0][3]); ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[1][0], w[1][3]);
+#pragma unroll
+                for (int j = 1; j < 3; j++) {
+                    ls.qmin[j] = __vimin3_s32(ls.qmin[j], q[0][j], q[1][j]);
+                    ls.qmax[j] = __vimax3_s32(ls.qmax[j], q[0][j], q[1][j]);
+                    ls.wmin[j] = __vimin3_u32(ls.wmin[j], w[0][j], w[1][j]);
+                    ls.wmax[j] = __vimax3_u32(ls.wmax[j], w[0][j], w[1][j]);
+                }
+            }
+        };
+#pragma unroll 1
+        for (int p0 = 0; p0 < PASSES; p0 += UNROLL) {
+            LocalStat ls;
+            ls.reset();
+            batch(std::false_type{}, p0, ls);
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                ok = ok && (unsigned)(ls.qmin[j] - 1) < Pm1[j] && (unsigned)(ls.qmax[j] - 1) < Pm1[j];
+            if (!ok) {
+                ls.reset();
+                batch(std::true_type{}, p0, ls);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                run.wmin[j] = min(run.wmin[j], ls.wmin[j]); run.wmax[j] = max(run.wmax[j], ls.wmax[j]);
+                run.qmin[j] = min(run.qmin[j], ls.qmin[j]); run.qmax[j] = max(run.qmax[j], ls.qmax[j]);
             }
         }
 
@@ -286,10 +359,10 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const int j = (k - a0 + 3) % 3;   // relative index of actual axis k
-            unsigned a = j == 0 ? wmin[0] : (j == 1 ? wmin[1] : wmin[2]);
-            unsigned b = j == 0 ? wmax[0] : (j == 1 ? wmax[1] : wmax[2]);
-            int c = j == 0 ? qmin[0] : (j == 1 ? qmin[1] : qmin[2]);
-            int d = j == 0 ? qmax[0] : (j == 1 ? qmax[1] : qmax[2]);
+            unsigned a = j == 0 ? run.wmin[0] : (j == 1 ? run.wmin[1] : run.wmin[2]);
+            unsigned b = j == 0 ? run.wmax[0] : (j == 1 ? run.wmax[1] : run.wmax[2]);
+            int c = j == 0 ? run.qmin[0] : (j == 1 ? run.qmin[1] : run.qmin[2]);
+            int d = j == 0 ? run.qmax[0] : (j == 1 ? run.qmax[1] : run.qmax[2]);
             a = __reduce_min_sync(0xffffffffu, a);
             b = __reduce_max_sync(0xffffffffu, b);
             c = __reduce_min_sync(0xffffffffu, c);
@@ -322,6 +395,21 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
         }
         cluster_sync_all<CS>();
 
+        // ---- pull the next unit's rows towards L2 while this one is being packed ----
+        if (A.prefetch) {
+            const long long nu = s_unit[par ^ 1];
+            if (nu < A.nunits) {
+                const long long nf = nu / A.sc3, nsc = nu - nf * A.sc3;
+                const unsigned nx0 = NSUB * (unsigned)(nsc % S), ny0 = NSUB * (unsigned)((nsc / S) % S), nz0 = NSUB * (unsigned)(nsc / ((long long)S * S));
+                const float4 *nb = (const float4 *)(A.aos + 3 * nf * (long long)nfile * nfile * nfile) + (3u * nx0 / 4u + ny0 * row4 + nz0 * plane4);
+                for (unsigned r = tid; r < (unsigned)ROWS; r += NT) {
+                    const unsigned rowg = rank * ROWS + r;
+                    const float4 *p = nb + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(NSUB * 12) : "memory");
+                }
+            }
+        }
+
         // ---- finalise + look-back: warp k handles axis k (every CTA, redundantly) ----
         if (warp < 3) {
             const int k = warp;
@@ -351,17 +439,16 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
                 long long m = q0k + ((long long)x.wmin - K);
                 if (m < 0) m += Pk;
                 pmin = m; mn = m; maxoff = spread - 1ULL;
-                base = x.wmin; padj = (unsigned)Pk;
+                base = x.wmin; padj = 0;
             }
             int bits = precision_needed(maxoff);
             long long nbytes = array_bytes(bits, N);
             const bool slow = x.oob != 0;
             if (slow) { bits = 0; nbytes = 0; }
-            if (Pk > 65536) {   // staged values are only the low 16 bits of w
-                base &= 0xffffu; padj = 65536u;
-            }
             if (rank == 0 && lane == 0) st_relaxed(A.W.pub + b, PUB_AGG | (unsigned long long)nbytes);
             const long long off = lookback(A.W.pub, chain0, b);
+            // staged values are the low 16 bits of w: enough when the packed value has <= 16 bits
+            // and (wide arcs) w itself fits, i.e. pixels <= 65536
             int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
             if (lane == 0) {
                 if (off + nbytes > A.axis_stride) {   // never write past the caller's buffer
@@ -397,40 +484,42 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
             const int eb = gi * 1024 + 32 * lane;   // this lane's first element within the CTA's chunk
             const int sw = (eb >> 6) & 7;
             unsigned v[32];
+            uint4 r[4];
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const int chunk = ((eb >> 3) + s) ^ sw;
-                const uint4 r = *(const uint4 *)(stage + k * CHUNK + (chunk << 3));
-                const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+            for (int s = 0; s < 4; s++) r[s] = *(const uint4 *)(stage + k * CHUNK + ((((eb >> 3) + s) ^ sw) << 3));
+            if (fin.padj == 0) {   // narrow arc: v = w - wmin, exact modulo 2^16
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    unsigned lo = (rr[t] & 0xffffu) - fin.base, hi = (rr[t] >> 16) - fin.base;
-                    v[8 * s + 2 * t] = min(lo, lo + fin.padj) & 0xffffu;
-                    v[8 * s + 2 * t + 1] = min(hi, hi + fin.padj) & 0xffffu;
+                for (int s = 0; s < 4; s++) {
+                    const unsigned rr[4] = {r[s].x, r[s].y, r[s].z, r[s].w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        v[8 * s + 2 * t] = (rr[t] - fin.base) & 0xffffu;
+                        v[8 * s + 2 * t + 1] = ((rr[t] >> 16) - fin.base) & 0xffffu;
+                    }
+                }
+            } else {               // wide arc (pixels <= 65536): v = (w - C - qmin) mod pixels
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const unsigned rr[4] = {r[s].x, r[s].y, r[s].z, r[s].w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const unsigned lo = (rr[t] & 0xffffu) - fin.base, hi = (rr[t] >> 16) - fin.base;
+                        v[8 * s + 2 * t] = min(lo, lo + fin.padj);
+                        v[8 * s + 2 * t + 1] = min(hi, hi + fin.padj);
+                    }
                 }
             }
-            unsigned o[16];
+            unsigned *region = (unsigned *)(stage + k * CHUNK + gi * 1024);
             switch (fin.bits) {
-#define MNW_CASE(B) case B: pack32<B>(v, o); break;
+#define MNW_CASE(B) case B: pack_group_words<B>(v, region, lane); break;
                 MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
                 MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
 #undef MNW_CASE
                 default: break;
             }
-            // in-place transpose: the group's 2 KiB of staging now holds its packed words
-            unsigned *region = (unsigned *)(stage + k * CHUNK + gi * 1024);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j < fin.bits) {
-                    const int W = lane * fin.bits + j;
-                    region[W ^ (W >> 5)] = o[j];
-                }
-            }
-            __syncwarp();
             const long long e0 = (long long)rank * CHUNK + (long long)gi * 1024;   // element index in the block
             uint8_t *dst = A.out + (f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
-            warp_store_stream(dst, 128LL * fin.bits, lane, [&](int j) { return region[j ^ (j >> 5)]; });
+            write_group(dst, region, fin.bits, lane);
         }
         par ^= 1;
     }
@@ -446,129 +535,216 @@ struct DecVec3Args {
     const FloatParams *tab;
     int tab_per_file;
     float wrap_L;
-    int jmode;
     unsigned long long seed, block_id0;
     int nfile, subcells;
-    long long sc3;
+    long long sc3, nslabs;
     float *out;
 };
 
-// value i of a block whose stream starts at the 4-byte aligned word pointer `base`,
-// `a8` bits into it: bits <= 32
-__device__ __forceinline__ unsigned extract32(const uint32_t *__restrict__ base, unsigned bitpos, int bits, unsigned mask) {
-    const unsigned wi = bitpos >> 5, sh = bitpos & 31;
-    const uint32_t w0 = __ldg(base + wi);
-    const uint32_t w1 = (sh + bits > 32) ? __ldg(base + wi + 1) : 0u;
-    return __funnelshift_r(w0, w1, sh) & mask;
+// What a CTA needs to know about one axis block of the slab it is about to decode
+// (written by the producer thread together with the bulk copy of the packed bytes).
+struct SlabAxis {
+    const uint8_t *gsrc;   // slow path: first byte of the block's stream
+    long long mn;
+    long long pixels;
+    float low, dx;
+    unsigned key;          // jitter key of the block
+    int bits;
+    int shift;             // fast path: bit position of the slab's first value in the staged bytes
+    int fast;              // 1: 32-bit path from shared memory
+    int periodic;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Slow lane path of the decoder: any bit width, 64-bit arithmetic, straight from global memory.
+__device__ __noinline__ float decode_rare(const SlabAxis &h, long long e, int jmode, float wrap_L) {
+    const uint8_t *stream = h.gsrc;
+    const int a = (int)((uintptr_t)stream & 3);
+    const uint32_t *base = (const uint32_t *)(stream - a);
+    unsigned long long v = 0;
+    const int bits = h.bits;
+    if (bits) {
+        const unsigned long long bitpos = 8ULL * a + (unsigned long long)e * bits;
+        const long long wi = (long long)(bitpos >> 5);
+        const int sh = (int)(bitpos & 31);
+        const uint32_t w0 = __ldg(base + wi);
+        const uint32_t w1 = (sh + bits > 32) ? __ldg(base + wi + 1) : 0u;
+        v = (((unsigned long long)w1 << 32) | w0) >> sh;
+        if (sh + bits > 64) v |= (unsigned long long)__ldg(base + wi + 2) << (64 - sh);
+        if (bits < 64) v &= (1ULL << bits) - 1ULL;
+    }
+    long long q = (long long)((unsigned long long)h.mn + v);            // go/group.go:262
+    if (h.periodic) q = bound1(q, 0, h.pixels);                          // :303
+    double u = 0.5;
+    if (jmode == 1) u = (double)(jitter_hash_keyed(h.key, (uint32_t)e) >> 8) * 0x1p-24;
+    const float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));  // :308
+    float o = __fadd_rn(__fmul_rn(h.dx, t), h.low);
+    if (wrap_L > 0.0f) {                                                 // go/minp/minp.go:195-203
+        if (o < 0.0f) o = __fadd_rn(o, wrap_L);
+        else if (o >= wrap_L) o = __fsub_rn(o, wrap_L);
+    }
+    return o;
 }
 
-template <int NSUB, int NT>
-__global__ void __launch_bounds__(NT) k_decode_vec3(const DecVec3Args A) {
+// Persistent CTAs walk the slabs (SLAB consecutive elements of the three axis blocks of
+// one sub-cell).  Thread 0 fetches the packed bytes of the NEXT slab with three TMA bulk
+// copies (cp.async.bulk, completion on an mbarrier) while the CTA decodes the current one;
+// every thread then produces whole float4 pieces of AoS rows, so each output row is
+// written once with coalesced 128-bit stores and no axis ever touches a sector alone.
+template <int NSUB, int NT, bool HASH, bool WRAP>
+__global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
     constexpr int N = NSUB * NSUB * NSUB;
-    constexpr int SLAB = N < 4096 ? N : 4096;   // elements per CTA and axis
+    constexpr int SLAB = N < 4096 ? N : 4096;   // elements per slab and axis
     constexpr int SLABS = N / SLAB;
     constexpr int ROWS = SLAB / NSUB;
     constexpr int R4 = 3 * NSUB / 4;
     constexpr int RPP = NT / R4;
+    constexpr int STAGE_BYTES = SLAB * 3 + 32;   // up to 24 bits per value, + alignment slack
     static_assert(NT % R4 == 0, "threads tile the rows exactly");
-    __shared__ __align__(16) float dec[3][SLAB];
+    extern __shared__ __align__(128) unsigned char dsm[];   // [2][3][STAGE_BYTES]
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ SlabAxis s_hdr[2][3];
 
     const int tid = threadIdx.x;
-    const long long unit = blockIdx.x / SLABS;
-    const int slab = (int)(blockIdx.x - unit * SLABS);
-    const long long f = unit / A.sc3, sc = unit - f * A.sc3;
-    const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
+    const int S = A.subcells, nfile = A.nfile;
+    const unsigned row4 = 3u * (unsigned)nfile / 4u, plane4 = row4 * (unsigned)nfile;
+    const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
+    int ecol[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) ecol[c] = (4 * col4 + c) / 3;
 
-    // ---- phase 1: unpack + dequantise each axis into planar shared memory ----
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) {
-        const long long b = f * 3 * A.sc3 + k * A.sc3 + sc;
-        const long long mn = A.mins[b];
-        const int bits = (int)A.bits[b];
-        const FloatParams fp = tab[k];
-        const long long Pk = fp.pixels;
-        const bool periodic = fp.flags & F_PERIODIC;
-        const uint8_t *stream = A.data + (f * 3 + k) * A.stream_len + A.offsets[b];
-        const int a = (int)((uintptr_t)stream & 3);
-        const uint32_t *base = (const uint32_t *)(stream - a);
-        const uint32_t key = jitter_key(A.seed, A.block_id0 + (unsigned long long)b);
-        // 32-bit fast path: every q of the block is known to land in (-2^23, 2^23) after bound(),
-        // so float32 holds it exactly; anything else takes the 64-bit path below
-        const long long qlo = mn, qhi = mn + (long long)((bits >= 1 && bits <= 30) ? ((1u << bits) - 1u) : 0u);
-        const bool small = bits <= 30 && mn > -(1LL << 30) && mn < (1LL << 30) && Pk > 0 && Pk < (1LL << 23) &&
-                           (periodic ? (qlo >= -Pk && qhi < 2 * Pk) : (qlo > -(1LL << 23) && qhi < (1LL << 23)));
-        if (small) {   // everything fits 32-bit integers and float32 holds q exactly
-            const unsigned mask = bits ? (0xffffffffu >> (32 - bits)) : 0u;
-            const int mn32 = (int)mn, P32 = (int)Pk;
-#pragma unroll 4
-            for (int i = tid; i < SLAB; i += NT) {
-                const unsigned e = (unsigned)(slab * SLAB + i);
-                const unsigned v = bits ? extract32(base, 8u * a + e * (unsigned)bits, bits, mask) : 0u;
-                int q = mn32 + (int)v;                                      // go/group.go:262
-                if (periodic) { if (q < 0) q += P32; else if (q >= P32) q -= P32; }   // bound(q, 0, pixels), :303
-                float t;
-                if (A.jmode == 1) {
-                    // u = h24 * 2^-24 is exact in float32 and q + u needs at most 47 bits: one FMA
-                    // rounds once, exactly like float32(float64(q) + u) (go/group.go:308)
-                    const float h = (float)(jitter_hash_keyed(key, e) >> 8);
-                    t = __fmaf_rn(h, 0x1p-24f, (float)q);
-                } else {
-                    t = __fadd_rn((float)q, 0.5f);   // q < 2^23: q + 0.5 is exact
-                }
-                float o = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);
-                if (A.wrap_L > 0.0f) {                                        // go/minp/minp.go:195-203
-                    if (o < 0.0f) o = __fadd_rn(o, A.wrap_L);
-                    else if (o >= A.wrap_L) o = __fsub_rn(o, A.wrap_L);
-                }
-                dec[k][i] = o;
-            }
-        } else {
-            for (int i = tid; i < SLAB; i += NT) {
-                const long long e = (long long)slab * SLAB + i;
-                unsigned long long v = 0;
-                if (bits) {
-                    const unsigned long long bitpos = 8ULL * a + (unsigned long long)e * bits;
-                    const long long wi = (long long)(bitpos >> 5);
-                    const int sh = (int)(bitpos & 31);
-                    const uint32_t w0 = __ldg(base + wi);
-                    const uint32_t w1 = (sh + bits > 32) ? __ldg(base + wi + 1) : 0u;
-                    v = (((unsigned long long)w1 << 32) | w0) >> sh;
-                    if (sh + bits > 64) v |= (unsigned long long)__ldg(base + wi + 2) << (64 - sh);
-                    if (bits < 64) v &= (1ULL << bits) - 1ULL;
-                }
-                long long q = (long long)((unsigned long long)mn + v);
-                if (periodic) q = bound1(q, 0, Pk);
-                double u = 0.5;
-                if (A.jmode == 1) u = (double)(jitter_hash_keyed(key, (uint32_t)e) >> 8) * 0x1p-24;
-                const float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));
-                float o = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);
-                if (A.wrap_L > 0.0f) {
-                    if (o < 0.0f) o = __fadd_rn(o, A.wrap_L);
-                    else if (o >= A.wrap_L) o = __fsub_rn(o, A.wrap_L);
-                }
-                dec[k][i] = o;
-            }
-        }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- phase 2: whole AoS rows, coalesced 128-bit stores (setSubCell, go/minp/minp.go:270-288) ----
-    const int S = A.subcells, nfile = A.nfile;
-    const int ix0 = NSUB * (int)(sc % S), iy0 = NSUB * (int)((sc / S) % S), iz0 = NSUB * (int)(sc / ((long long)S * S));
-    float *cube = A.out + 3 * f * (long long)nfile * nfile * nfile;
-    const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
-    int src[4];
+    // producer: describe slab g and start the copies of its packed bytes into stage st
+    auto issue = [&](int st, long long g) {
+        const long long unit = g / SLABS;
+        const int slab = (int)(g - unit * SLABS);
+        const long long f = unit / A.sc3, sc = unit - f * A.sc3;
+        const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
+        unsigned bytes[3] = {0, 0, 0};
+        const uint8_t *src[3] = {nullptr, nullptr, nullptr};
+        unsigned total = 0;
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            const long long b = f * 3 * A.sc3 + k * A.sc3 + sc;
+            const FloatParams fp = tab[k];
+            SlabAxis h;
+            h.mn = A.mins[b]; h.bits = (int)A.bits[b]; h.pixels = fp.pixels; h.low = fp.low; h.dx = fp.dx;
+            h.periodic = (fp.flags & F_PERIODIC) ? 1 : 0;
+            h.key = jitter_key(A.seed, A.block_id0 + (unsigned long long)b);
+            h.gsrc = A.data + (f * 3 + k) * A.stream_len + A.offsets[b];
+            const long long mask = (h.bits >= 1 && h.bits <= 24) ? (long long)((1u << h.bits) - 1u) : 0;
+            // 32-bit path: q = mn + v lies in [0, 2*pixels) (periodic) or [0, 2^23), and float32 holds it exactly
+            h.fast = h.bits <= 24 && h.mn >= 0 && fp.pixels > 0 && fp.pixels < (1LL << 23) &&
+                     (h.periodic ? h.mn + mask < 2 * fp.pixels : h.mn + mask < (1LL << 23));
+            h.shift = 0;
+            if (h.fast && h.bits > 0) {
+                const uint8_t *p = h.gsrc + (((long long)slab * SLAB * h.bits) >> 3);
+                const unsigned a16 = (unsigned)((uintptr_t)p & 15);
+                src[k] = p - a16;
+                bytes[k] = (a16 + (unsigned)(SLAB * h.bits / 8) + 15u) & ~15u;
+                h.shift = 8 * (int)a16;
+                total += bytes[k];
+            }
+            s_hdr[st][k] = h;
+        }
+        const unsigned bar = smem_u32(&s_bar[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
 #pragma unroll
-    for (int c = 0; c < 4; c++) src[c] = ((a0 + c) % 3) * SLAB + (4 * col4 + c) / 3;
-    const float *flat = &dec[0][0];
-    for (int rl = rsub; rl < ROWS; rl += RPP) {
-        const int rowg = slab * ROWS + rl;
-        const int jz = rowg / NSUB, jy = rowg % NSUB;
-        const long long idx = ix0 + (long long)(jy + iy0) * nfile + (long long)(jz + iz0) * nfile * nfile;
-        float4 o;
-        o.x = flat[src[0] + rl * NSUB]; o.y = flat[src[1] + rl * NSUB];
-        o.z = flat[src[2] + rl * NSUB]; o.w = flat[src[3] + rl * NSUB];
-        __stcs((float4 *)(cube + 3 * idx) + col4, o);
+        for (int k = 0; k < 3; k++)
+            if (bytes[k])
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(dsm + (st * 3 + k) * STAGE_BYTES)), "l"(src[k]), "r"(bytes[k]), "r"(bar) : "memory");
+    };
+
+    if (tid == 0 && (long long)blockIdx.x < A.nslabs) issue(0, blockIdx.x);
+    __syncthreads();
+
+    int it = 0;
+    for (long long g = blockIdx.x; g < A.nslabs; g += gridDim.x, it++) {
+        const int st = it & 1;
+        if (tid == 0 && g + gridDim.x < A.nslabs) issue(st ^ 1, g + gridDim.x);
+        {   // wait for this slab's bytes
+            const unsigned bar = smem_u32(&s_bar[st]), parity = (it >> 1) & 1;
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        const long long unit = g / SLABS;
+        const int slab = (int)(g - unit * SLABS);
+        const long long f = unit / A.sc3, sc = unit - f * A.sc3;
+        const unsigned ix0 = NSUB * (unsigned)(sc % S), iy0 = NSUB * (unsigned)((sc / S) % S), iz0 = NSUB * (unsigned)(sc / ((long long)S * S));
+        float4 *pbase = (float4 *)(A.out + 3 * f * (long long)nfile * nfile * nfile) + (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
+
+        // per-axis constants in this thread's axis order
+        const uint32_t *buf[3];
+        int bits[3], shift[3], mn[3], P[3];
+        unsigned mask[3], key[3];
+        float low[3], dx[3];
+        bool fast = true;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int k = (a0 + j) % 3;
+            const SlabAxis &h = s_hdr[st][k];
+            buf[j] = (const uint32_t *)(dsm + (st * 3 + k) * STAGE_BYTES);
+            bits[j] = h.bits; shift[j] = h.shift; mn[j] = (int)h.mn; P[j] = h.periodic ? (int)h.pixels : 0;
+            mask[j] = h.bits ? (0xffffffffu >> (32 - h.bits)) : 0u;
+            key[j] = h.key; low[j] = h.low; dx[j] = h.dx;
+            fast = fast && h.fast;
+        }
+
+        if (fast) {
+#pragma unroll 2
+            for (int rl = rsub; rl < ROWS; rl += RPP) {
+                float o[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int j = c % 3;
+                    const unsigned el = (unsigned)(rl * NSUB + ecol[c]);            // element within the slab
+                    const unsigned bp = (unsigned)shift[j] + el * (unsigned)bits[j];
+                    const uint32_t w0 = buf[j][bp >> 5], w1 = buf[j][(bp >> 5) + 1];
+                    const unsigned v = __funnelshift_r(w0, w1, bp & 31) & mask[j];  // Array.Slice, go/bit/bit.go:29-82
+                    unsigned q = (unsigned)mn[j] + v;                               // go/group.go:262
+                    q = min(q, q - (unsigned)P[j]);                                 // bound(q, 0, pixels), :303 (P = 0: not periodic)
+                    float t;
+                    if constexpr (HASH) {
+                        // u = h24 * 2^-24 is exact in float32 and q + u needs at most 47 bits: the FMA
+                        // rounds once, exactly like float32(float64(q) + u) (go/group.go:308)
+                        const float hh = (float)(jitter_hash_keyed(key[j], (unsigned)slab * SLAB + el) >> 8);
+                        t = __fmaf_rn(hh, 0x1p-24f, (float)q);
+                    } else {
+                        t = __fadd_rn((float)q, 0.5f);   // q < 2^23: exact
+                    }
+                    float x = __fadd_rn(__fmul_rn(dx[j], t), low[j]);
+                    if constexpr (WRAP) {                                           // go/minp/minp.go:195-203
+                        if (x < 0.0f) x = __fadd_rn(x, A.wrap_L);
+                        else if (x >= A.wrap_L) x = __fsub_rn(x, A.wrap_L);
+                    }
+                    o[c] = x;
+                }
+                const unsigned rowg = (unsigned)(slab * ROWS + rl);
+                __stcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));   // setSubCell, :270-288
+            }
+        } else {
+            for (int rl = rsub; rl < ROWS; rl += RPP) {
+                float o[4];
+                for (int c = 0; c < 4; c++) {
+                    const int k = (a0 + c) % 3;
+                    const long long e = (long long)slab * SLAB + rl * NSUB + ecol[c];
+                    o[c] = decode_rare(s_hdr[st][k], e, HASH ? 1 : 0, WRAP ? A.wrap_L : 0.0f);
+                }
+                const unsigned rowg = (unsigned)(slab * ROWS + rl);
+                __stcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        __syncthreads();   // stage st and its header may be refilled from the next iteration on
     }
 }
 
@@ -613,7 +789,7 @@ bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile,
     if (subcells <= 0 || nfile % subcells) return false;
     const int nsub = nfile / subcells;
     if (nsub != 16 && nsub != 32 && nsub != 64) return false;
-    if (((uintptr_t)aos & 15) != 0) return false;
+    if (((uintptr_t)aos & 15) != 0 || nfile > 1024) return false;   // 32-bit float4 offsets inside a file
     for (int64_t i = 0; i < nparams; i++) {
         const FloatParamsHost &p = fp[i];
         if (!(p.flags & F_PERIODIC) || (p.flags & (F_LOG10 | F_CLAMP))) return false;
@@ -664,6 +840,8 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
     A.nunits = nfiles * A.sc3;
     A.stats = stats; A.mins = mins; A.bits = bits; A.offsets = offsets; A.out_len = out_len; A.out = out;
     A.axis_stride = out_axis_stride; A.W = W;
+    static const int prefetch = getenv("MNW_PREFETCH") ? atoi(getenv("MNW_PREFETCH")) : 1;   // tuning knob
+    A.prefetch = prefetch;
     if (A.nunits == 0) return cudaSuccess;
     switch (nfile / subcells) {
         case 64: {
@@ -678,35 +856,66 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
 }
 
 bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out) {
-    if (subcells <= 0 || nfile % subcells) return false;
+    if (subcells <= 0 || nfile % subcells || nfile > 1024) return false;
     const int nsub = nfile / subcells;
     if (nsub != 16 && nsub != 32 && nsub != 64) return false;
     return ((uintptr_t)aos_out & 15) == 0;
 }
 
+template <int NSUB, bool HASH, bool WRAP>
+static cudaError_t launch_decode_vec3_t(Launcher &L, const DecVec3Args &A) {
+    constexpr int NT = 384;
+    constexpr int N = NSUB * NSUB * NSUB, SLAB = N < 4096 ? N : 4096;
+    constexpr size_t smem = (size_t)2 * 3 * (SLAB * 3 + 32);
+    auto kern = k_decode_vec3<NSUB, NT, HASH, WRAP>;
+    static bool configured = false;
+    static int per_sm = 1;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        per_sm *= sms;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_decode_vec3<%d>: %d co-resident CTAs, %zu B dynamic smem\n", NSUB, per_sm, smem);
+        configured = true;
+    }
+    const long long grid = A.nslabs < per_sm ? A.nslabs : per_sm;
+    L.begin("k_decode_vec3");
+    kern<<<(unsigned)grid, NT, smem, L.stream>>>(A);
+    L.end();
+    L.count++;
+    return cudaGetLastError();
+}
+
+template <int NSUB>
+static cudaError_t launch_decode_vec3_n(Launcher &L, const DecVec3Args &A, bool hash, bool wrap) {
+    if (hash) return wrap ? launch_decode_vec3_t<NSUB, true, true>(L, A) : launch_decode_vec3_t<NSUB, true, false>(L, A);
+    return wrap ? launch_decode_vec3_t<NSUB, false, true>(L, A) : launch_decode_vec3_t<NSUB, false, false>(L, A);
+}
+
 cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t nfiles) {
     DecVec3Args A = {};
     A.data = h.data; A.stream_len = h.stream_len; A.offsets = h.offsets; A.mins = h.mins; A.bits = h.bits;
-    A.tab = h.tab; A.tab_per_file = h.tab_per_file; A.wrap_L = h.wrap_L; A.jmode = h.jmode; A.seed = h.seed;
+    A.tab = h.tab; A.tab_per_file = h.tab_per_file; A.wrap_L = h.wrap_L; A.seed = h.seed;
     A.block_id0 = h.block_id0; A.nfile = h.nfile; A.subcells = h.subcells;
     A.sc3 = (long long)h.subcells * h.subcells * h.subcells;
     A.out = (float *)h.out;
     const long long units = nfiles * A.sc3;
     if (units == 0) return cudaSuccess;
     const int nsub = h.nfile / h.subcells;
-    const long long n = (long long)nsub * nsub * nsub, slabs = n < 4096 ? 1 : n / 4096;
-    if (units * slabs >= (1LL << 31)) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)(units * slabs);
-    L.begin("k_decode_vec3");
+    const long long n = (long long)nsub * nsub * nsub;
+    A.nslabs = units * (n < 4096 ? 1 : n / 4096);
+    const bool hash = h.jmode == 1, wrap = h.wrap_L > 0.0f;
     switch (nsub) {
-        case 64: k_decode_vec3<64, 384><<<grid, 384, 0, L.stream>>>(A); break;
-        case 32: k_decode_vec3<32, 384><<<grid, 384, 0, L.stream>>>(A); break;
-        case 16: k_decode_vec3<16, 384><<<grid, 384, 0, L.stream>>>(A); break;
-        default: L.end(); return cudaErrorNotSupported;
+        case 64: return launch_decode_vec3_n<64>(L, A, hash, wrap);
+        case 32: return launch_decode_vec3_n<32>(L, A, hash, wrap);
+        case 16: return launch_decode_vec3_n<16>(L, A, hash, wrap);
     }
-    L.end();
-    L.count++;
-    return cudaGetLastError();
+    return cudaErrorNotSupported;
 }
 
 }  // namespace mnw
