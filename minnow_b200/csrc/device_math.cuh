@@ -178,7 +178,14 @@ MNW_HD uint32_t jitter_key(unsigned long long seed, unsigned long long block) {
     k = mix32((uint32_t)(block >> 32) ^ k);
     return mix32((uint32_t)block ^ k);
 }
-MNW_HD uint32_t jitter_hash_keyed(uint32_t key, uint32_t i) { return mix32(i * 0x9E3779B1U + key); }
+// two multiply-xorshift rounds over a Weyl sequence in i; the jitter is the TOP 24 bits,
+// which the final xorshift of mix32 would not touch, so it is left out
+MNW_HD uint32_t jitter_hash_keyed(uint32_t key, uint32_t i) {
+    uint32_t x = i * 0x9E3779B1U + key;
+    x ^= x >> 16; x *= 0x7feb352dU;
+    x ^= x >> 15; x *= 0x846ca68bU;
+    return x;
+}
 MNW_HD uint32_t jitter_hash32(unsigned long long seed, unsigned long long block, unsigned long long i) {
     return jitter_hash_keyed(jitter_key(seed, block), (uint32_t)i);
 }

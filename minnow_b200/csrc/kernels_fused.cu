@@ -134,12 +134,46 @@ __device__ __forceinline__ void pack32(const unsigned (&v)[32], unsigned (&o)[16
     }
 }
 
+// Write the group's 32*B stream words to dst (any byte alignment).  Interior words go
+// out as aligned 32-bit stores, 128 bytes per instruction; the bytes of the first and last
+// partial word are stored one by one, because the neighbouring groups own the rest of
+// those words.  Word j of the stream sits at region[j ^ (j >> 5)].
+template <int B>
+__device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region, int lane) {
+    const int a = (int)((uintptr_t)dst & 3);
+    uint32_t *base = (uint32_t *)(dst - a) + lane;
+    if (a == 0) {
+#pragma unroll
+        for (int m = 0; m < B; m++) base[32 * m] = region[32 * m + (lane ^ m)];
+        return;
+    }
+    const int sh = 32 - 8 * a;
+    // aligned word j (1 <= j < 32*B) = stream words j-1 and j, funnel-shifted
+    unsigned prev = 0;   // stream word 32*m - 1, wanted by lane 0
+#pragma unroll
+    for (int m = 0; m < B; m++) {
+        const unsigned hi = region[32 * m + (lane ^ m)];
+        unsigned lo = __shfl_up_sync(0xffffffffu, hi, 1);
+        if (lane == 0) lo = prev;
+        prev = __shfl_sync(0xffffffffu, hi, 31);
+        if (m > 0 || lane > 0) base[32 * m] = __funnelshift_r(lo, hi, sh);
+        else {   // head: bytes a..3 of aligned word 0 = low bytes of stream word 0
+            uint8_t *bp = (uint8_t *)base;
+            for (int k = a; k < 4; k++) bp[k] = (uint8_t)(hi >> (8 * (k - a)));
+        }
+    }
+    if (lane == 0) {   // tail: bytes 0..a-1 of aligned word 32*B = high bytes of the last stream word
+        uint8_t *bp = (uint8_t *)(base + 32 * B);
+        for (int k = 0; k < a; k++) bp[k] = (uint8_t)(prev >> (8 * (4 - a + k)));
+    }
+}
+
 // One pack group = 1024 consecutive elements of one block = 32 lanes x 32 values ->
 // 32*B words.  The words are transposed in place through the group's own 2 KiB of
 // staging (XOR swizzle: conflict-free both ways) so that the warp can write them out in
 // stream order, 128 bytes per store instruction.
 template <int B>
-__device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane) {
+__device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst) {
     unsigned o[16];
     pack32<B>(v, o);
     __syncwarp();
@@ -149,39 +183,7 @@ __device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsign
         region[W ^ (W >> 5)] = o[j];
     }
     __syncwarp();
-}
-
-// Write the group's nwords = 32*bits stream words to dst (any byte alignment).  Interior
-// words go out as aligned 32-bit stores; the bytes of the first and last partial word are
-// stored one by one, because the neighbouring groups own the rest of those words.
-__device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region, int bits, int lane) {
-    const int a = (int)((uintptr_t)dst & 3);
-    uint32_t *base = (uint32_t *)(dst - a);
-    const int nsrc = 32 * bits;
-    if (a == 0) {
-#pragma unroll 2
-        for (int j = lane; j < nsrc; j += 32) base[j] = region[j ^ (j >> 5)];
-        return;
-    }
-    const int sh = 32 - 8 * a;
-    // aligned word j (1 <= j < nsrc) = stream words j-1 and j, funnel-shifted
-#pragma unroll 2
-    for (int j = lane; j < nsrc; j += 32) {
-        if (j > 0) {
-            const unsigned lo = region[(j - 1) ^ ((j - 1) >> 5)], hi = region[j ^ (j >> 5)];
-            base[j] = __funnelshift_r(lo, hi, sh);
-        }
-    }
-    if (lane == 0) {          // head: bytes a..3 of aligned word 0 = low bytes of stream word 0
-        const unsigned w = region[0];
-        uint8_t *bp = (uint8_t *)base;
-        for (int k = a; k < 4; k++) bp[k] = (uint8_t)(w >> (8 * (k - a)));
-    } else if (lane == 1) {   // tail: bytes 0..a-1 of aligned word nsrc = high bytes of the last stream word
-        const int l = nsrc - 1;
-        const unsigned w = region[l ^ (l >> 5)];
-        uint8_t *bp = (uint8_t *)(base + nsrc);
-        for (int k = 0; k < a; k++) bp[k] = (uint8_t)(w >> (8 * (4 - a + k)));
-    }
+    write_group<B>(dst, region, lane);
 }
 
 template <int CS>
@@ -205,8 +207,8 @@ struct LocalStat {
 // ---------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------
-template <int NSUB, int CS, int NT, int UNROLL>
-__global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
+template <int NSUB, int CS, int NT, int UNROLL, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     constexpr int N = NSUB * NSUB * NSUB;   // elements per block
     constexpr int CHUNK = N / CS;           // elements per CTA and axis
     constexpr int ROWS = CHUNK / NSUB;      // sub-cell rows per CTA
@@ -219,6 +221,9 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
     static_assert((RPP * NSUB) % 512 == 0, "swizzle term must be a per-thread constant");
     static_assert(CHUNK % 1024 == 0 && N % CS == 0, "whole pack groups per CTA");
     static_assert(PASSES % UNROLL == 0 && UNROLL % 2 == 0, "batches of float4 pairs");
+    // rows of one batch: either all in one z-plane (RPP*UNROLL divides NSUB) or one row per
+    // plane step (RPP is a multiple of NSUB); both make the row offset linear in u
+    static_assert(NSUB % (RPP * UNROLL) == 0 || RPP % NSUB == 0, "batch rows are equally spaced");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *stage = (unsigned short *)smem_raw;   // [3][CHUNK], swizzled
@@ -299,11 +304,11 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
         auto batch = [&](auto exact_tag, int p0, LocalStat &ls) {
             constexpr bool EXACT = decltype(exact_tag)::value;
             float4 v[UNROLL];
+            const unsigned rowg0 = rank * ROWS + rsub + RPP * p0;
+            const float4 *p = pbase + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
+            const unsigned step = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;   // float4 units per pass
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const unsigned rowg = rank * ROWS + rsub + RPP * (p0 + u);
-                v[u] = __ldcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4));
-            }
+            for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(p + (size_t)u * step);
 #pragma unroll
             for (int u = 0; u < UNROLL; u += 2) {
                 int q[2][4];
@@ -510,16 +515,15 @@ __global__ void __launch_bounds__(NT, 1) k_fused_vec3(const FusedArgs A) {
                 }
             }
             unsigned *region = (unsigned *)(stage + k * CHUNK + gi * 1024);
+            const long long e0 = (long long)rank * CHUNK + (long long)gi * 1024;   // element index in the block
+            uint8_t *dst = A.out + (f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
             switch (fin.bits) {
-#define MNW_CASE(B) case B: pack_group_words<B>(v, region, lane); break;
+#define MNW_CASE(B) case B: pack_group_words<B>(v, region, lane, dst); break;
                 MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
                 MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
 #undef MNW_CASE
                 default: break;
             }
-            const long long e0 = (long long)rank * CHUNK + (long long)gi * 1024;   // element index in the block
-            uint8_t *dst = A.out + (f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
-            write_group(dst, region, fin.bits, lane);
         }
         par ^= 1;
     }
@@ -549,10 +553,16 @@ struct SlabAxis {
     long long pixels;
     float low, dx;
     unsigned key;          // jitter key of the block
+    unsigned mask;         // fast path: (1 << bits) - 1
     int bits;
     int shift;             // fast path: bit position of the slab's first value in the staged bytes
     int fast;              // 1: 32-bit path from shared memory
     int periodic;
+};
+struct SlabInfo {
+    long long out4;        // float4 index (in the output array) of row 0 of the slab, column 0
+    unsigned e0;           // element index of the slab's first element within its blocks
+    int fast;              // all three axes take the fast path
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -589,11 +599,12 @@ __device__ __noinline__ float decode_rare(const SlabAxis &h, long long e, int jm
 
 // Persistent CTAs walk the slabs (SLAB consecutive elements of the three axis blocks of
 // one sub-cell).  Thread 0 fetches the packed bytes of the NEXT slab with three TMA bulk
-// copies (cp.async.bulk, completion on an mbarrier) while the CTA decodes the current one;
-// every thread then produces whole float4 pieces of AoS rows, so each output row is
-// written once with coalesced 128-bit stores and no axis ever touches a sector alone.
-template <int NSUB, int NT, bool HASH, bool WRAP>
-__global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
+// copies (cp.async.bulk, completion on an mbarrier) and works out everything that is
+// uniform over the slab, while the CTA decodes the current one; every thread then
+// produces whole float4 pieces of AoS rows, so each output row is written once with
+// coalesced 128-bit stores and no axis ever touches a sector alone.
+template <int NSUB, int NT, int MINB, bool HASH, bool WRAP>
+__global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
     constexpr int N = NSUB * NSUB * NSUB;
     constexpr int SLAB = N < 4096 ? N : 4096;   // elements per slab and axis
     constexpr int SLABS = N / SLAB;
@@ -605,10 +616,11 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
     extern __shared__ __align__(128) unsigned char dsm[];   // [2][3][STAGE_BYTES]
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ SlabAxis s_hdr[2][3];
+    __shared__ SlabInfo s_info[2];
 
     const int tid = threadIdx.x;
-    const int S = A.subcells, nfile = A.nfile;
-    const unsigned row4 = 3u * (unsigned)nfile / 4u, plane4 = row4 * (unsigned)nfile;
+    const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
+    const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
     const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
     int ecol[4];
 #pragma unroll
@@ -622,27 +634,27 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
     __syncthreads();
 
     // producer: describe slab g and start the copies of its packed bytes into stage st
-    auto issue = [&](int st, long long g) {
-        const long long unit = g / SLABS;
-        const int slab = (int)(g - unit * SLABS);
-        const long long f = unit / A.sc3, sc = unit - f * A.sc3;
+    auto issue = [&](int st, unsigned g) {
+        const unsigned unit = g / SLABS, slab = g % SLABS;
+        const unsigned f = unit / sc3, sc = unit % sc3;
         const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
         unsigned bytes[3] = {0, 0, 0};
         const uint8_t *src[3] = {nullptr, nullptr, nullptr};
         unsigned total = 0;
+        int all_fast = 1;
 #pragma unroll 1
         for (int k = 0; k < 3; k++) {
-            const long long b = f * 3 * A.sc3 + k * A.sc3 + sc;
+            const long long b = ((long long)f * 3 + k) * sc3 + sc;
             const FloatParams fp = tab[k];
             SlabAxis h;
             h.mn = A.mins[b]; h.bits = (int)A.bits[b]; h.pixels = fp.pixels; h.low = fp.low; h.dx = fp.dx;
             h.periodic = (fp.flags & F_PERIODIC) ? 1 : 0;
             h.key = jitter_key(A.seed, A.block_id0 + (unsigned long long)b);
-            h.gsrc = A.data + (f * 3 + k) * A.stream_len + A.offsets[b];
-            const long long mask = (h.bits >= 1 && h.bits <= 24) ? (long long)((1u << h.bits) - 1u) : 0;
+            h.gsrc = A.data + ((long long)f * 3 + k) * A.stream_len + A.offsets[b];
+            h.mask = (h.bits >= 1 && h.bits <= 24) ? ((1u << h.bits) - 1u) : 0u;
             // 32-bit path: q = mn + v lies in [0, 2*pixels) (periodic) or [0, 2^23), and float32 holds it exactly
-            h.fast = h.bits <= 24 && h.mn >= 0 && fp.pixels > 0 && fp.pixels < (1LL << 23) &&
-                     (h.periodic ? h.mn + mask < 2 * fp.pixels : h.mn + mask < (1LL << 23));
+            h.fast = h.bits >= 0 && h.bits <= 24 && h.mn >= 0 && fp.pixels > 0 && fp.pixels < (1LL << 23) &&
+                     (h.periodic ? h.mn + (long long)h.mask < 2 * fp.pixels : h.mn + (long long)h.mask < (1LL << 23));
             h.shift = 0;
             if (h.fast && h.bits > 0) {
                 const uint8_t *p = h.gsrc + (((long long)slab * SLAB * h.bits) >> 3);
@@ -652,8 +664,17 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
                 h.shift = 8 * (int)a16;
                 total += bytes[k];
             }
+            all_fast &= h.fast;
             s_hdr[st][k] = h;
         }
+        SlabInfo info;
+        const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
+        const unsigned row0 = slab * ROWS;   // first sub-cell row of the slab
+        info.out4 = (long long)f * ((long long)plane4 * nfile) +
+                    (long long)(3u * ix0 / 4u) + (long long)(iy0 + row0 % NSUB) * row4 + (long long)(iz0 + row0 / NSUB) * plane4;
+        info.e0 = slab * SLAB;
+        info.fast = all_fast;
+        s_info[st] = info;
         const unsigned bar = smem_u32(&s_bar[st]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
 #pragma unroll
@@ -663,13 +684,16 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
                              ::"r"(smem_u32(dsm + (st * 3 + k) * STAGE_BYTES)), "l"(src[k]), "r"(bytes[k]), "r"(bar) : "memory");
     };
 
-    if (tid == 0 && (long long)blockIdx.x < A.nslabs) issue(0, blockIdx.x);
+    const unsigned nslabs = (unsigned)A.nslabs;
+    if (tid == 0 && blockIdx.x < nslabs) issue(0, blockIdx.x);
     __syncthreads();
 
+    // rows of the slab handled by this thread are rl = rsub + RPP*i: offset of row rl from the slab's row 0
+    // (a slab is one z-plane of the sub-cell when NSUB = 64, several planes otherwise)
     int it = 0;
-    for (long long g = blockIdx.x; g < A.nslabs; g += gridDim.x, it++) {
+    for (unsigned g = blockIdx.x; g < nslabs; g += gridDim.x, it++) {
         const int st = it & 1;
-        if (tid == 0 && g + gridDim.x < A.nslabs) issue(st ^ 1, g + gridDim.x);
+        if (tid == 0 && g + gridDim.x < nslabs) issue(st ^ 1, g + gridDim.x);
         {   // wait for this slab's bytes
             const unsigned bar = smem_u32(&s_bar[st]), parity = (it >> 1) & 1;
             unsigned done = 0;
@@ -677,30 +701,23 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                              : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         }
-        const long long unit = g / SLABS;
-        const int slab = (int)(g - unit * SLABS);
-        const long long f = unit / A.sc3, sc = unit - f * A.sc3;
-        const unsigned ix0 = NSUB * (unsigned)(sc % S), iy0 = NSUB * (unsigned)((sc / S) % S), iz0 = NSUB * (unsigned)(sc / ((long long)S * S));
-        float4 *pbase = (float4 *)(A.out + 3 * f * (long long)nfile * nfile * nfile) + (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
+        const SlabInfo info = s_info[st];
+        float4 *pbase = (float4 *)A.out + info.out4 + col4;
 
-        // per-axis constants in this thread's axis order
-        const uint32_t *buf[3];
-        int bits[3], shift[3], mn[3], P[3];
-        unsigned mask[3], key[3];
-        float low[3], dx[3];
-        bool fast = true;
+        if (info.fast) {
+            // per-axis constants in this thread's axis order
+            unsigned buf[3], bits[3], shift[3], mn[3], P[3], mask[3], key[3];
+            float low[3], dx[3];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const int k = (a0 + j) % 3;
-            const SlabAxis &h = s_hdr[st][k];
-            buf[j] = (const uint32_t *)(dsm + (st * 3 + k) * STAGE_BYTES);
-            bits[j] = h.bits; shift[j] = h.shift; mn[j] = (int)h.mn; P[j] = h.periodic ? (int)h.pixels : 0;
-            mask[j] = h.bits ? (0xffffffffu >> (32 - h.bits)) : 0u;
-            key[j] = h.key; low[j] = h.low; dx[j] = h.dx;
-            fast = fast && h.fast;
-        }
-
-        if (fast) {
+            for (int j = 0; j < 3; j++) {
+                const int k = (a0 + j) % 3;
+                const SlabAxis &h = s_hdr[st][k];
+                buf[j] = smem_u32(dsm + (st * 3 + k) * STAGE_BYTES);
+                bits[j] = (unsigned)h.bits; shift[j] = (unsigned)h.shift; mn[j] = (unsigned)h.mn;
+                P[j] = h.periodic ? (unsigned)h.pixels : 0u;
+                mask[j] = h.mask; key[j] = h.key + info.e0 * 0x9E3779B1U;   // hash(key, e0 + el) = f(el * M + key')
+                low[j] = h.low; dx[j] = h.dx;
+            }
 #pragma unroll 2
             for (int rl = rsub; rl < ROWS; rl += RPP) {
                 float o[4];
@@ -708,40 +725,43 @@ __global__ void __launch_bounds__(NT, 3) k_decode_vec3(const DecVec3Args A) {
                 for (int c = 0; c < 4; c++) {
                     const int j = c % 3;
                     const unsigned el = (unsigned)(rl * NSUB + ecol[c]);            // element within the slab
-                    const unsigned bp = (unsigned)shift[j] + el * (unsigned)bits[j];
-                    const uint32_t w0 = buf[j][bp >> 5], w1 = buf[j][(bp >> 5) + 1];
-                    const unsigned v = __funnelshift_r(w0, w1, bp & 31) & mask[j];  // Array.Slice, go/bit/bit.go:29-82
-                    unsigned q = (unsigned)mn[j] + v;                               // go/group.go:262
-                    q = min(q, q - (unsigned)P[j]);                                 // bound(q, 0, pixels), :303 (P = 0: not periodic)
+                    const unsigned bp = shift[j] + el * bits[j];
+                    unsigned w0, w1;
+                    const unsigned addr = buf[j] + ((bp >> 5) << 2);
+                    asm("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(addr));
+                    asm("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(addr));
+                    const unsigned v = __funnelshift_r(w0, w1, bp) & mask[j];       // Array.Slice, go/bit/bit.go:29-82
+                    unsigned q = mn[j] + v;                                          // go/group.go:262
+                    q = min(q, q - P[j]);                                            // bound(q, 0, pixels), :303 (P = 0: not periodic)
                     float t;
                     if constexpr (HASH) {
                         // u = h24 * 2^-24 is exact in float32 and q + u needs at most 47 bits: the FMA
                         // rounds once, exactly like float32(float64(q) + u) (go/group.go:308)
-                        const float hh = (float)(jitter_hash_keyed(key[j], (unsigned)slab * SLAB + el) >> 8);
-                        t = __fmaf_rn(hh, 0x1p-24f, (float)q);
+                        unsigned x = el * 0x9E3779B1U + key[j];
+                        x ^= x >> 16; x *= 0x7feb352dU;
+                        x ^= x >> 15; x *= 0x846ca68bU;
+                        t = __fmaf_rn((float)(x >> 8), 0x1p-24f, (float)q);
                     } else {
                         t = __fadd_rn((float)q, 0.5f);   // q < 2^23: exact
                     }
                     float x = __fadd_rn(__fmul_rn(dx[j], t), low[j]);
-                    if constexpr (WRAP) {                                           // go/minp/minp.go:195-203
-                        if (x < 0.0f) x = __fadd_rn(x, A.wrap_L);
-                        else if (x >= A.wrap_L) x = __fsub_rn(x, A.wrap_L);
+                    if constexpr (WRAP) {                                            // go/minp/minp.go:195-203
+                        const float xp = __fadd_rn(x, A.wrap_L), xm = __fsub_rn(x, A.wrap_L);
+                        x = x < 0.0f ? xp : (x >= A.wrap_L ? xm : x);
                     }
                     o[c] = x;
                 }
-                const unsigned rowg = (unsigned)(slab * ROWS + rl);
-                __stcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));   // setSubCell, :270-288
+                __stcs(pbase + ((unsigned)(rl / NSUB) * plane4 + (unsigned)(rl % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));   // setSubCell, :270-288
             }
         } else {
             for (int rl = rsub; rl < ROWS; rl += RPP) {
                 float o[4];
                 for (int c = 0; c < 4; c++) {
                     const int k = (a0 + c) % 3;
-                    const long long e = (long long)slab * SLAB + rl * NSUB + ecol[c];
+                    const long long e = (long long)info.e0 + rl * NSUB + ecol[c];
                     o[c] = decode_rare(s_hdr[st][k], e, HASH ? 1 : 0, WRAP ? A.wrap_L : 0.0f);
                 }
-                const unsigned rowg = (unsigned)(slab * ROWS + rl);
-                __stcs(pbase + ((rowg / NSUB) * plane4 + (rowg % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));
+                __stcs(pbase + ((unsigned)(rl / NSUB) * plane4 + (unsigned)(rl % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));
             }
         }
         __syncthreads();   // stage st and its header may be refilled from the next iteration on
@@ -798,9 +818,9 @@ bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile,
     return true;
 }
 
-template <int NSUB, int CS, int NT, int UNROLL>
+template <int NSUB, int CS, int NT, int UNROLL, int MINB>
 static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
-    auto kern = k_fused_vec3<NSUB, CS, NT, UNROLL>;
+    auto kern = k_fused_vec3<NSUB, CS, NT, UNROLL, MINB>;
     const size_t smem = (size_t)6 * (NSUB * NSUB * NSUB / CS);
     static bool configured = false;
     static int max_clusters = 0;
@@ -814,6 +834,10 @@ static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
     if (!configured) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        if (CS > 8) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
         cfg.gridDim = dim3(CS);
         e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
         if (e != cudaSuccess) return e;
@@ -845,12 +869,20 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
     if (A.nunits == 0) return cudaSuccess;
     switch (nfile / subcells) {
         case 64: {
-            static const int nt = getenv("MNW_FUSED_NT") ? atoi(getenv("MNW_FUSED_NT")) : 768;   // tuning knob
-            if (nt == 384) return launch_fused_vec3_t<64, 8, 384, 8>(L, A);
-            return launch_fused_vec3_t<64, 8, 768, 4>(L, A);
+            // tuning knob: 0 = 16-CTA cluster, 2 CTAs per SM (default when it can be scheduled);
+            // 384 / 768 = 8-CTA cluster, 1 CTA per SM with that many threads
+            static int variant = getenv("MNW_FUSED_NT") ? atoi(getenv("MNW_FUSED_NT")) : 0;
+            if (variant == 0) {
+                cudaError_t e = launch_fused_vec3_t<64, 16, 384, 4, 2>(L, A);
+                if (e == cudaSuccess) return e;
+                (void)cudaGetLastError();   // 16-CTA clusters are a non-portable size: fall back to 8
+                variant = 384;
+            }
+            if (variant == 768) return launch_fused_vec3_t<64, 8, 768, 4, 1>(L, A);
+            return launch_fused_vec3_t<64, 8, 384, 8, 1>(L, A);
         }
-        case 32: return launch_fused_vec3_t<32, 1, 768, 4>(L, A);
-        case 16: return launch_fused_vec3_t<16, 1, 384, 4>(L, A);
+        case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1>(L, A);
+        case 16: return launch_fused_vec3_t<16, 1, 384, 4, 1>(L, A);
     }
     return cudaErrorNotSupported;
 }
@@ -864,10 +896,10 @@ bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out) {
 
 template <int NSUB, bool HASH, bool WRAP>
 static cudaError_t launch_decode_vec3_t(Launcher &L, const DecVec3Args &A) {
-    constexpr int NT = 384;
+    constexpr int NT = 384, MINB = 3;
     constexpr int N = NSUB * NSUB * NSUB, SLAB = N < 4096 ? N : 4096;
     constexpr size_t smem = (size_t)2 * 3 * (SLAB * 3 + 32);
-    auto kern = k_decode_vec3<NSUB, NT, HASH, WRAP>;
+    auto kern = k_decode_vec3<NSUB, NT, MINB, HASH, WRAP>;
     static bool configured = false;
     static int per_sm = 1;
     if (!configured) {
@@ -909,6 +941,7 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
     const int nsub = h.nfile / h.subcells;
     const long long n = (long long)nsub * nsub * nsub;
     A.nslabs = units * (n < 4096 ? 1 : n / 4096);
+    if (A.nslabs >= (1LL << 31)) return cudaErrorInvalidValue;
     const bool hash = h.jmode == 1, wrap = h.wrap_L > 0.0f;
     switch (nsub) {
         case 64: return launch_decode_vec3_n<64>(L, A, hash, wrap);
