@@ -313,7 +313,14 @@ def run_gpu(args):
     pk_total = packed_bytes["x"] + packed_bytes["v"]
     algo = {  # algorithmic bytes per step, summed over both fields (DESIGN.md "Kernels")
         "k_stats": 2 * field_bytes, "k_pack": 2 * field_bytes + pk_total,
-        "k_fused_vec3": 2 * field_bytes + pk_total, "k_decode": pk_total + 2 * field_bytes}
+        "k_fused_vec3": 2 * field_bytes + pk_total, "k_decode": pk_total + 2 * field_bytes,
+        "k_decode_vec3": pk_total + 2 * field_bytes}
+    traffic = {}
+    try:   # DRAM bytes per particle and launch from the committed ncu --set full capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     roof = None
     if prof:
         top = max(prof, key=lambda r: r["ms"])
@@ -322,12 +329,17 @@ def run_gpu(args):
         a = algo.get(top["kernel"], 0) / launches_per_step / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": a / peaks["hbm_gbs"], "peak_source": peaks["src"] + " (MEASURED_PEAKS.json copy bandwidth)",
-                "traffic": None, "ms_per_launch": per_launch_ms,
+                "traffic": (traffic[top["kernel"]]["dram_bytes_per_particle"] * NSIDE ** 3
+                            if top["kernel"] in traffic else None),
+                "traffic_source": traffic.get(top["kernel"], {}).get("source"),
+                "ms_per_launch": per_launch_ms,
                 "algorithmic_bytes_per_launch": algo.get(top["kernel"], 0) / launches_per_step,
-                "kernels": [dict(r, share=r["ms"] / (ms_total)) for r in prof]}
+                "kernels": [dict(r, share=r["ms"] / (ms_total),
+                                 achieved_gbs=(algo.get(r["kernel"], 0) * args.steps / (r["ms"] * 1e-3) / 1e9 if r["ms"] else None))
+                            for r in prof]}
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ------
-    e2e = run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev)
+    e2e = None if args.no_e2e else run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev)
 
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on the host cores ----------
     cpu = None
@@ -436,6 +448,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

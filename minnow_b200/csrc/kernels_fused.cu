@@ -173,7 +173,8 @@ __device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region
 // staging (XOR swizzle: conflict-free both ways) so that the warp can write them out in
 // stream order, 128 bytes per store instruction.
 template <int B>
-__device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst) {
+__device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst0,
+                                                 const long long *off, const int *offgen, int gen) {
     unsigned o[16];
     pack32<B>(v, o);
     __syncwarp();
@@ -182,14 +183,22 @@ __device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsign
         const int W = lane * B + j;
         region[W ^ (W >> 5)] = o[j];
     }
+    // the block's byte offset is posted by the look-back warp of its axis
+    while (*(const volatile int *)offgen != gen) { }
     __syncwarp();
-    write_group<B>(dst, region, lane);
+    const long long o64 = *(const volatile long long *)off;
+    if (o64 >= 0) write_group<B>(dst0 + o64, region, lane);
 }
 
+// Cluster-wide barrier with release/acquire at cluster scope: all it has to order are the
+// distributed-shared-memory stores of the statistics exchange.
 template <int CS>
 __device__ __forceinline__ void cluster_sync_all() {
-    if constexpr (CS > 1) cg::this_cluster().sync();
-    else __syncthreads();
+    if constexpr (CS > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
 }
 
 // Batch-local statistics of phase 1, in the thread's relative axis order.
@@ -207,7 +216,7 @@ struct LocalStat {
 // ---------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------
-template <int NSUB, int CS, int NT, int UNROLL, int MINB>
+template <int NSUB, int CS, int NT, int UNROLL, int MINB, bool PIPE>
 __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     constexpr int N = NSUB * NSUB * NSUB;   // elements per block
     constexpr int CHUNK = N / CS;           // elements per CTA and axis
@@ -232,6 +241,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     __shared__ unsigned s_red[NW][3][5];
     __shared__ Fin s_fin[3];
     __shared__ long long s_q0[3];
+    __shared__ long long s_off[3];     // byte offset of the unit's blocks (-1: does not fit the output)
+    __shared__ int s_offgen[3];        // == gen once s_off is valid for this unit
+    __shared__ int s_gctr;             // next pack group of the unit
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned rank = 0;
@@ -250,7 +262,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     const int S = A.subcells, nfile = A.nfile;
     const unsigned row4 = 3u * (unsigned)nfile / 4u, plane4 = row4 * (unsigned)nfile;   // float4 units
 
-    int par = 0;
+    int par = 0, gen = 1;
+    if (tid < 3) s_offgen[tid] = 0;
     if (rank == 0 && tid == 0) {
         const long long u = (long long)atomicAdd(A.W.ticket, 1u);
         if constexpr (CS > 1) {
@@ -301,14 +314,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
         // A batch = UNROLL float4 per thread.  The fast quantiser is trusted only for pixel
         // indices in [1, pixels): the batch minimum and maximum tell whether every element
         // qualified; if not (rare) the batch is redone with the IEEE divide.
-        auto batch = [&](auto exact_tag, int p0, LocalStat &ls) {
-            constexpr bool EXACT = decltype(exact_tag)::value;
-            float4 v[UNROLL];
+        auto load = [&](int p0, float4 (&v)[UNROLL]) {
             const unsigned rowg0 = rank * ROWS + rsub + RPP * p0;
             const float4 *p = pbase + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
             const unsigned step = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;   // float4 units per pass
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(p + (size_t)u * step);
+        };
+        auto batch = [&](auto exact_tag, int p0, const float4 (&v)[UNROLL], LocalStat &ls) {
+            constexpr bool EXACT = decltype(exact_tag)::value;
 #pragma unroll
             for (int u = 0; u < UNROLL; u += 2) {
                 int q[2][4];
@@ -340,23 +354,43 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
                 }
             }
         };
-#pragma unroll 1
-        for (int p0 = 0; p0 < PASSES; p0 += UNROLL) {
+        auto step = [&](int p0, float4 (&v)[UNROLL]) {
             LocalStat ls;
             ls.reset();
-            batch(std::false_type{}, p0, ls);
+            batch(std::false_type{}, p0, v, ls);
             bool ok = true;
 #pragma unroll
             for (int j = 0; j < 3; j++)
                 ok = ok && (unsigned)(ls.qmin[j] - 1) < Pm1[j] && (unsigned)(ls.qmax[j] - 1) < Pm1[j];
             if (!ok) {
                 ls.reset();
-                batch(std::true_type{}, p0, ls);
+                load(p0, v);
+                batch(std::true_type{}, p0, v, ls);
             }
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 run.wmin[j] = min(run.wmin[j], ls.wmin[j]); run.wmax[j] = max(run.wmax[j], ls.wmax[j]);
                 run.qmin[j] = min(run.qmin[j], ls.qmin[j]); run.qmax[j] = max(run.qmax[j], ls.qmax[j]);
+            }
+        };
+        if constexpr (PIPE) {
+            // two register buffers, ping-pong: the loads of batch i+1 are in flight while batch i is quantised
+            static_assert(!PIPE || PASSES % (2 * UNROLL) == 0, "pairs of batches");
+            float4 va[UNROLL], vb[UNROLL];
+            load(0, va);
+#pragma unroll 1
+            for (int p0 = 0; p0 < PASSES; p0 += 2 * UNROLL) {
+                load(p0 + UNROLL, vb);
+                step(p0, va);
+                if (p0 + 2 * UNROLL < PASSES) load(p0 + 2 * UNROLL, va);
+                step(p0 + UNROLL, vb);
+            }
+        } else {
+            float4 v[UNROLL];
+#pragma unroll 1
+            for (int p0 = 0; p0 < PASSES; p0 += UNROLL) {
+                load(p0, v);
+                step(p0, v);
             }
         }
 
@@ -415,18 +449,17 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
             }
         }
 
-        // ---- finalise + look-back: warp k handles axis k (every CTA, redundantly) ----
+        // ---- finalise: warp k combines the cluster's statistics of axis k (every CTA, redundantly) ----
+        long long f_off = 0, f_nbytes = 0, f_b = 0;   // warps 0..2 only
         if (warp < 3) {
             const int k = warp;
-            const long long b = f * 3 * A.sc3 + k * A.sc3 + sc;      // block id in the batch
-            const long long chain0 = b - sc;                          // first block of the group
-            XStat x = s_x[par][0][k];
-            for (int r = 1; r < CS; r++) {
-                const XStat y = s_x[par][r][k];
-                x.wmin = min(x.wmin, y.wmin); x.wmax = max(x.wmax, y.wmax);
-                x.qmin = min(x.qmin, y.qmin); x.qmax = max(x.qmax, y.qmax);
-                x.oob |= y.oob;
-            }
+            f_b = f * 3 * A.sc3 + k * A.sc3 + sc;                    // block id in the batch
+            XStat x;
+            x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
+            if (lane < CS) x = s_x[par][lane][k];
+            x.wmin = __reduce_min_sync(0xffffffffu, x.wmin); x.wmax = __reduce_max_sync(0xffffffffu, x.wmax);
+            x.qmin = __reduce_min_sync(0xffffffffu, x.qmin); x.qmax = __reduce_max_sync(0xffffffffu, x.qmax);
+            x.oob = __reduce_or_sync(0xffffffffu, x.oob);
             const FloatParams fp = tab[k];
             const long long Pk = fp.pixels, half = Pk / 2, K = Pk - half - 1;
             const long long q0k = s_q0[k];
@@ -446,43 +479,64 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
                 pmin = m; mn = m; maxoff = spread - 1ULL;
                 base = x.wmin; padj = 0;
             }
-            int bits = precision_needed(maxoff);
+            // bit.PrecisionNeeded: below 2^48 Go's float64 log2 agrees with the integer bit length
+            int bits = maxoff < (1ULL << 48) ? 64 - __clzll((long long)maxoff) : precision_needed(maxoff);
             long long nbytes = array_bytes(bits, N);
             const bool slow = x.oob != 0;
             if (slow) { bits = 0; nbytes = 0; }
-            if (rank == 0 && lane == 0) st_relaxed(A.W.pub + b, PUB_AGG | (unsigned long long)nbytes);
-            const long long off = lookback(A.W.pub, chain0, b);
+            f_nbytes = nbytes;
+            if (rank == 0 && lane == 0) st_relaxed(A.W.pub + f_b, PUB_AGG | (unsigned long long)nbytes);
             // staged values are the low 16 bits of w: enough when the packed value has <= 16 bits
             // and (wide arcs) w itself fits, i.e. pixels <= 65536
-            int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
+            const int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
             if (lane == 0) {
-                if (off + nbytes > A.axis_stride) {   // never write past the caller's buffer
-                    mode = 0;
-                    if (rank == 0) atomicExch(A.W.err, 2);
-                } else if (rank == 0 && !slow && bits > 0 && mode == 0) {
-                    A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = b;
-                }
+                Fin fin;
+                fin.off = 0; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj;
+                s_fin[k] = fin;
                 if (rank == 0) {
-                    st_relaxed(A.W.pub + b, PUB_PREFIX | (unsigned long long)(off + nbytes));
+                    if (!slow && bits > 0 && mode == 0) A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = f_b;
                     if (slow) atomicExch(A.W.abort_flag, 1);
                     BlockStat st = {};
-                    st.pmin = pmin; st.min = mn; st.nbytes = nbytes; st.out_off = off; st.do_bound = 1; st.bits = bits;
+                    st.pmin = pmin; st.min = mn; st.nbytes = nbytes; st.out_off = 0; st.do_bound = 1; st.bits = bits;
                     st.q0 = q0k; st.oob = x.oob;
-                    A.stats[b] = st;
-                    if (A.mins) A.mins[b] = mn;
-                    if (A.bits) A.bits[b] = bits;
-                    if (A.offsets) A.offsets[b] = off;
-                    if (A.out_len && sc == A.sc3 - 1) A.out_len[f * 3 + k] = off + nbytes;
+                    A.stats[f_b] = st;
+                    if (A.mins) A.mins[f_b] = mn;
+                    if (A.bits) A.bits[f_b] = bits;
                 }
-                Fin fin;
-                fin.off = off; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj;
-                s_fin[k] = fin;
             }
         }
+        if (tid == 0) s_gctr = 0;
         __syncthreads();
 
+        // ---- byte offsets: warps 0..2 walk back over the earlier sub-cells of the group while the
+        // other warps already pack; a group is written out once its block's offset is posted ----
+        if (warp < 3) {
+            const int k = warp;
+            long long off = lookback(A.W.pub, f_b - sc, f_b);
+            if (lane == 0) {
+                if (off + f_nbytes > A.axis_stride) {   // never write past the caller's buffer
+                    if (rank == 0) atomicExch(A.W.err, 2);
+                    s_off[k] = -1;
+                } else {
+                    s_off[k] = off;
+                }
+                if (rank == 0) {
+                    st_relaxed(A.W.pub + f_b, PUB_PREFIX | (unsigned long long)(off + f_nbytes));
+                    A.stats[f_b].out_off = off;
+                    if (A.offsets) A.offsets[f_b] = off;
+                    if (A.out_len && sc == A.sc3 - 1) A.out_len[f * 3 + k] = off + f_nbytes;
+                }
+                __threadfence_block();
+                *(volatile int *)&s_offgen[k] = gen;
+            }
+        }
+
         // ---- phase 2: pack groups of 1024 elements straight from shared memory ----
-        for (int g = warp; g < 3 * GPA; g += NW) {
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&s_gctr, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= 3 * GPA) break;
             const int k = g / GPA, gi = g - k * GPA;
             const Fin fin = s_fin[k];
             if (fin.mode == 0) continue;
@@ -516,9 +570,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
             }
             unsigned *region = (unsigned *)(stage + k * CHUNK + gi * 1024);
             const long long e0 = (long long)rank * CHUNK + (long long)gi * 1024;   // element index in the block
-            uint8_t *dst = A.out + (f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
+            uint8_t *dst0 = A.out + (f * 3 + k) * A.axis_stride + ((e0 * fin.bits) >> 3);
             switch (fin.bits) {
-#define MNW_CASE(B) case B: pack_group_words<B>(v, region, lane, dst); break;
+#define MNW_CASE(B) case B: pack_group_words<B>(v, region, lane, dst0, &s_off[k], &s_offgen[k], gen); break;
                 MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
                 MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
 #undef MNW_CASE
@@ -526,6 +580,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
             }
         }
         par ^= 1;
+        gen++;
     }
 }
 
@@ -818,9 +873,9 @@ bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile,
     return true;
 }
 
-template <int NSUB, int CS, int NT, int UNROLL, int MINB>
+template <int NSUB, int CS, int NT, int UNROLL, int MINB, bool PIPE>
 static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
-    auto kern = k_fused_vec3<NSUB, CS, NT, UNROLL, MINB>;
+    auto kern = k_fused_vec3<NSUB, CS, NT, UNROLL, MINB, PIPE>;
     const size_t smem = (size_t)6 * (NSUB * NSUB * NSUB / CS);
     static bool configured = false;
     static int max_clusters = 0;
@@ -869,20 +924,21 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
     if (A.nunits == 0) return cudaSuccess;
     switch (nfile / subcells) {
         case 64: {
-            // tuning knob: 0 = 16-CTA cluster, 2 CTAs per SM (default when it can be scheduled);
-            // 384 / 768 = 8-CTA cluster, 1 CTA per SM with that many threads
-            static int variant = getenv("MNW_FUSED_NT") ? atoi(getenv("MNW_FUSED_NT")) : 0;
+            // tuning knob: 384 (default) / 385 / 768 = 8-CTA cluster, 1 CTA per SM with 384 threads
+            // (pipelined loads / 8-deep batches) or 768 threads; 0 = 16-CTA cluster, 2 CTAs per SM
+            static int variant = getenv("MNW_FUSED_NT") ? atoi(getenv("MNW_FUSED_NT")) : 384;
             if (variant == 0) {
-                cudaError_t e = launch_fused_vec3_t<64, 16, 384, 4, 2>(L, A);
+                cudaError_t e = launch_fused_vec3_t<64, 16, 384, 4, 2, false>(L, A);
                 if (e == cudaSuccess) return e;
                 (void)cudaGetLastError();   // 16-CTA clusters are a non-portable size: fall back to 8
                 variant = 384;
             }
-            if (variant == 768) return launch_fused_vec3_t<64, 8, 768, 4, 1>(L, A);
-            return launch_fused_vec3_t<64, 8, 384, 8, 1>(L, A);
+            if (variant == 768) return launch_fused_vec3_t<64, 8, 768, 4, 1, false>(L, A);
+            if (variant == 385) return launch_fused_vec3_t<64, 8, 384, 8, 1, false>(L, A);
+            return launch_fused_vec3_t<64, 8, 384, 4, 1, true>(L, A);
         }
-        case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1>(L, A);
-        case 16: return launch_fused_vec3_t<16, 1, 384, 4, 1>(L, A);
+        case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
+        case 16: return launch_fused_vec3_t<16, 1, 384, 4, 1, true>(L, A);
     }
     return cudaErrorNotSupported;
 }
