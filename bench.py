@@ -186,6 +186,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import minnow_b200 as mb
+    from minnow_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,9 +219,6 @@ def run_gpu(args):
     out_len = {k: torch.zeros(3 * NFILES, **i64) for k in ("x", "v")}
     packed = {k: torch.empty(3 * NFILES * stride, dtype=torch.uint8, device=dev) for k in ("x", "v")}
     decoded = torch.empty((NFILES, NP_FILE, 3), dtype=torch.float32, device=dev)
-    sizes_all = torch.zeros(world * 2 * nb, **i64)
-    offs_all = torch.zeros(world * 2 * nb, **i64)
-    total_all = torch.zeros(1, **i64)
 
     ppx = mb.float_group_pixels(0.0, L_BOX, DX_POS)
     pdescs = [mb.FloatDesc.make(0.0, L_BOX, ppx) for _ in range(3)]
@@ -248,9 +246,8 @@ def run_gpu(args):
             if world > 1:
                 # the one exchange of the sharded path: all-gather per-block packed sizes, then every
                 # rank scans them to the global byte offsets
-                local = torch.cat([(meta[k][1] * NSUB3 + 7) >> 3 for k in ("x", "v")])
-                dist.all_gather_into_tensor(sizes_all, local)
-                ctx.scan_offsets_dev(sizes_all, sizes_all.numel(), 0, offs_all, total_all)
+                local = torch.cat([shard.packed_sizes(meta[k][1], NSUB3) for k in ("x", "v")])
+                state["global"] = shard.global_offsets(local, world * 2 * nb, SC3, ctx=ctx)
             ctx.decode_vec3_subcells_dev(pdescs, packed["x"], stride, meta["x"][2], meta["x"][0], meta["x"][1],
                                          NFILE, SUB_CELLS, NFILES, L_BOX, jit, decoded)
             if record: e[3].record(stream)
