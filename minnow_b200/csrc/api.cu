@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,7 +50,7 @@ struct mnw_ctx {
     std::string err;
     int last_path = 0;
     int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, flat_ws, flat_scratch;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
 };
 
@@ -350,7 +351,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params})
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->flat_ws, &ctx->flat_scratch})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     cudaStreamDestroy(ctx->L.stream);
@@ -541,8 +542,18 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         W.repack_list = (int64_t *)(W.pub + nb);
         W.err = d_flags + 1; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
         CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
-        cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
-                                          ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride);
+        static const bool use_cluster = getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "cluster");   // tuning knob
+        cudaError_t e;
+        if (use_cluster) {
+            e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
+                                  ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride);
+        } else {
+            CU(ctx->flat_ws.reserve(flat_work_bytes(nfiles * sc3)));
+            CU(ctx->flat_scratch.reserve(flat_scratch_bytes()));
+            e = launch_flat_vec3(ctx->L, W, ctx->flat_ws.p, ctx->flat_scratch.p, tab, desc_per_file, aos, (int)nfile,
+                                 (int)subcells, nfiles, ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out,
+                                 out_axis_stride);
+        }
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
         // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
         launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,

@@ -110,6 +110,15 @@ __device__ long long lookback(const unsigned long long *pub, long long first, lo
     return sum;
 }
 
+// Streaming 128-bit load that the compiler may not move across other memory operations: the
+// software pipeline below relies on the loads of the NEXT batch being issued before the
+// current batch is processed (nvcc otherwise sinks them to save registers).
+__device__ __forceinline__ float4 ld_stream_pinned(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // Exact lane path of the quantiser: anything the fast quotient could not vouch for.
 // Returns the folded pixel index (pixels -> 0) or flags the element out of range.
 __device__ __noinline__ int quantize_rare(float x, float low, float dx, int P, unsigned &oob) {
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
             const float4 *p = pbase + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
             const unsigned step = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;   // float4 units per pass
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) v[u] = __ldcs(p + (size_t)u * step);
+            for (int u = 0; u < UNROLL; u++) v[u] = ld_stream_pinned(p + (size_t)u * step);
         };
         auto batch = [&](auto exact_tag, int p0, const float4 (&v)[UNROLL], LocalStat &ls) {
             constexpr bool EXACT = decltype(exact_tag)::value;
@@ -581,6 +590,431 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
         }
         par ^= 1;
         gen++;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// encode, flat variant: no clusters.  A unit (sub-cell) is cut into tiles of 4096
+// particles; every tile is visited twice by independent CTAs, in ticket order:
+//   A-tile  read the AoS rows once, quantise, accumulate the block statistics with
+//           atomics, and park the 16-bit rotated pixel indices, planar per axis, in a
+//           scratch RING in global memory (24 MB: it lives in L2, the input stream is
+//           read with evict-first loads);
+//   B-tile  D units later: fetch the parked indices (L2), subtract the block origin, pack
+//           with compile-time bit width and write the bytes to their final offset.
+// The CTA that completes the last A-tile of a unit finalises it: (min, bits, nbytes), the
+// decoupled look-back over the earlier sub-cells of the file, and a `ready` flag.
+// Tickets are handed out in an order in which everything a CTA can wait for (ready flag,
+// ring slot, look-back words) belongs to LOWER tickets, i.e. to CTAs that are running or
+// done: no co-residency assumption, no deadlock.
+// ---------------------------------------------------------------------------
+struct UFin {   // finalised block, as the B-tiles need it
+    long long off;
+    int bits, mode;
+    unsigned base, padj;
+    unsigned pad0, pad1;
+};
+
+struct FlatArgs {
+    const float *aos;
+    const FloatParams *tab;
+    int tab_per_file;
+    int nfile, subcells;
+    int nunits, sc3;
+    int D, R;                 // B-runs follow D units behind the A-runs; the scratch ring holds R units
+    const long long *q0tab;   // [nunits][3] exact pixel index of x[0] of every block (k_unit_q0)
+    BlockStat *stats;
+    int64_t *mins, *bits, *offsets, *out_len;
+    uint8_t *out;
+    long long axis_stride;
+    unsigned *ustat;          // [nunits][3][4]: ~wmin, wmax, ~qmin, qmax (atomicMax, zero-initialised)
+    unsigned *uoob;           // [nunits]
+    int *adone, *bdone, *ready;   // [nunits] each
+    UFin *ufin;               // [nunits][3]
+    unsigned short *scratch;  // [R][3][N]
+    FusedWork W;
+};
+
+__device__ __forceinline__ int ld_volatile_i32(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int B>
+__device__ __forceinline__ void pack_group_flat(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst) {
+    unsigned o[16];
+    pack32<B>(v, o);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        const int W = lane * B + j;
+        region[W ^ (W >> 5)] = o[j];
+    }
+    __syncwarp();
+    write_group<B>(dst, region, lane);
+}
+
+// x[0] of every block, quantised exactly: fixes the rotation of the arc statistics of its unit.
+__global__ void k_unit_q0(const FlatArgs A, long long *q0tab, int nsub) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * A.nunits) return;
+    const unsigned unit = i / 3, k = i % 3;
+    const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
+    const unsigned f = unit / sc3, sc = unit % sc3;
+    const unsigned ix0 = nsub * (sc % S), iy0 = nsub * ((sc / S) % S), iz0 = nsub * (sc / (S * S));
+    const float *cube = A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile);
+    const FloatParams fp = A.tab[(A.tab_per_file ? 3 * f : 0) + k];
+    const unsigned long long idx0 = ix0 + (unsigned long long)iy0 * nfile + (unsigned long long)iz0 * nfile * nfile;
+    q0tab[i] = quantize_exact(__ldg(cube + 3 * idx0 + k), fp.low, fp.dx);
+}
+
+template <int NSUB, int NT, int UNROLL, int MINB, int GMAX>
+__global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
+    constexpr int N = NSUB * NSUB * NSUB;
+    constexpr int TILE = N < 4096 ? N : 4096;   // particles per tile
+    constexpr int TPU = N / TILE;               // tiles per unit
+    constexpr int G = TPU < GMAX ? TPU : GMAX;  // tiles per run = per claimed ticket
+    constexpr int RPU = TPU / G;                // runs per unit
+    constexpr int ROWS = TILE / NSUB;
+    constexpr int R4 = 3 * NSUB / 4;
+    constexpr int RPP = NT / R4;
+    constexpr int PASSES = ROWS / RPP;
+    constexpr int BPT = PASSES / UNROLL;        // batches per tile
+    constexpr int GPA = TILE / 1024;            // pack groups per tile and axis
+    constexpr int NW = NT / 32;
+    static_assert(NT % R4 == 0 && ROWS % RPP == 0, "threads tile the rows exactly");
+    static_assert(PASSES % (2 * UNROLL) == 0 && UNROLL % 2 == 0, "pairs of batches of float4 pairs");
+    static_assert(NSUB % (RPP * UNROLL) == 0 || RPP % NSUB == 0, "batch rows are equally spaced");
+    static_assert(3 * TILE * 2 >= NW * 2048, "transposition regions fit one staging buffer");
+
+    extern __shared__ __align__(16) unsigned char flat_smem[];
+    // double buffered: tile p is parked while tile p+1 is quantised
+    unsigned short (*stage)[3 * TILE] = (unsigned short (*)[3 * TILE])flat_smem;
+    __shared__ unsigned s_red[NW][3][5];
+    __shared__ unsigned s_ticket[2];
+    __shared__ UFin s_fin[3];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
+    int soff[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) soff[c] = ((a0 + c) % 3) * TILE + rsub * NSUB + (4 * col4 + c) / 3;
+    const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
+    const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
+    // Tickets: per unit-step first the RPU A-runs of unit `step`, then the RPU B-runs of unit
+    // `step - D`.  Everything a run can wait for (ring slot, ready flag, look-back words) belongs
+    // to lower tickets, i.e. to CTAs that are running or done.
+    const unsigned total = (unsigned)(A.nunits + A.D) * (2u * RPU);
+    if (tid == 0) s_ticket[0] = atomicAdd(A.W.ticket, 1u);
+    __syncthreads();
+    float4 va[UNROLL], vb[UNROLL];   // the load pipeline of the A-runs lives across runs
+    bool preloaded = false;
+    for (int it = 0;; it++) {
+        const unsigned t = s_ticket[it & 1];
+        if (t >= total) break;
+        if (tid == 0) s_ticket[(it + 1) & 1] = atomicAdd(A.W.ticket, 1u);   // the next run, claimed a whole run ahead
+        const unsigned step = t / (2u * RPU), r = t % (2u * RPU);
+        const bool isA = r < (unsigned)RPU;
+        const int unit = isA ? (int)step : (int)step - A.D;
+        const unsigned tile0 = (isA ? r : r - RPU) * G;
+        if (unit < 0 || unit >= A.nunits) { __syncthreads(); continue; }
+        const unsigned f = (unsigned)unit / sc3, sc = (unsigned)unit % sc3;
+        const int slot = unit % A.R;
+
+        if (isA) {
+            // ================= A-run: G tiles of one unit =================
+            const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
+            const float *cube = A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile);
+            const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
+            float low[3], rcp[3], ndx[3];
+            int P[3];
+            unsigned Pm1[3], C[3];
+            unsigned oob = 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int ax = (a0 + j) % 3;
+                const FloatParams fp = tab[ax];
+                low[j] = fp.low; rcp[j] = fp.rcp; ndx[j] = -fp.dx;
+                P[j] = (int)fp.pixels;
+                Pm1[j] = (fp.flags & F_FASTDIV) ? (unsigned)(P[j] - 1) : 0u;
+                const long long q0 = A.q0tab[(size_t)unit * 3 + ax];
+                const bool ok = (unsigned long long)q0 < (unsigned long long)fp.pixels;
+                C[j] = ok ? (unsigned)arc_rotation(q0, fp.pixels) : 0u;
+                if (!ok) oob = 1;   // periodicMin starting outside [0, pixels): exact path only
+            }
+            const float4 *pbase = (const float4 *)cube + (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
+            if (tid == 32 && unit >= A.R) {   // the ring slot is free once the unit that used it is packed
+                while (ld_volatile_i32(A.bdone + (unit - A.R)) < TPU) { __nanosleep(100); }
+            }
+            LocalStat run;
+            run.reset();
+            // batch b of the run: tile tile0 + b / BPT, passes (b % BPT) * UNROLL ...
+            auto load = [&](int b, float4 (&v)[UNROLL]) {
+                const unsigned rowg0 = (tile0 + b / BPT) * ROWS + rsub + RPP * ((b % BPT) * UNROLL);
+                const float4 *p = pbase + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
+                const unsigned stp = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) v[u] = ld_stream_pinned(p + (size_t)u * stp);
+            };
+            auto batch = [&](auto exact_tag, int b, const float4 (&v)[UNROLL], LocalStat &ls) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                unsigned short *stg = stage[(b / BPT) & 1] + ((b % BPT) * UNROLL) * (RPP * NSUB);
+#pragma unroll
+                for (int u = 0; u < UNROLL; u += 2) {
+                    int q[2][4];
+                    unsigned w[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float x[4] = {v[u + h].x, v[u + h].y, v[u + h].z, v[u + h].w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int j = c % 3;
+                            if constexpr (EXACT) q[h][c] = quantize_rare(x[c], low[j], -ndx[j], P[j], oob);
+                            else q[h][c] = quantize_fast(x[c], low[j], rcp[j], ndx[j]);
+                            const unsigned tt = (unsigned)q[h][c] + C[j];
+                            w[h][c] = min(tt, tt - (unsigned)P[j]);
+                            stg[soff[c] + (u + h) * (RPP * NSUB)] = (unsigned short)w[h][c];
+                        }
+                    }
+                    ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[0][0], q[0][3]); ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[1][0], q[1][3]);
+                    ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[0][0], q[0][3]); ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[1][0], q[1][3]);
+                    ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[0][0], w[0][3]); ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[1][0], w[1][3]);
+                    ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[0][0], w[0][3]); ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[1][0], w[1][3]);
+#pragma unroll
+                    for (int j = 1; j < 3; j++) {
+                        ls.qmin[j] = __vimin3_s32(ls.qmin[j], q[0][j], q[1][j]);
+                        ls.qmax[j] = __vimax3_s32(ls.qmax[j], q[0][j], q[1][j]);
+                        ls.wmin[j] = __vimin3_u32(ls.wmin[j], w[0][j], w[1][j]);
+                        ls.wmax[j] = __vimax3_u32(ls.wmax[j], w[0][j], w[1][j]);
+                    }
+                }
+            };
+            // park tile `pl` of the run: its 16-bit indices go to the scratch ring, planar per axis
+            auto park = [&](int pl) {
+                unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)(tile0 + pl) * TILE;
+                const unsigned short *stg = stage[pl & 1];
+                for (int i = tid; i < 3 * TILE / 8; i += NT) {
+                    const int k = i / (TILE / 8), wdx = i - k * (TILE / 8);
+                    __stcg((uint4 *)(scr + (size_t)k * N) + wdx, ((const uint4 *)(stg + k * TILE))[wdx]);
+                }
+            };
+            auto stepf = [&](int b, float4 (&v)[UNROLL]) {
+                LocalStat ls;
+                ls.reset();
+                batch(std::false_type{}, b, v, ls);
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    ok = ok && (unsigned)(ls.qmin[j] - 1) < Pm1[j] && (unsigned)(ls.qmax[j] - 1) < Pm1[j];
+                if (!ok) {
+                    ls.reset();
+                    load(b, v);
+                    batch(std::true_type{}, b, v, ls);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    run.wmin[j] = min(run.wmin[j], ls.wmin[j]); run.wmax[j] = max(run.wmax[j], ls.wmax[j]);
+                    run.qmin[j] = min(run.qmin[j], ls.qmin[j]); run.qmax[j] = max(run.qmax[j], ls.qmax[j]);
+                }
+            };
+            {
+                // one continuous stream of batches over the G tiles: the loads of batch b+1 are in
+                // flight while batch b is quantised, also across tile boundaries, barriers and parking
+                constexpr int NB = G * BPT;
+                if (!preloaded) load(0, va);
+                preloaded = false;
+#pragma unroll 1
+                for (int b = 0; b < NB; b += 2) {
+                    load(b + 1, vb);
+                    stepf(b, va);
+                    if (b + 2 < NB) load(b + 2, va);
+                    stepf(b + 1, vb);
+                    if ((b + 2) % BPT == 0 && b + 2 < NB) {   // a tile is complete (not the last one)
+                        __syncthreads();
+                        park((b + 2) / BPT - 1);
+                    }
+                }
+            }
+            // ---- run statistics -> unit statistics (atomicMax on complemented minima) ----
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int j = (k - a0 + 3) % 3;
+                unsigned a = j == 0 ? run.wmin[0] : (j == 1 ? run.wmin[1] : run.wmin[2]);
+                unsigned bb = j == 0 ? run.wmax[0] : (j == 1 ? run.wmax[1] : run.wmax[2]);
+                int c = j == 0 ? run.qmin[0] : (j == 1 ? run.qmin[1] : run.qmin[2]);
+                int d = j == 0 ? run.qmax[0] : (j == 1 ? run.qmax[1] : run.qmax[2]);
+                a = __reduce_min_sync(0xffffffffu, a);
+                bb = __reduce_max_sync(0xffffffffu, bb);
+                c = __reduce_min_sync(0xffffffffu, c);
+                d = __reduce_max_sync(0xffffffffu, d);
+                if (lane == 0) { s_red[warp][k][0] = ~a; s_red[warp][k][1] = bb; s_red[warp][k][2] = ~(unsigned)c; s_red[warp][k][3] = (unsigned)d; }
+            }
+            oob = __any_sync(0xffffffffu, oob);
+            if (lane == 0) s_red[warp][0][4] = oob;
+            __syncthreads();
+            {   // the next run's first loads go out before this run's bookkeeping (its ticket is known)
+                const unsigned tn = s_ticket[(it + 1) & 1];
+                if (tn < total) {
+                    const unsigned stepn = tn / (2u * RPU), rn = tn % (2u * RPU);
+                    if (rn < (unsigned)RPU && (int)stepn < A.nunits) {
+                        const unsigned fn = stepn / sc3, scn = stepn % sc3;
+                        const unsigned nx0 = NSUB * (scn % S), ny0 = NSUB * ((scn / S) % S), nz0 = NSUB * (scn / (S * S));
+                        const float4 *pb = (const float4 *)(A.aos + 3ull * fn * ((unsigned long long)nfile * nfile * nfile)) +
+                                           (3u * nx0 / 4u + ny0 * row4 + nz0 * plane4) + col4;
+                        const unsigned rowg0 = (rn * G) * ROWS + rsub;
+                        const float4 *p = pb + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
+                        const unsigned stp = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;
+#pragma unroll
+                        for (int u = 0; u < UNROLL; u++) va[u] = ld_stream_pinned(p + (size_t)u * stp);
+                        preloaded = true;
+                    }
+                }
+            }
+            park(G - 1);
+            if (tid < 12) {
+                const int k = tid >> 2, st = tid & 3;
+                unsigned m = 0;
+                for (int wi = 0; wi < NW; wi++) m = max(m, s_red[wi][k][st]);
+                atomicMax(A.ustat + ((size_t)unit * 3 + k) * 4 + st, m);
+            } else if (tid == 12) {
+                unsigned o = 0;
+                for (int wi = 0; wi < NW; wi++) o |= s_red[wi][0][4];
+                if (o) atomicOr(A.uoob + unit, 1u);
+            }
+            __threadfence();
+            __syncthreads();
+            if (warp == 0) {
+                int last = 0;
+                if (lane == 0) last = atomicAdd(A.adone + unit, G) + G == TPU;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    // ================= finalise the unit =================
+                    __threadfence();
+#pragma unroll 1
+                    for (int k = 0; k < 3; k++) {
+                        const long long b = ((long long)f * 3 + k) * sc3 + sc;
+                        const unsigned *us = A.ustat + ((size_t)unit * 3 + k) * 4;
+                        const unsigned wmin = ~__ldcg(us), wmax = __ldcg(us + 1);
+                        const int qmin = (int)~__ldcg(us + 2), qmax = (int)__ldcg(us + 3);
+                        const bool slow = __ldcg(A.uoob + unit) != 0;
+                        const FloatParams fp = tab[k];
+                        const long long Pk = fp.pixels, half = Pk / 2, K = Pk - half - 1;
+                        const long long q0k = A.q0tab[(size_t)unit * 3 + k];
+                        long long mn, pmin;
+                        unsigned long long maxoff;
+                        unsigned base, padj;
+                        bool wide;
+                        const unsigned long long spread = (unsigned long long)wmax - wmin + 1ULL;
+                        if (spread > (unsigned long long)half) {
+                            wide = true;
+                            pmin = 0; mn = qmin; maxoff = (unsigned long long)((long long)qmax - qmin);
+                            base = (unsigned)arc_rotation(q0k, Pk) + (unsigned)qmin; padj = (unsigned)Pk;
+                        } else {
+                            wide = false;
+                            long long m = q0k + ((long long)wmin - K);
+                            if (m < 0) m += Pk;
+                            pmin = m; mn = m; maxoff = spread - 1ULL;
+                            base = wmin; padj = 0;
+                        }
+                        int bits = maxoff < (1ULL << 48) ? 64 - __clzll((long long)maxoff) : precision_needed(maxoff);
+                        long long nbytes = array_bytes(bits, N);
+                        if (slow) { bits = 0; nbytes = 0; }
+                        if (lane == 0) st_relaxed(A.W.pub + b, PUB_AGG | (unsigned long long)nbytes);
+                        long long off = lookback(A.W.pub, b - sc, b);
+                        int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
+                        if (lane == 0) {
+                            st_relaxed(A.W.pub + b, PUB_PREFIX | (unsigned long long)(off + nbytes));
+                            if (off + nbytes > A.axis_stride) {   // never write past the caller's buffer
+                                atomicExch(A.W.err, 2);
+                                mode = 0;
+                            } else if (!slow && bits > 0 && mode == 0) {
+                                A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = b;
+                            }
+                            if (slow) atomicExch(A.W.abort_flag, 1);
+                            BlockStat st = {};
+                            st.pmin = pmin; st.min = mn; st.nbytes = nbytes; st.out_off = off; st.do_bound = 1; st.bits = bits;
+                            st.q0 = q0k; st.oob = slow;
+                            A.stats[b] = st;
+                            if (A.mins) A.mins[b] = mn;
+                            if (A.bits) A.bits[b] = bits;
+                            if (A.offsets) A.offsets[b] = off;
+                            if (A.out_len && sc == sc3 - 1) A.out_len[f * 3 + k] = off + nbytes;
+                            UFin fin;
+                            fin.off = off; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj; fin.pad0 = fin.pad1 = 0;
+                            A.ufin[(size_t)unit * 3 + k] = fin;
+                        }
+                    }
+                    __threadfence();
+                    if (lane == 0) atomicExch(A.ready + unit, 1);
+                }
+            }
+        } else {
+            // ================= B-run: pack G tiles of one unit =================
+            if (tid < 3) {
+                if (tid == 0) {
+                    while (ld_volatile_i32(A.ready + unit) == 0) { __nanosleep(100); }
+                    __threadfence();   // acquire: the unit's parked indices and UFin records are visible
+                }
+                __syncwarp(0x7);
+                const uint4 *fp4 = (const uint4 *)(A.ufin + (size_t)unit * 3 + tid);
+                uint4 *d4 = (uint4 *)&s_fin[tid];
+                d4[0] = __ldcg(fp4); d4[1] = __ldcg(fp4 + 1);
+            }
+            __syncthreads();
+            const unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile0 * TILE;
+            constexpr int NG = G * 3 * GPA;   // groups of the run: (tile, axis, group within tile)
+            auto gsrc = [&](int g) {
+                const int pl = g / (3 * GPA), rem = g - pl * (3 * GPA), k = rem / GPA, gi = rem - k * GPA;
+                return (const uint4 *)(scr + (size_t)k * N + (size_t)pl * TILE + gi * 1024 + 32 * lane);
+            };
+#pragma unroll 1
+            for (int g = warp; g < NG; g += NW) {
+                uint4 cur[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) cur[s4] = __ldcg(gsrc(g) + s4);
+                const int pl = g / (3 * GPA), rem = g - pl * (3 * GPA), k = rem / GPA, gi = rem - k * GPA;
+                const UFin fin = s_fin[k];
+                if (fin.mode != 0) {
+                    unsigned v[32];
+                    if (fin.padj == 0) {   // narrow arc: v = w - wmin, exact modulo 2^16
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const unsigned rr[4] = {cur[s4].x, cur[s4].y, cur[s4].z, cur[s4].w};
+#pragma unroll
+                            for (int tt = 0; tt < 4; tt++) {
+                                v[8 * s4 + 2 * tt] = (rr[tt] - fin.base) & 0xffffu;
+                                v[8 * s4 + 2 * tt + 1] = ((rr[tt] >> 16) - fin.base) & 0xffffu;
+                            }
+                        }
+                    } else {               // wide arc (pixels <= 65536): v = (w - C - qmin) mod pixels
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const unsigned rr[4] = {cur[s4].x, cur[s4].y, cur[s4].z, cur[s4].w};
+#pragma unroll
+                            for (int tt = 0; tt < 4; tt++) {
+                                const unsigned lo = (rr[tt] & 0xffffu) - fin.base, hi = (rr[tt] >> 16) - fin.base;
+                                v[8 * s4 + 2 * tt] = min(lo, lo + fin.padj);
+                                v[8 * s4 + 2 * tt + 1] = min(hi, hi + fin.padj);
+                            }
+                        }
+                    }
+                    unsigned *region = (unsigned *)stage[0] + warp * 512;
+                    const long long e0 = (long long)(tile0 + pl) * TILE + (long long)gi * 1024;
+                    uint8_t *dst = A.out + ((long long)f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
+                    switch (fin.bits) {
+#define MNW_CASE(B) case B: pack_group_flat<B>(v, region, lane, dst); break;
+                        MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
+                        MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
+#undef MNW_CASE
+                        default: break;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) atomicAdd(A.bdone + unit, G);
+        }
+        __syncthreads();   // the ticket slots and staging buffers are reused by the next run
     }
 }
 
@@ -939,6 +1373,88 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
         }
         case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
         case 16: return launch_fused_vec3_t<16, 1, 384, 4, 1, true>(L, A);
+    }
+    return cudaErrorNotSupported;
+}
+
+// ---- flat encode ----
+size_t flat_control_bytes(int64_t nunits) { return (size_t)(64 * nunits + 256); }            // zeroed per launch
+size_t flat_work_bytes(int64_t nunits) { return flat_control_bytes(nunits) + (size_t)((96 + 24) * nunits + 256); }
+size_t flat_scratch_bytes() {
+    static const size_t mb = getenv("MNW_FLAT_SCRATCH_MB") ? (size_t)atoi(getenv("MNW_FLAT_SCRATCH_MB")) : 26;   // tuning knob
+    return mb << 20;
+}
+
+template <int NSUB, int NT, int UNROLL, int MINB, int GMAX>
+static cudaError_t launch_flat_vec3_t(Launcher &L, FlatArgs &A) {
+    constexpr int N = NSUB * NSUB * NSUB, TILE = N < 4096 ? N : 4096, TPU = N / TILE;
+    auto kern = k_flat_vec3<NSUB, NT, UNROLL, MINB, GMAX>;
+    constexpr size_t smem = (size_t)2 * 3 * TILE * 2;
+    static int grid_max = 0;
+    if (!grid_max) {
+        int per_sm = 0, dev = 0, sms = 148;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        grid_max = per_sm * sms;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_flat_vec3<%d,%d,%d>: %d CTAs per SM\n", NSUB, NT, MINB, per_sm);
+    }
+    // B-runs follow D units behind the A-runs, far enough (about two grids' worth of tickets) that a
+    // unit is complete and finalised before its first B-run is handed out; the ring holds 2*D units
+    constexpr int G = TPU < GMAX ? TPU : GMAX, RPU = TPU / G;
+    A.D = (2 * grid_max + 2 * RPU - 1) / (2 * RPU);
+    const long long dmax = (long long)(flat_scratch_bytes() / (2 * 3 * (size_t)N * 2));
+    if (A.D > dmax) A.D = (int)dmax;
+    if (A.D < 1) return cudaErrorInvalidValue;
+    A.R = 2 * A.D;
+    const long long tickets = ((long long)A.nunits + A.D) * 2 * RPU;
+    const unsigned grid = (unsigned)(tickets < grid_max ? tickets : grid_max);
+    k_unit_q0<<<(3 * A.nunits + 255) / 256, 256, 0, L.stream>>>(A, (long long *)A.q0tab, NSUB);
+    L.count++;
+    L.begin("k_flat_vec3");
+    kern<<<grid, NT, smem, L.stream>>>(A);
+    L.end();
+    L.count++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flat_vec3(Launcher &L, const FusedWork &W, void *work, void *scratch, const FloatParams *tab,
+                             int tab_per_file, const float *aos, int nfile, int subcells, int64_t nfiles,
+                             BlockStat *stats, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
+                             uint8_t *out, int64_t out_axis_stride) {
+    FlatArgs A = {};
+    A.aos = aos; A.tab = tab; A.tab_per_file = tab_per_file; A.nfile = nfile; A.subcells = subcells;
+    A.sc3 = subcells * subcells * subcells;
+    const int64_t nunits = nfiles * A.sc3;
+    if (nunits == 0) return cudaSuccess;
+    if (nunits >= (1LL << 28)) return cudaErrorInvalidValue;
+    A.nunits = (int)nunits;
+    A.stats = stats; A.mins = mins; A.bits = bits; A.offsets = offsets; A.out_len = out_len; A.out = out;
+    A.axis_stride = out_axis_stride; A.W = W;
+    unsigned char *w = (unsigned char *)work;
+    A.ustat = (unsigned *)w;                     w += 48 * nunits;
+    A.uoob = (unsigned *)w;                      w += 4 * nunits;
+    A.adone = (int *)w;                          w += 4 * nunits;
+    A.bdone = (int *)w;                          w += 4 * nunits;
+    A.ready = (int *)w;
+    A.ufin = (UFin *)((unsigned char *)work + ((flat_control_bytes(nunits) + 31) & ~(size_t)31));
+    A.q0tab = (const long long *)(A.ufin + 3 * nunits);
+    A.scratch = (unsigned short *)scratch;
+    cudaError_t e = cudaMemsetAsync(work, 0, flat_control_bytes(nunits), L.stream);
+    if (e != cudaSuccess) return e;
+    switch (nfile / subcells) {
+        case 64: {
+            static const int minb = getenv("MNW_FLAT_MINB") ? atoi(getenv("MNW_FLAT_MINB")) : 4;   // tuning knobs
+            static const int g = getenv("MNW_FLAT_G") ? atoi(getenv("MNW_FLAT_G")) : 1;
+            if (minb == 4) return g == 2 ? launch_flat_vec3_t<64, 192, 2, 4, 2>(L, A) : launch_flat_vec3_t<64, 192, 2, 4, 1>(L, A);
+            return g == 2 ? launch_flat_vec3_t<64, 192, 2, 3, 2>(L, A) : launch_flat_vec3_t<64, 192, 2, 3, 1>(L, A);
+        }
+        case 32: return launch_flat_vec3_t<32, 192, 2, 4, 1>(L, A);
+        case 16: return launch_flat_vec3_t<16, 192, 2, 4, 1>(L, A);
     }
     return cudaErrorNotSupported;
 }
