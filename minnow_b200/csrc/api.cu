@@ -542,7 +542,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         W.repack_list = (int64_t *)(W.pub + nb);
         W.err = d_flags + 1; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
         CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
-        static const bool use_cluster = getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "cluster");   // tuning knob
+        static const bool use_cluster = !(getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "flat"));   // tuning knob
         cudaError_t e;
         if (use_cluster) {
             e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,

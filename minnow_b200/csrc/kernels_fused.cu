@@ -669,234 +669,215 @@ __global__ void k_unit_q0(const FlatArgs A, long long *q0tab, int nsub) {
     q0tab[i] = quantize_exact(__ldg(cube + 3 * idx0 + k), fp.low, fp.dx);
 }
 
-template <int NSUB, int NT, int UNROLL, int MINB, int GMAX>
+// Exact redo of ONE thread's share of an A-tile (rare): some element left the range in which
+// the fast quantiser is trusted (negative or NaN offset, pixel index >= pixels).  Recomputes the
+// thread's staged indices with the IEEE divide and publishes its statistics straight to the unit
+// (the caller then contributes nothing for this thread).  Kept out of line so that the fast
+// path's register allocation does not pay for it.
+template <int NSUB, int NT>
+__device__ __noinline__ void flat_redo_thread(const float4 *b, unsigned tile, unsigned nfile, const FloatParams *tab,
+                                              const long long *q0u, unsigned short *stage, unsigned *ustat,
+                                              unsigned *uoob) {
+    constexpr int N3 = NSUB * NSUB * NSUB, TILE = N3 < 4096 ? N3 : 4096, R4 = 3 * NSUB / 4, RPP = NT / R4;
+    constexpr int ROWS = TILE / NSUB, passes = ROWS / RPP;
+    const int tid = threadIdx.x, col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
+    const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
+    unsigned oob = 0;
+    for (int c = 0; c < 4; c++) {
+        const int ax = (a0 + c) % 3;
+        const FloatParams fp = tab[ax];
+        const long long P = fp.pixels, q0 = q0u[ax];
+        const bool q0ok = (unsigned long long)q0 < (unsigned long long)P;
+        const unsigned C = q0ok ? (unsigned)arc_rotation(q0, P) : 0u;
+        if (!q0ok) oob = 1;
+        unsigned wmin = ~0u, wmax = 0u;
+        int qmin = INT_MAX, qmax = INT_MIN;
+        const int so = ax * TILE + rsub * NSUB + (4 * col4 + c) / 3;
+        for (int p = 0; p < passes; p++) {
+            const unsigned rowg = tile * ROWS + rsub + RPP * p;
+            const float x = ((const float *)(b + (size_t)((rowg / NSUB) * plane4 + (rowg % NSUB) * row4)))[c];
+            int q = quantize_rare(x, fp.low, fp.dx, (int)P, oob);
+            unsigned w = (unsigned)q + C;
+            w = min(w, w - (unsigned)P);
+            wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
+            stage[so + p * (RPP * NSUB)] = (unsigned short)w;
+        }
+        atomicMax(ustat + ax * 4 + 0, ~wmin); atomicMax(ustat + ax * 4 + 1, wmax);
+        atomicMax(ustat + ax * 4 + 2, ~(unsigned)qmin); atomicMax(ustat + ax * 4 + 3, (unsigned)qmax);
+    }
+    if (oob) atomicOr(uoob, 1u);
+}
+
+template <int NSUB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
     constexpr int N = NSUB * NSUB * NSUB;
     constexpr int TILE = N < 4096 ? N : 4096;   // particles per tile
     constexpr int TPU = N / TILE;               // tiles per unit
-    constexpr int G = TPU < GMAX ? TPU : GMAX;  // tiles per run = per claimed ticket
-    constexpr int RPU = TPU / G;                // runs per unit
     constexpr int ROWS = TILE / NSUB;
     constexpr int R4 = 3 * NSUB / 4;
     constexpr int RPP = NT / R4;
     constexpr int PASSES = ROWS / RPP;
-    constexpr int BPT = PASSES / UNROLL;        // batches per tile
     constexpr int GPA = TILE / 1024;            // pack groups per tile and axis
     constexpr int NW = NT / 32;
-    static_assert(NT % R4 == 0 && ROWS % RPP == 0, "threads tile the rows exactly");
-    static_assert(PASSES % (2 * UNROLL) == 0 && UNROLL % 2 == 0, "pairs of batches of float4 pairs");
-    static_assert(NSUB % (RPP * UNROLL) == 0 || RPP % NSUB == 0, "batch rows are equally spaced");
-    static_assert(3 * TILE * 2 >= NW * 2048, "transposition regions fit one staging buffer");
+    static_assert(NT % R4 == 0 && ROWS % RPP == 0 && PASSES % 2 == 0, "threads tile the rows exactly");
+    static_assert(NSUB % (RPP * 2) == 0 || RPP % NSUB == 0, "the two rows of a step lie in one plane or one per plane");
+    static_assert(3 * TILE * 2 >= NW * 2048, "transposition regions fit the staging buffer");
 
-    extern __shared__ __align__(16) unsigned char flat_smem[];
-    // double buffered: tile p is parked while tile p+1 is quantised
-    unsigned short (*stage)[3 * TILE] = (unsigned short (*)[3 * TILE])flat_smem;
-    __shared__ unsigned s_red[NW][3][5];
-    __shared__ unsigned s_ticket[2];
-    __shared__ UFin s_fin[3];
+    __shared__ __align__(16) unsigned short stage[3 * TILE];
+    __shared__ unsigned s_red[NW][3][4];
+    __shared__ unsigned s_ticket;
+    __shared__ __align__(16) UFin s_fin[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
-    int soff[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) soff[c] = ((a0 + c) % 3) * TILE + rsub * NSUB + (4 * col4 + c) / 3;
     const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
     const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
-    // Tickets: per unit-step first the RPU A-runs of unit `step`, then the RPU B-runs of unit
-    // `step - D`.  Everything a run can wait for (ring slot, ready flag, look-back words) belongs
-    // to lower tickets, i.e. to CTAs that are running or done.
-    const unsigned total = (unsigned)(A.nunits + A.D) * (2u * RPU);
-    if (tid == 0) s_ticket[0] = atomicAdd(A.W.ticket, 1u);
-    __syncthreads();
-    float4 va[UNROLL], vb[UNROLL];   // the load pipeline of the A-runs lives across runs
-    bool preloaded = false;
-    for (int it = 0;; it++) {
-        const unsigned t = s_ticket[it & 1];
+    const unsigned total = (unsigned)(A.nunits + A.D) * (2u * TPU);
+
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(A.W.ticket, 1u);
+        __syncthreads();
+        const unsigned t = s_ticket;
         if (t >= total) break;
-        if (tid == 0) s_ticket[(it + 1) & 1] = atomicAdd(A.W.ticket, 1u);   // the next run, claimed a whole run ahead
-        const unsigned step = t / (2u * RPU), r = t % (2u * RPU);
-        const bool isA = r < (unsigned)RPU;
+        // Tickets: per unit-step first the TPU A-tiles of unit `step`, then the TPU B-tiles of unit
+        // `step - D`; everything a tile can wait for (ring slot, ready flag, look-back words) belongs
+        // to lower tickets, i.e. to CTAs that are running or done.
+        const unsigned step = t / (2u * TPU), r = t % (2u * TPU);
+        const bool isA = r < (unsigned)TPU;
         const int unit = isA ? (int)step : (int)step - A.D;
-        const unsigned tile0 = (isA ? r : r - RPU) * G;
+        const unsigned tile = isA ? r : r - TPU;
         if (unit < 0 || unit >= A.nunits) { __syncthreads(); continue; }
         const unsigned f = (unsigned)unit / sc3, sc = (unsigned)unit % sc3;
         const int slot = unit % A.R;
 
         if (isA) {
-            // ================= A-run: G tiles of one unit =================
+            // ================= A-tile =================
             const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
-            const float *cube = A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile);
             const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
+            // row of pass p: tile * ROWS + rsub + RPP * p; the two rows of a step are `stp` apart, steps
+            // may cross z-planes of the sub-cell (NSUB < 64)
+            const float4 *b = (const float4 *)(A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile)) +
+                              (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
+            constexpr bool PLANE_STEP = RPP % NSUB == 0;
+            const unsigned stp = PLANE_STEP ? (RPP / NSUB) * plane4 : RPP * row4;   // float4 units per pass
+            auto row_off = [&](int p) {
+                const unsigned rowg = tile * ROWS + rsub + RPP * p;
+                return (size_t)((rowg / NSUB) * plane4 + (rowg % NSUB) * row4);
+            };
+            // parameters in this thread's axis order: relative axis j = actual axis (a0 + j) % 3
             float low[3], rcp[3], ndx[3];
-            int P[3];
-            unsigned Pm1[3], C[3];
-            unsigned oob = 0;
+            unsigned P[3], C[3], tmax[3];
+            bool bad = false;
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const int ax = (a0 + j) % 3;
                 const FloatParams fp = tab[ax];
                 low[j] = fp.low; rcp[j] = fp.rcp; ndx[j] = -fp.dx;
-                P[j] = (int)fp.pixels;
-                Pm1[j] = (fp.flags & F_FASTDIV) ? (unsigned)(P[j] - 1) : 0u;
+                P[j] = (unsigned)fp.pixels;
+                // offsets x - low are trusted in [+0, high - low]: as unsigned bit patterns that is one
+                // comparison, and it also rejects negative, NaN, infinite and overflowing values
+                tmax[j] = __float_as_uint(__fsub_rn(fp.high, fp.low));
                 const long long q0 = A.q0tab[(size_t)unit * 3 + ax];
                 const bool ok = (unsigned long long)q0 < (unsigned long long)fp.pixels;
                 C[j] = ok ? (unsigned)arc_rotation(q0, fp.pixels) : 0u;
-                if (!ok) oob = 1;   // periodicMin starting outside [0, pixels): exact path only
+                if (!ok || !(fp.flags & F_FASTDIV)) bad = true;   // exact path: x[0] out of range / dx not vouched for
             }
-            const float4 *pbase = (const float4 *)cube + (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
-            if (tid == 32 && unit >= A.R) {   // the ring slot is free once the unit that used it is packed
-                while (ld_volatile_i32(A.bdone + (unit - A.R)) < TPU) { __nanosleep(100); }
-            }
-            LocalStat run;
-            run.reset();
-            // batch b of the run: tile tile0 + b / BPT, passes (b % BPT) * UNROLL ...
-            auto load = [&](int b, float4 (&v)[UNROLL]) {
-                const unsigned rowg0 = (tile0 + b / BPT) * ROWS + rsub + RPP * ((b % BPT) * UNROLL);
-                const float4 *p = pbase + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
-                const unsigned stp = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;
+            unsigned wmin[3] = {~0u, ~0u, ~0u}, wmax[3] = {0u, 0u, 0u};
+            unsigned qmin[3] = {~0u, ~0u, ~0u}, qmax[3] = {0u, 0u, 0u};   // valid pixel indices are >= 0
+            int so[4];
 #pragma unroll
-                for (int u = 0; u < UNROLL; u++) v[u] = ld_stream_pinned(p + (size_t)u * stp);
-            };
-            auto batch = [&](auto exact_tag, int b, const float4 (&v)[UNROLL], LocalStat &ls) {
-                constexpr bool EXACT = decltype(exact_tag)::value;
-                unsigned short *stg = stage[(b / BPT) & 1] + ((b % BPT) * UNROLL) * (RPP * NSUB);
+            for (int c = 0; c < 4; c++) so[c] = ((a0 + c) % 3) * TILE + rsub * NSUB + (4 * col4 + c) / 3;
+
+#pragma unroll 1
+            for (int p0 = 0; p0 < PASSES; p0 += 2) {
+                float4 v[2];
+                const float4 *bp = b + row_off(p0);
 #pragma unroll
-                for (int u = 0; u < UNROLL; u += 2) {
-                    int q[2][4];
-                    unsigned w[2][4];
+                for (int u = 0; u < 2; u++) v[u] = __ldcs(bp + (size_t)u * stp);
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float x[4] = {v[u + h].x, v[u + h].y, v[u + h].z, v[u + h].w};
+                for (int u = 0; u < 2; u++) {
+                    const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    unsigned q[4], w[4];
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const int j = c % 3;
-                            if constexpr (EXACT) q[h][c] = quantize_rare(x[c], low[j], -ndx[j], P[j], oob);
-                            else q[h][c] = quantize_fast(x[c], low[j], rcp[j], ndx[j]);
-                            const unsigned tt = (unsigned)q[h][c] + C[j];
-                            w[h][c] = min(tt, tt - (unsigned)P[j]);
-                            stg[soff[c] + (u + h) * (RPP * NSUB)] = (unsigned short)w[h][c];
-                        }
+                    for (int c = 0; c < 4; c++) {
+                        const int j = c % 3;
+                        // go/group.go:319 without the divide (device_math.cuh quantize_fast); trusted for
+                        // offsets in [0, high - low] and pixel indices < pixels, checked once per tile below
+                        const float tt = __fsub_rn(x[c], low[j]);
+                        float y = __fmul_rn(tt, rcp[j]);
+                        float e = __fmaf_rn(ndx[j], y, tt);
+                        y = __fmaf_rn(e, rcp[j], y);
+                        e = __fmaf_rn(ndx[j], y, tt);
+                        y = __fmaf_rn(e, rcp[j], y);
+                        q[c] = (unsigned)__float2int_rd(y);
+                        bad |= __float_as_uint(tt) > tmax[j];
+                        const unsigned wr = q[c] + C[j];
+                        w[c] = min(wr, wr - P[j]);
+                        stage[so[c] + (p0 + u) * (RPP * NSUB)] = (unsigned short)w[c];
                     }
-                    ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[0][0], q[0][3]); ls.qmin[0] = __vimin3_s32(ls.qmin[0], q[1][0], q[1][3]);
-                    ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[0][0], q[0][3]); ls.qmax[0] = __vimax3_s32(ls.qmax[0], q[1][0], q[1][3]);
-                    ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[0][0], w[0][3]); ls.wmin[0] = __vimin3_u32(ls.wmin[0], w[1][0], w[1][3]);
-                    ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[0][0], w[0][3]); ls.wmax[0] = __vimax3_u32(ls.wmax[0], w[1][0], w[1][3]);
+                    qmin[0] = __vimin3_u32(qmin[0], q[0], q[3]); qmax[0] = __vimax3_u32(qmax[0], q[0], q[3]);
+                    wmin[0] = __vimin3_u32(wmin[0], w[0], w[3]); wmax[0] = __vimax3_u32(wmax[0], w[0], w[3]);
 #pragma unroll
                     for (int j = 1; j < 3; j++) {
-                        ls.qmin[j] = __vimin3_s32(ls.qmin[j], q[0][j], q[1][j]);
-                        ls.qmax[j] = __vimax3_s32(ls.qmax[j], q[0][j], q[1][j]);
-                        ls.wmin[j] = __vimin3_u32(ls.wmin[j], w[0][j], w[1][j]);
-                        ls.wmax[j] = __vimax3_u32(ls.wmax[j], w[0][j], w[1][j]);
-                    }
-                }
-            };
-            // park tile `pl` of the run: its 16-bit indices go to the scratch ring, planar per axis
-            auto park = [&](int pl) {
-                unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)(tile0 + pl) * TILE;
-                const unsigned short *stg = stage[pl & 1];
-                for (int i = tid; i < 3 * TILE / 8; i += NT) {
-                    const int k = i / (TILE / 8), wdx = i - k * (TILE / 8);
-                    __stcg((uint4 *)(scr + (size_t)k * N) + wdx, ((const uint4 *)(stg + k * TILE))[wdx]);
-                }
-            };
-            auto stepf = [&](int b, float4 (&v)[UNROLL]) {
-                LocalStat ls;
-                ls.reset();
-                batch(std::false_type{}, b, v, ls);
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-                    ok = ok && (unsigned)(ls.qmin[j] - 1) < Pm1[j] && (unsigned)(ls.qmax[j] - 1) < Pm1[j];
-                if (!ok) {
-                    ls.reset();
-                    load(b, v);
-                    batch(std::true_type{}, b, v, ls);
-                }
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    run.wmin[j] = min(run.wmin[j], ls.wmin[j]); run.wmax[j] = max(run.wmax[j], ls.wmax[j]);
-                    run.qmin[j] = min(run.qmin[j], ls.qmin[j]); run.qmax[j] = max(run.qmax[j], ls.qmax[j]);
-                }
-            };
-            {
-                // one continuous stream of batches over the G tiles: the loads of batch b+1 are in
-                // flight while batch b is quantised, also across tile boundaries, barriers and parking
-                constexpr int NB = G * BPT;
-                if (!preloaded) load(0, va);
-                preloaded = false;
-#pragma unroll 1
-                for (int b = 0; b < NB; b += 2) {
-                    load(b + 1, vb);
-                    stepf(b, va);
-                    if (b + 2 < NB) load(b + 2, va);
-                    stepf(b + 1, vb);
-                    if ((b + 2) % BPT == 0 && b + 2 < NB) {   // a tile is complete (not the last one)
-                        __syncthreads();
-                        park((b + 2) / BPT - 1);
+                        qmin[j] = min(qmin[j], q[j]); qmax[j] = max(qmax[j], q[j]);
+                        wmin[j] = min(wmin[j], w[j]); wmax[j] = max(wmax[j], w[j]);
                     }
                 }
             }
-            // ---- run statistics -> unit statistics (atomicMax on complemented minima) ----
+#pragma unroll
+            for (int j = 0; j < 3; j++) bad |= qmax[j] >= P[j];
+            if (bad) {   // rare: this thread's elements again, exactly; it publishes its own statistics
+                flat_redo_thread<NSUB, NT>(b, tile, nfile, tab, A.q0tab + (size_t)unit * 3, stage,
+                                           A.ustat + (size_t)unit * 12, A.uoob + unit);
+#pragma unroll
+                for (int j = 0; j < 3; j++) { wmin[j] = ~0u; wmax[j] = 0u; qmin[j] = ~0u; qmax[j] = 0u; }
+            }
+            // ---- tile statistics -> unit statistics (atomicMax on complemented minima) ----
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const int j = (k - a0 + 3) % 3;
-                unsigned a = j == 0 ? run.wmin[0] : (j == 1 ? run.wmin[1] : run.wmin[2]);
-                unsigned bb = j == 0 ? run.wmax[0] : (j == 1 ? run.wmax[1] : run.wmax[2]);
-                int c = j == 0 ? run.qmin[0] : (j == 1 ? run.qmin[1] : run.qmin[2]);
-                int d = j == 0 ? run.qmax[0] : (j == 1 ? run.qmax[1] : run.qmax[2]);
+                unsigned a = j == 0 ? wmin[0] : (j == 1 ? wmin[1] : wmin[2]);
+                unsigned bb = j == 0 ? wmax[0] : (j == 1 ? wmax[1] : wmax[2]);
+                unsigned cq = j == 0 ? qmin[0] : (j == 1 ? qmin[1] : qmin[2]);
+                unsigned dq = j == 0 ? qmax[0] : (j == 1 ? qmax[1] : qmax[2]);
                 a = __reduce_min_sync(0xffffffffu, a);
                 bb = __reduce_max_sync(0xffffffffu, bb);
-                c = __reduce_min_sync(0xffffffffu, c);
-                d = __reduce_max_sync(0xffffffffu, d);
-                if (lane == 0) { s_red[warp][k][0] = ~a; s_red[warp][k][1] = bb; s_red[warp][k][2] = ~(unsigned)c; s_red[warp][k][3] = (unsigned)d; }
+                cq = __reduce_min_sync(0xffffffffu, cq);
+                dq = __reduce_max_sync(0xffffffffu, dq);
+                if (lane == 0) { s_red[warp][k][0] = ~a; s_red[warp][k][1] = bb; s_red[warp][k][2] = ~cq; s_red[warp][k][3] = dq; }
             }
-            oob = __any_sync(0xffffffffu, oob);
-            if (lane == 0) s_red[warp][0][4] = oob;
+            if (tid == 32 && unit >= A.R) {   // the ring slot is free once the unit that used it is packed
+                while (ld_volatile_i32(A.bdone + (unit - A.R)) < TPU) { __nanosleep(64); }
+            }
             __syncthreads();
-            {   // the next run's first loads go out before this run's bookkeeping (its ticket is known)
-                const unsigned tn = s_ticket[(it + 1) & 1];
-                if (tn < total) {
-                    const unsigned stepn = tn / (2u * RPU), rn = tn % (2u * RPU);
-                    if (rn < (unsigned)RPU && (int)stepn < A.nunits) {
-                        const unsigned fn = stepn / sc3, scn = stepn % sc3;
-                        const unsigned nx0 = NSUB * (scn % S), ny0 = NSUB * ((scn / S) % S), nz0 = NSUB * (scn / (S * S));
-                        const float4 *pb = (const float4 *)(A.aos + 3ull * fn * ((unsigned long long)nfile * nfile * nfile)) +
-                                           (3u * nx0 / 4u + ny0 * row4 + nz0 * plane4) + col4;
-                        const unsigned rowg0 = (rn * G) * ROWS + rsub;
-                        const float4 *p = pb + ((rowg0 / NSUB) * plane4 + (rowg0 % NSUB) * row4);
-                        const unsigned stp = RPP % NSUB == 0 ? (RPP / NSUB) * plane4 : RPP * row4;
-#pragma unroll
-                        for (int u = 0; u < UNROLL; u++) va[u] = ld_stream_pinned(p + (size_t)u * stp);
-                        preloaded = true;
-                    }
-                }
-            }
-            park(G - 1);
             if (tid < 12) {
                 const int k = tid >> 2, st = tid & 3;
                 unsigned m = 0;
                 for (int wi = 0; wi < NW; wi++) m = max(m, s_red[wi][k][st]);
                 atomicMax(A.ustat + ((size_t)unit * 3 + k) * 4 + st, m);
-            } else if (tid == 12) {
-                unsigned o = 0;
-                for (int wi = 0; wi < NW; wi++) o |= s_red[wi][0][4];
-                if (o) atomicOr(A.uoob + unit, 1u);
+            }
+            {   // park the 16-bit indices, planar per axis, in the scratch ring
+                unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile * TILE;
+                for (int i = tid; i < 3 * TILE / 8; i += NT) {
+                    const int k = i / (TILE / 8), wdx = i - k * (TILE / 8);
+                    __stcg((uint4 *)(scr + (size_t)k * N) + wdx, ((const uint4 *)(stage + k * TILE))[wdx]);
+                }
             }
             __threadfence();
             __syncthreads();
             if (warp == 0) {
                 int last = 0;
-                if (lane == 0) last = atomicAdd(A.adone + unit, G) + G == TPU;
+                if (lane == 0) last = atomicAdd(A.adone + unit, 1) == TPU - 1;
                 last = __shfl_sync(0xffffffffu, last, 0);
                 if (last) {
                     // ================= finalise the unit =================
                     __threadfence();
 #pragma unroll 1
                     for (int k = 0; k < 3; k++) {
-                        const long long b = ((long long)f * 3 + k) * sc3 + sc;
+                        const long long blk = ((long long)f * 3 + k) * sc3 + sc;
                         const unsigned *us = A.ustat + ((size_t)unit * 3 + k) * 4;
-                        const unsigned wmin = ~__ldcg(us), wmax = __ldcg(us + 1);
-                        const int qmin = (int)~__ldcg(us + 2), qmax = (int)__ldcg(us + 3);
+                        const unsigned uwmin = ~__ldcg(us), uwmax = __ldcg(us + 1);
+                        const int uqmin = (int)~__ldcg(us + 2), uqmax = (int)__ldcg(us + 3);
                         const bool slow = __ldcg(A.uoob + unit) != 0;
                         const FloatParams fp = tab[k];
                         const long long Pk = fp.pixels, half = Pk / 2, K = Pk - half - 1;
@@ -905,40 +886,43 @@ __global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
                         unsigned long long maxoff;
                         unsigned base, padj;
                         bool wide;
-                        const unsigned long long spread = (unsigned long long)wmax - wmin + 1ULL;
-                        if (spread > (unsigned long long)half) {
+                        const unsigned long long spread = (unsigned long long)uwmax - uwmin + 1ULL;
+                        if (spread > (unsigned long long)half) {   // arc too wide: periodicMin returns 0
                             wide = true;
-                            pmin = 0; mn = qmin; maxoff = (unsigned long long)((long long)qmax - qmin);
-                            base = (unsigned)arc_rotation(q0k, Pk) + (unsigned)qmin; padj = (unsigned)Pk;
+                            pmin = 0; mn = uqmin; maxoff = (unsigned long long)((long long)uqmax - uqmin);
+                            base = (unsigned)arc_rotation(q0k, Pk) + (unsigned)uqmin; padj = (unsigned)Pk;
                         } else {
                             wide = false;
-                            long long m = q0k + ((long long)wmin - K);
+                            long long m = q0k + ((long long)uwmin - K);
                             if (m < 0) m += Pk;
                             pmin = m; mn = m; maxoff = spread - 1ULL;
-                            base = wmin; padj = 0;
+                            base = uwmin; padj = 0;
                         }
+                        // bit.PrecisionNeeded: below 2^48 Go's float64 log2 agrees with the integer bit length
                         int bits = maxoff < (1ULL << 48) ? 64 - __clzll((long long)maxoff) : precision_needed(maxoff);
                         long long nbytes = array_bytes(bits, N);
                         if (slow) { bits = 0; nbytes = 0; }
-                        if (lane == 0) st_relaxed(A.W.pub + b, PUB_AGG | (unsigned long long)nbytes);
-                        long long off = lookback(A.W.pub, b - sc, b);
+                        if (lane == 0) st_relaxed(A.W.pub + blk, PUB_AGG | (unsigned long long)nbytes);
+                        const long long off = lookback(A.W.pub, blk - sc, blk);
+                        // parked values are the low 16 bits of w: enough when the packed value has <= 16 bits
+                        // and (wide arcs) w itself fits, i.e. pixels <= 65536
                         int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
                         if (lane == 0) {
-                            st_relaxed(A.W.pub + b, PUB_PREFIX | (unsigned long long)(off + nbytes));
+                            st_relaxed(A.W.pub + blk, PUB_PREFIX | (unsigned long long)(off + nbytes));
                             if (off + nbytes > A.axis_stride) {   // never write past the caller's buffer
                                 atomicExch(A.W.err, 2);
                                 mode = 0;
                             } else if (!slow && bits > 0 && mode == 0) {
-                                A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = b;
+                                A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = blk;
                             }
                             if (slow) atomicExch(A.W.abort_flag, 1);
                             BlockStat st = {};
                             st.pmin = pmin; st.min = mn; st.nbytes = nbytes; st.out_off = off; st.do_bound = 1; st.bits = bits;
                             st.q0 = q0k; st.oob = slow;
-                            A.stats[b] = st;
-                            if (A.mins) A.mins[b] = mn;
-                            if (A.bits) A.bits[b] = bits;
-                            if (A.offsets) A.offsets[b] = off;
+                            A.stats[blk] = st;
+                            if (A.mins) A.mins[blk] = mn;
+                            if (A.bits) A.bits[blk] = bits;
+                            if (A.offsets) A.offsets[blk] = off;
                             if (A.out_len && sc == sc3 - 1) A.out_len[f * 3 + k] = off + nbytes;
                             UFin fin;
                             fin.off = off; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj; fin.pad0 = fin.pad1 = 0;
@@ -950,10 +934,10 @@ __global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
                 }
             }
         } else {
-            // ================= B-run: pack G tiles of one unit =================
+            // ================= B-tile: pack 3 x GPA groups of 1024 parked indices =================
             if (tid < 3) {
                 if (tid == 0) {
-                    while (ld_volatile_i32(A.ready + unit) == 0) { __nanosleep(100); }
+                    while (ld_volatile_i32(A.ready + unit) == 0) { __nanosleep(64); }
                     __threadfence();   // acquire: the unit's parked indices and UFin records are visible
                 }
                 __syncwarp(0x7);
@@ -962,59 +946,54 @@ __global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
                 d4[0] = __ldcg(fp4); d4[1] = __ldcg(fp4 + 1);
             }
             __syncthreads();
-            const unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile0 * TILE;
-            constexpr int NG = G * 3 * GPA;   // groups of the run: (tile, axis, group within tile)
-            auto gsrc = [&](int g) {
-                const int pl = g / (3 * GPA), rem = g - pl * (3 * GPA), k = rem / GPA, gi = rem - k * GPA;
-                return (const uint4 *)(scr + (size_t)k * N + (size_t)pl * TILE + gi * 1024 + 32 * lane);
-            };
+            const unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile * TILE;
 #pragma unroll 1
-            for (int g = warp; g < NG; g += NW) {
-                uint4 cur[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) cur[s4] = __ldcg(gsrc(g) + s4);
-                const int pl = g / (3 * GPA), rem = g - pl * (3 * GPA), k = rem / GPA, gi = rem - k * GPA;
+            for (int g = warp; g < 3 * GPA; g += NW) {
+                const int k = g / GPA, gi = g - k * GPA;
                 const UFin fin = s_fin[k];
-                if (fin.mode != 0) {
-                    unsigned v[32];
-                    if (fin.padj == 0) {   // narrow arc: v = w - wmin, exact modulo 2^16
+                if (fin.mode == 0) continue;
+                const uint4 *src = (const uint4 *)(scr + (size_t)k * N + gi * 1024 + 32 * lane);
+                uint4 r4[4];
 #pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const unsigned rr[4] = {cur[s4].x, cur[s4].y, cur[s4].z, cur[s4].w};
+                for (int s4 = 0; s4 < 4; s4++) r4[s4] = __ldcg(src + s4);
+                unsigned v[32];
+                if (fin.padj == 0) {   // narrow arc: v = w - wmin, exact modulo 2^16
 #pragma unroll
-                            for (int tt = 0; tt < 4; tt++) {
-                                v[8 * s4 + 2 * tt] = (rr[tt] - fin.base) & 0xffffu;
-                                v[8 * s4 + 2 * tt + 1] = ((rr[tt] >> 16) - fin.base) & 0xffffu;
-                            }
-                        }
-                    } else {               // wide arc (pixels <= 65536): v = (w - C - qmin) mod pixels
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const unsigned rr[4] = {r4[s4].x, r4[s4].y, r4[s4].z, r4[s4].w};
 #pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const unsigned rr[4] = {cur[s4].x, cur[s4].y, cur[s4].z, cur[s4].w};
-#pragma unroll
-                            for (int tt = 0; tt < 4; tt++) {
-                                const unsigned lo = (rr[tt] & 0xffffu) - fin.base, hi = (rr[tt] >> 16) - fin.base;
-                                v[8 * s4 + 2 * tt] = min(lo, lo + fin.padj);
-                                v[8 * s4 + 2 * tt + 1] = min(hi, hi + fin.padj);
-                            }
+                        for (int tt = 0; tt < 4; tt++) {
+                            v[8 * s4 + 2 * tt] = (rr[tt] - fin.base) & 0xffffu;
+                            v[8 * s4 + 2 * tt + 1] = ((rr[tt] >> 16) - fin.base) & 0xffffu;
                         }
                     }
-                    unsigned *region = (unsigned *)stage[0] + warp * 512;
-                    const long long e0 = (long long)(tile0 + pl) * TILE + (long long)gi * 1024;
-                    uint8_t *dst = A.out + ((long long)f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
-                    switch (fin.bits) {
+                } else {               // wide arc (pixels <= 65536): v = (w - C - qmin) mod pixels
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const unsigned rr[4] = {r4[s4].x, r4[s4].y, r4[s4].z, r4[s4].w};
+#pragma unroll
+                        for (int tt = 0; tt < 4; tt++) {
+                            const unsigned lo = (rr[tt] & 0xffffu) - fin.base, hi = (rr[tt] >> 16) - fin.base;
+                            v[8 * s4 + 2 * tt] = min(lo, lo + fin.padj);
+                            v[8 * s4 + 2 * tt + 1] = min(hi, hi + fin.padj);
+                        }
+                    }
+                }
+                unsigned *region = (unsigned *)stage + warp * 512;
+                const long long e0 = (long long)tile * TILE + (long long)gi * 1024;
+                uint8_t *dst = A.out + ((long long)f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
+                switch (fin.bits) {
 #define MNW_CASE(B) case B: pack_group_flat<B>(v, region, lane, dst); break;
-                        MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
-                        MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
+                    MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
+                    MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
 #undef MNW_CASE
-                        default: break;
-                    }
+                    default: break;
                 }
             }
             __syncthreads();
-            if (tid == 0) atomicAdd(A.bdone + unit, G);
+            if (tid == 0) atomicAdd(A.bdone + unit, 1);
         }
-        __syncthreads();   // the ticket slots and staging buffers are reused by the next run
+        __syncthreads();   // s_ticket and the staging buffer are reused by the next tile
     }
 }
 
@@ -1269,7 +1248,9 @@ __global__ void k_selftest_fastdiv(FloatParams fp, unsigned long long first, uns
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned)(first + i));
         const int qi = quantize_fast(x, fp.low, fp.rcp, -fp.dx);
-        if ((unsigned)(qi - 1) < Pm1) {   // the fast result would be used as is
+        // the widest acceptance rule in use (k_flat_vec3): offset in [+0, high - low] and pixel index < pixels
+        if (Pm1 && __float_as_uint(__fsub_rn(x, fp.low)) <= __float_as_uint(__fsub_rn(fp.high, fp.low)) &&
+            (unsigned)qi < (unsigned)P) {
             acc++;
             if ((long long)qi != quantize_exact(x, fp.low, fp.dx)) bad++;
         }
@@ -1385,17 +1366,14 @@ size_t flat_scratch_bytes() {
     return mb << 20;
 }
 
-template <int NSUB, int NT, int UNROLL, int MINB, int GMAX>
+template <int NSUB, int NT, int MINB>
 static cudaError_t launch_flat_vec3_t(Launcher &L, FlatArgs &A) {
     constexpr int N = NSUB * NSUB * NSUB, TILE = N < 4096 ? N : 4096, TPU = N / TILE;
-    auto kern = k_flat_vec3<NSUB, NT, UNROLL, MINB, GMAX>;
-    constexpr size_t smem = (size_t)2 * 3 * TILE * 2;
+    auto kern = k_flat_vec3<NSUB, NT, MINB>;
     static int grid_max = 0;
     if (!grid_max) {
         int per_sm = 0, dev = 0, sms = 148;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         cudaGetDevice(&dev);
@@ -1403,20 +1381,19 @@ static cudaError_t launch_flat_vec3_t(Launcher &L, FlatArgs &A) {
         grid_max = per_sm * sms;
         if (getenv("MNW_DEBUG")) fprintf(stderr, "k_flat_vec3<%d,%d,%d>: %d CTAs per SM\n", NSUB, NT, MINB, per_sm);
     }
-    // B-runs follow D units behind the A-runs, far enough (about two grids' worth of tickets) that a
-    // unit is complete and finalised before its first B-run is handed out; the ring holds 2*D units
-    constexpr int G = TPU < GMAX ? TPU : GMAX, RPU = TPU / G;
-    A.D = (2 * grid_max + 2 * RPU - 1) / (2 * RPU);
+    // B-tiles follow D units behind the A-tiles, far enough (about two grids' worth of tickets) that a
+    // unit is complete and finalised before its first B-tile is handed out; the ring holds 2*D units
+    A.D = (2 * grid_max + 2 * TPU - 1) / (2 * TPU);
     const long long dmax = (long long)(flat_scratch_bytes() / (2 * 3 * (size_t)N * 2));
     if (A.D > dmax) A.D = (int)dmax;
     if (A.D < 1) return cudaErrorInvalidValue;
     A.R = 2 * A.D;
-    const long long tickets = ((long long)A.nunits + A.D) * 2 * RPU;
+    const long long tickets = ((long long)A.nunits + A.D) * 2 * TPU;
     const unsigned grid = (unsigned)(tickets < grid_max ? tickets : grid_max);
     k_unit_q0<<<(3 * A.nunits + 255) / 256, 256, 0, L.stream>>>(A, (long long *)A.q0tab, NSUB);
     L.count++;
     L.begin("k_flat_vec3");
-    kern<<<grid, NT, smem, L.stream>>>(A);
+    kern<<<grid, NT, 0, L.stream>>>(A);
     L.end();
     L.count++;
     return cudaGetLastError();
@@ -1448,13 +1425,13 @@ cudaError_t launch_flat_vec3(Launcher &L, const FusedWork &W, void *work, void *
     if (e != cudaSuccess) return e;
     switch (nfile / subcells) {
         case 64: {
-            static const int minb = getenv("MNW_FLAT_MINB") ? atoi(getenv("MNW_FLAT_MINB")) : 4;   // tuning knobs
-            static const int g = getenv("MNW_FLAT_G") ? atoi(getenv("MNW_FLAT_G")) : 1;
-            if (minb == 4) return g == 2 ? launch_flat_vec3_t<64, 192, 2, 4, 2>(L, A) : launch_flat_vec3_t<64, 192, 2, 4, 1>(L, A);
-            return g == 2 ? launch_flat_vec3_t<64, 192, 2, 3, 2>(L, A) : launch_flat_vec3_t<64, 192, 2, 3, 1>(L, A);
+            static const int minb = getenv("MNW_FLAT_MINB") ? atoi(getenv("MNW_FLAT_MINB")) : 5;   // tuning knob
+            if (minb == 5) return launch_flat_vec3_t<64, 192, 5>(L, A);
+            if (minb == 3) return launch_flat_vec3_t<64, 192, 3>(L, A);
+            return launch_flat_vec3_t<64, 192, 4>(L, A);
         }
-        case 32: return launch_flat_vec3_t<32, 192, 2, 4, 1>(L, A);
-        case 16: return launch_flat_vec3_t<16, 192, 2, 4, 1>(L, A);
+        case 32: return launch_flat_vec3_t<32, 192, 4>(L, A);
+        case 16: return launch_flat_vec3_t<16, 192, 4>(L, A);
     }
     return cudaErrorNotSupported;
 }
