@@ -237,10 +237,10 @@ def run_gpu(args):
         with torch.cuda.stream(stream):
             e = [ev() for _ in range(5)] if record else None
             if record: e[0].record(stream)
-            vd = vel_descs()
-            state["vd"] = vd
             ctx.encode_vec3_subcells_dev(pdescs, pos, NFILE, SUB_CELLS, NFILES, *meta["x"], packed["x"], stride, out_len["x"])
             if record: e[1].record(stream)
+            vd = vel_descs()          # bounds() of the velocity field: its host sync overlaps the x encode
+            state["vd"] = vd
             ctx.encode_vec3_subcells_dev(vd, vel, NFILE, SUB_CELLS, NFILES, *meta["v"], packed["v"], stride, out_len["v"])
             if record: e[2].record(stream)
             if world > 1:
@@ -370,9 +370,13 @@ def run_gpu(args):
 
 
 def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
-    """The same step through mnw_encode_vec3_subcells / mnw_decode_vec3_subcells with
-    HOST buffers: every file's particles come from pinned host memory, packed bytes
-    and metadata go back to the host, are sent down again and decoded to host memory."""
+    """The same step through the host-pointer C ABI: every file's particles come from pinned host
+    memory (mnw_minp_encode_vectors: upload, limits, encode), packed bytes and metadata go back to
+    the host, are sent down again and decoded to host memory (mnw_decode_vec3_subcells).  A context
+    is single-threaded like a minnow.Writer, so the files are spread over a few worker threads with
+    one context each: the copies of one file overlap the kernels and the opposite-direction copies
+    of the others (the calls release the GIL)."""
+    import ctypes as C
     import psutil
     budget = 0.35 * psutil.virtual_memory().available / max(world, 1)
     per_file = 2 * 12 * NP_FILE
@@ -382,46 +386,54 @@ def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
     hpos.copy_(pos[:nfiles])
     hvel.copy_(vel[:nfiles])
     stride = 4 * NP_FILE + 256
-    hout = torch.empty(3 * stride, dtype=torch.uint8).pin_memory()
-    hdec = torch.empty((NP_FILE, 3), dtype=torch.float32).pin_memory()
     nbk = 3 * SC3
-    mins, bits, offs = (np.zeros(nbk, np.int64) for _ in range(3))
-    lens = np.zeros(3, np.int64)
-    import ctypes as C
-    lib, h = ctx.lib, ctx.h
-    jit = mb.Jitter.make(mb.JITTER_HASH, 7)
+    nworkers = max(1, min(args.e2e_threads, nfiles))
     P = lambda a: C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
-    h2d = d2h = 0
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    def one(field, f, count):
-        nonlocal h2d, d2h
-        src = hpos[f] if field == "x" else hvel[f]
-        if field == "x":
-            d3 = (mb.FloatDesc * 3)(*pdescs)
-            wrap = L_BOX
-        else:
-            lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
-            ctx._check(lib.mnw_vec3_limits(h, P(src), NP_FILE, 1, P(lo), P(hi)))
-            d3 = (mb.FloatDesc * 3)(*[mb.FloatDesc.make(lo[k], hi[k], mb.float_group_pixels(lo[k], hi[k], DV)) for k in range(3)])
-            wrap = 0.0
-            if count: h2d += 12 * NP_FILE
-        ctx._check(lib.mnw_encode_vec3_subcells(h, d3, P(src), NFILE, SUB_CELLS, P(mins), P(bits), P(offs), P(hout), stride, P(lens)))
-        ptrs = (C.c_void_p * 3)(*[hout.data_ptr() + k * stride for k in range(3)])
-        ctx._check(lib.mnw_decode_vec3_subcells(h, d3, ptrs, P(lens), P(offs), P(mins), P(bits), NFILE, SUB_CELLS, wrap,
-                                                C.byref(jit), P(hdec)))
-        if count:
-            pk = int(lens.sum())
-            h2d += 12 * NP_FILE + pk + 3 * 8 * nbk
-            d2h += pk + 3 * 8 * nbk + 12 * NP_FILE
+    class Worker:
+        def __init__(self):
+            self.ctx = mb.Context(local_rank)
+            self.hout = torch.empty(3 * stride, dtype=torch.uint8).pin_memory()
+            self.hdec = torch.empty((NP_FILE, 3), dtype=torch.float32).pin_memory()
+            self.mins, self.bits, self.offs = (np.zeros(nbk, np.int64) for _ in range(3))
+            self.lens = np.zeros(3, np.int64)
+            self.d3 = (mb.FloatDesc * 3)()
+            self.jit = mb.Jitter.make(mb.JITTER_HASH, 7)
+            self.h2d = self.d2h = 0
 
-    one("x", 0, False); one("v", 0, False)     # warm-up (buffers grow once)
+        def one(self, field, f, count):
+            c, lib = self.ctx, self.ctx.lib
+            src = hpos[f] if field == "x" else hvel[f]
+            periodic = field == "x"
+            c._check(lib.mnw_minp_encode_vectors(c.h, P(src), NFILE, SUB_CELLS, int(periodic), L_BOX if periodic else 0.0,
+                                                 DX_POS if periodic else DV, self.d3, P(self.mins), P(self.bits),
+                                                 P(self.offs), P(self.hout), stride, P(self.lens)))
+            ptrs = (C.c_void_p * 3)(*[self.hout.data_ptr() + k * stride for k in range(3)])
+            c._check(lib.mnw_decode_vec3_subcells(c.h, self.d3, ptrs, P(self.lens), P(self.offs), P(self.mins), P(self.bits),
+                                                  NFILE, SUB_CELLS, L_BOX if periodic else 0.0, C.byref(self.jit), P(self.hdec)))
+            if count:
+                pk = int(self.lens.sum())
+                self.h2d += 12 * NP_FILE + pk + 3 * 8 * nbk
+                self.d2h += pk + 3 * 8 * nbk + 12 * NP_FILE
+
+        def run(self, files, count):
+            for f in files:
+                self.one("x", f, count)
+                self.one("v", f, count)
+
+    workers = [Worker() for _ in range(nworkers)]
+    for w in workers:                              # warm-up (buffers grow once)
+        w.run([0], False)
     torch.cuda.synchronize()
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
-        for f in range(nfiles):
-            one("x", f, True)
-            one("v", f, True)
+        ths = [threading.Thread(target=w.run, args=(range(i, nfiles, nworkers), True)) for i, w in enumerate(workers)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -431,11 +443,14 @@ def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
     dt = float(t.item())
     nbytes = steps * nfiles * 4 * 12 * NP_FILE
     scale = NFILES / nfiles                       # bytes per full step, as counted from the copies made
+    h2d, d2h = sum(w.h2d for w in workers), sum(w.d2h for w in workers)
+    for w in workers:
+        w.ctx.close()
     return {"value": world * nbytes / dt / 1e9, "unit": "GB/s",
             "h2d_bytes_per_step": int(h2d / steps * scale), "d2h_bytes_per_step": int(d2h / steps * scale),
-            "files_timed_per_step": nfiles, "steps": steps,
-            "api": "mnw_vec3_limits + mnw_encode_vec3_subcells + mnw_decode_vec3_subcells, one file per call, "
-                   "pinned host buffers, synchronous"}
+            "files_timed_per_step": nfiles, "steps": steps, "host_threads": nworkers,
+            "api": "mnw_minp_encode_vectors + mnw_decode_vec3_subcells, one file per call, pinned host buffers, "
+                   "%d host threads with one context each" % nworkers}
 
 
 def main():
@@ -446,6 +461,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

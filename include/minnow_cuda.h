@@ -169,6 +169,13 @@ MNW_API int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3],
                                      int64_t nfile, int64_t subcells, int64_t *mins, int64_t *bits,
                                      int64_t *offsets, uint8_t *out, int64_t out_axis_stride,
                                      int64_t out_len[3]);
+/* The whole of minp.Writer.Vectors for one file (go/minp/minp.go:86-119) with ONE upload of the
+ * particles: limits ([0, L) per axis when periodic, go/minp/minp.go:88-90; else bounds() and
+ * Nextafter32, :92-95), pixels (go/writer.go:73), then the encode above.  desc_out receives the
+ * three FloatGroup parameter sets the file's group tails need. */
+MNW_API int mnw_minp_encode_vectors(mnw_ctx *ctx, const float *aos, int64_t nfile, int64_t subcells, int periodic,
+                                    float L, float dx, mnw_float_desc desc_out[3], int64_t *mins, int64_t *bits,
+                                    int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t out_len[3]);
 MNW_API int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3],
                                      const uint8_t *const data[3], const int64_t data_len[3],
                                      const int64_t *offsets, const int64_t *mins, const int64_t *bits,

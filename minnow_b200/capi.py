@@ -57,6 +57,7 @@ SIGNATURES = {
     "mnw_version": (C.c_char_p, []),
     "mnw_launch_count": (_i64, [_p]),
     "mnw_selftest_fastdiv": (_int, [_p, _FD, C.c_uint32, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "mnw_minp_encode_vectors": (_int, [_p, _p, _i64, _i64, _int, _f32, _f32, _FD, _p, _p, _p, _p, _i64, _p]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
     "mnw_pack": (_int, [_p, _int, _p, _i64, _p]),
@@ -297,6 +298,22 @@ class Context:
         self._check(self.lib.mnw_encode_vec3_subcells(self.h, d3, _ptr(aos), nfile, subcells, _ptr(mins),
                                                       _ptr(bits), _ptr(offs), _ptr(out), stride, _ptr(lens)))
         return mins, bits, offs, [out[k * stride:k * stride + lens[k]].copy() for k in range(3)]
+
+    def minp_encode_vectors(self, aos, nfile, subcells, periodic, L, dx):
+        """minp.Writer.Vectors for one file (go/minp/minp.go:86-119), one upload.
+        -> (descs[3], mins, bits, offsets, [bytes_x, bytes_y, bytes_z])"""
+        aos = _np(aos, np.float32).reshape(-1)
+        assert len(aos) == 3 * nfile ** 3
+        nb = 3 * subcells ** 3
+        mins, bits, offs = (np.zeros(nb, np.int64) for _ in range(3))
+        stride = 8 * nfile ** 3 + 8
+        out = np.zeros(3 * stride, np.uint8)
+        lens = np.zeros(3, np.int64)
+        d3 = (FloatDesc * 3)()
+        self._check(self.lib.mnw_minp_encode_vectors(self.h, _ptr(aos), nfile, subcells, int(bool(periodic)), float(L), float(dx),
+                                                     d3, _ptr(mins), _ptr(bits), _ptr(offs), _ptr(out), stride, _ptr(lens)))
+        descs = [FloatDesc.make(d.low, d.high, d.pixels, d.periodic) for d in d3]
+        return descs, mins, bits, offs, [out[k * stride:k * stride + lens[k]].copy() for k in range(3)]
 
     def decode_vec3_subcells(self, descs, data3, offsets, mins, bits, nfile, subcells, wrap_L=0.0, jitter=None):
         """body of minp.Reader.Vectors (go/minp/minp.go:191-206) -> [nfile^3, 3] float32"""

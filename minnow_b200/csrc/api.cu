@@ -600,18 +600,15 @@ int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
 }
 
 // ---- minp host-pointer entry points -------------------------------------------
-int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
-                             int64_t subcells, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
-                             int64_t out_axis_stride, int64_t out_len[3]) {
-    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
-        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+// Encode the cube already resident in ctx->in and stage the results out to the host.
+static int encode_vec3_resident(mnw_ctx *ctx, const mnw_float_desc desc[3], int64_t nfile, int64_t subcells,
+                                int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                                int64_t out_axis_stride, int64_t out_len[3]) {
     const int64_t np = nfile * nfile * nfile, sc3 = subcells * subcells * subcells, nb = 3 * sc3;
     const int64_t stride = (8 * np + 255) & ~255LL;  // worst case: 64 bits per value
-    CU(ctx->in.reserve(12 * (size_t)np + 16));
     CU(ctx->out.reserve(3 * (size_t)stride + 64));
     int rc = reserve_batch(ctx, nb, 3);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));
     int64_t *d_meta = ctx->meta.as<int64_t>();
     rc = mnw_encode_vec3_subcells_dev(ctx, desc, 0, ctx->in.as<float>(), nfile, subcells, 1, d_meta, d_meta + nb,
                                       d_meta + 2 * nb, ctx->out.as<uint8_t>(), stride, d_meta + 3 * nb);
@@ -634,6 +631,41 @@ int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const f
     }
     CU(cudaStreamSynchronize(ctx->L.stream));
     return MNW_OK;
+}
+
+int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
+                             int64_t subcells, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                             int64_t out_axis_stride, int64_t out_len[3]) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    const int64_t np = nfile * nfile * nfile;
+    CU(ctx->in.reserve(12 * (size_t)np + 16));
+    CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));
+    return encode_vec3_resident(ctx, desc, nfile, subcells, mins, bits, offsets, out, out_axis_stride, out_len);
+}
+
+int mnw_minp_encode_vectors(mnw_ctx *ctx, const float *aos, int64_t nfile, int64_t subcells, int periodic, float L,
+                            float dx, mnw_float_desc desc_out[3], int64_t *mins, int64_t *bits, int64_t *offsets,
+                            uint8_t *out, int64_t out_axis_stride, int64_t out_len[3]) {
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    const int64_t np = nfile * nfile * nfile;
+    CU(ctx->in.reserve(12 * (size_t)np + 16));
+    CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));   // the one upload
+    float lo[3] = {0.0f, 0.0f, 0.0f}, hi[3] = {L, L, L};                                            // go/minp/minp.go:88-90
+    if (!periodic) {                                                                                // :92-95
+        int rc = mnw_vec3_limits_dev(ctx, ctx->in.as<float>(), np, 1, lo, hi);
+        if (rc) return rc;
+    }
+    mnw_float_desc d[3];
+    for (int k = 0; k < 3; k++) {
+        memset(&d[k], 0, sizeof d[k]);
+        d[k].low = lo[k]; d[k].high = hi[k];
+        d[k].pixels = mnw_float_group_pixels(lo[k], hi[k], dx);                                     // go/writer.go:73
+        d[k].periodic = 1;                                                                          // go/writer.go:74
+        if (desc_out) desc_out[k] = d[k];
+    }
+    return encode_vec3_resident(ctx, d, nfile, subcells, mins, bits, offsets, out, out_axis_stride, out_len);
 }
 
 int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const uint8_t *const data[3],

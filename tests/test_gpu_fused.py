@@ -216,3 +216,23 @@ def test_fast_quantiser_matches_ieee_divide(ctx):
         hi = float(np.float32(dx) * np.float32(pixels))
         bad, acc = ctx.selftest_fastdiv(mb.FloatDesc.make(0.0, hi, pixels), 0x3f800000, 1 << 28)
         assert bad == 0, hex(dxbits)
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_minp_encode_vectors_single_upload(ctx, orc, periodic):
+    """mnw_minp_encode_vectors = limits + pixels + encode of minp.Writer.Vectors (go/minp/minp.go:86-119)
+    in one call: same group parameters and bytes as the oracle's writer"""
+    rng = np.random.default_rng(77)
+    nfile, subcells, L, dx = 32, 2, 250.0, 0.01
+    vec = lagrangian(rng, nfile, L, 1.5) if periodic else (150.0 * rng.standard_normal((nfile ** 3, 3))).astype(np.float32)
+    descs, mins, bits, offs, streams = ctx.minp_encode_vectors(vec, nfile, subcells, periodic, L, dx)
+    lo, hi = orc.minp_limits(vec, periodic, L)
+    px = [orc.float_group_pixels(float(lo[k]), float(hi[k]), np.float32(dx)) for k in range(3)]
+    for k in range(3):
+        assert (np.float32(descs[k].low), np.float32(descs[k].high), descs[k].pixels) == (lo[k], hi[k], px[k])
+    om, ob, onb, packed, stride, _ = orc.bench_minp_encode(vec, nfile, subcells, lo.tolist(), hi.tolist(), px)
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob)
+    sc3 = subcells ** 3
+    for k in range(3):
+        want = b"".join(packed[t * stride:t * stride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
+        assert streams[k].tobytes() == want
