@@ -132,6 +132,15 @@ def physical_gpu_index(local_rank):
 # CPU legs (oracle = port of the reference; test infrastructure, only ever the thing timed
 # here as the BASELINE, never as the product)
 # ---------------------------------------------------------------------------------------
+def host_threads():
+    """All the cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not
+    what the CPU legs should be limited to)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_descs(orc, vel_np):
     lo, hi = orc.minp_limits(vel_np, False, L_BOX)
     vpx = [orc.float_group_pixels(float(lo[k]), float(hi[k]), np.float32(DV)) for k in range(3)]
@@ -157,7 +166,7 @@ def run_reference(args):
     import torch
     from oracle import oracle as orc
     orc.lib()
-    threads = orc.max_threads()
+    threads = host_threads()
     pos, vel = gen_file(torch, 0, 2, "cpu")
     pos_np, vel_np = pos.numpy(), vel.numpy()
     for _ in range(args.warmup):
@@ -343,7 +352,7 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as orc
         orc.lib()
-        threads = orc.max_threads()
+        threads = host_threads()
         p0, v0 = pos[0].cpu().numpy(), vel[0].cpu().numpy()
         cpu_step(orc, p0, v0, threads)
         t0 = time.perf_counter()

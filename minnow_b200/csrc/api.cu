@@ -361,6 +361,7 @@ void mnw_destroy(mnw_ctx *ctx) {
 const char *mnw_last_error(const mnw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int mnw_sync(mnw_ctx *ctx) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     CU(cudaStreamSynchronize(ctx->L.stream));
     return MNW_OK;
 }
@@ -385,6 +386,7 @@ int64_t mnw_float_group_pixels(float lo, float hi, float dx) {
 uint32_t mnw_jitter_hash32(uint64_t seed, uint64_t block_id, uint64_t i) { return jitter_hash32(seed, block_id, i); }
 
 int mnw_pack(mnw_ctx *ctx, int bits, const uint64_t *x, int64_t n, uint8_t *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (bits > 64) return fail(ctx, MNW_ERR_ARG, "Cannot pack more than 64 bits per element into a bit.Array");
     if (bits < 1 || n < 0) return fail(ctx, MNW_ERR_ARG, "mnw_pack: bits = %d, n = %lld", bits, (long long)n);
     if (n == 0) return MNW_OK;
@@ -402,12 +404,14 @@ int mnw_pack(mnw_ctx *ctx, int bits, const uint64_t *x, int64_t n, uint8_t *out)
 }
 
 int mnw_unpack(mnw_ctx *ctx, int bits, const uint8_t *in, int64_t n, uint64_t *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (bits < 1 || bits > 64 || n < 0) return fail(ctx, MNW_ERR_ARG, "mnw_unpack: bits = %d, n = %lld", bits, (long long)n);
     int64_t off = 0, mn = 0, bt = bits;
     return decode_blocks_host(ctx, 0, nullptr, in, array_bytes(bits, n), &off, &mn, &bt, n, 1, nullptr, nullptr, out);
 }
 
 int mnw_bits(mnw_ctx *ctx, const uint64_t *x, int64_t n, int *bits) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (n < 0 || !bits) return fail(ctx, MNW_ERR_ARG, "mnw_bits: bad argument");
     if (n == 0) { *bits = 0; return MNW_OK; }
     CU(ctx->in.reserve(8 * (size_t)n));
@@ -427,12 +431,14 @@ int mnw_bits(mnw_ctx *ctx, const uint64_t *x, int64_t n, int *bits) {
 int mnw_encode_int_group(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks, const int64_t *starts,
                          int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap,
                          int64_t *out_len) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return encode_group_host(ctx, KIND_I64, nullptr, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
 }
 
 int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x, int64_t n, int64_t nblocks,
                            const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
                            int64_t out_cap, int64_t *out_len) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
     return encode_group_host(ctx, KIND_F32, desc, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
@@ -441,17 +447,20 @@ int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float
 int mnw_decode_int_blocks(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,
                           const int64_t *mins, const int64_t *bits, int64_t n, int64_t nsel, const int64_t *sel,
                           int64_t *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return decode_blocks_host(ctx, 0, nullptr, data, data_len, offsets, mins, bits, n, nsel, sel, nullptr, out);
 }
 
 int mnw_decode_float_blocks(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data, int64_t data_len,
                             const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n,
                             int64_t nsel, const int64_t *sel, const mnw_jitter *jitter, float *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return decode_blocks_host(ctx, 1, desc, data, data_len, offsets, mins, bits, n, nsel, sel, jitter, out);
 }
 
 int mnw_scan_offsets(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base, int64_t *offsets,
                      int64_t *total) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
     cudaError_t e = cudaSuccess;
     CU(ctx->meta.reserve(8 * (size_t)(2 * nblocks + 2)));
@@ -470,6 +479,7 @@ int mnw_scan_offsets(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64
 // ---- device-resident variants ------------------------------------------------
 int mnw_encode_int_group_dev(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t nblocks, int64_t *mins,
                              int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return encode_group_dev(ctx, KIND_I64, nullptr, x, n, nblocks, nullptr, nullptr, nullptr, 0, 0, mins, bits,
                             offsets, out, out_cap, out_len);
 }
@@ -477,6 +487,7 @@ int mnw_encode_int_group_dev(mnw_ctx *ctx, const int64_t *x, int64_t n, int64_t 
 int mnw_encode_float_group_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const float *x, int64_t n,
                                int64_t nblocks, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
                                int64_t out_cap, int64_t *out_len) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return encode_group_dev(ctx, KIND_F32, desc, x, n, nblocks, nullptr, nullptr, nullptr, 0, 0, mins, bits,
                             offsets, out, out_cap, out_len);
 }
@@ -484,6 +495,7 @@ int mnw_encode_float_group_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const f
 int mnw_decode_int_blocks_dev(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,
                               const int64_t *mins, const int64_t *bits, int64_t n, int64_t nsel,
                               const int64_t *sel, int64_t *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     DecodeHost h;
     h.mode = 0; h.data = data; h.stream_len = data_len; h.offsets = offsets; h.mins = mins; h.bits = bits;
     h.sel = sel; h.n = n; h.nsel = nsel; h.out = out;
@@ -495,6 +507,7 @@ int mnw_decode_int_blocks_dev(mnw_ctx *ctx, const uint8_t *data, int64_t data_le
 int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const uint8_t *data, int64_t data_len,
                                 const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n,
                                 int64_t nsel, const int64_t *sel, const mnw_jitter *jitter, float *out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     DecodeHost h;
     h.mode = 1;
     int rc = fill_decode_float(ctx, h, desc, 1, jitter);
@@ -510,6 +523,7 @@ int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const 
 int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file, const float *aos,
                                  int64_t nfile, int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
                                  int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0 || nfile > 2048)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     int rc0 = check_desc(ctx, desc);
@@ -577,6 +591,7 @@ int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
                                  int64_t data_axis_stride, const int64_t *offsets, const int64_t *mins,
                                  const int64_t *bits, int64_t nfile, int64_t subcells, int64_t nfiles,
                                  float wrap_L, const mnw_jitter *jitter, float *aos_out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     DecodeHost h;
@@ -636,6 +651,7 @@ static int encode_vec3_resident(mnw_ctx *ctx, const mnw_float_desc desc[3], int6
 int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const float *aos, int64_t nfile,
                              int64_t subcells, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
                              int64_t out_axis_stride, int64_t out_len[3]) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     const int64_t np = nfile * nfile * nfile;
@@ -647,6 +663,7 @@ int mnw_encode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const f
 int mnw_minp_encode_vectors(mnw_ctx *ctx, const float *aos, int64_t nfile, int64_t subcells, int periodic, float L,
                             float dx, mnw_float_desc desc_out[3], int64_t *mins, int64_t *bits, int64_t *offsets,
                             uint8_t *out, int64_t out_axis_stride, int64_t out_len[3]) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     const int64_t np = nfile * nfile * nfile;
@@ -672,6 +689,7 @@ int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const u
                              const int64_t data_len[3], const int64_t *offsets, const int64_t *mins,
                              const int64_t *bits, int64_t nfile, int64_t subcells, float wrap_L,
                              const mnw_jitter *jitter, float *aos_out) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0)
         return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
     const int64_t np = nfile * nfile * nfile, sc3 = subcells * subcells * subcells, nb = 3 * sc3;
@@ -704,6 +722,7 @@ int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const u
 
 int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base, int64_t *offsets,
                          int64_t *total) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
     cudaError_t e = launch_scan_sizes(ctx->L, nbytes, nblocks, base, offsets, total);
     if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
@@ -712,6 +731,7 @@ int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, i
 
 int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t first_bits, uint64_t count,
                          uint64_t *mismatches, uint64_t *accepted) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
     if ((uint64_t)first_bits + count > (1ULL << 32)) return fail(ctx, MNW_ERR_ARG, "bit pattern range exceeds 2^32");
@@ -727,11 +747,13 @@ int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t firs
 }
 
 int mnw_profile(mnw_ctx *ctx, int on) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     ctx->L.prof = on != 0;
     return MNW_OK;
 }
 
 int mnw_profile_summary(mnw_ctx *ctx, char *buf, int64_t cap) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     CU(cudaStreamSynchronize(ctx->L.stream));
     struct Agg { const char *name; int64_t n; double ms; };
     std::vector<Agg> agg;
@@ -765,6 +787,7 @@ static inline float key_to_float(uint32_t k) {
 }
 
 int mnw_vec3_limits_dev(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (np <= 0 || nfiles < 0) return fail(ctx, MNW_ERR_ARG, "vec3 limits of an empty cube (the reference indexes vec[0])");
     if ((np + 32767) / 32768 >= 65536LL * 32768 || nfiles > 65535) return fail(ctx, MNW_ERR_ARG, "too many files in one call");
     CU(ctx->aux.reserve(24 * (size_t)nfiles + 64));
@@ -783,6 +806,7 @@ int mnw_vec3_limits_dev(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfil
 }
 
 int mnw_vec3_limits(mnw_ctx *ctx, const float *aos, int64_t np, int64_t nfiles, float *lo, float *hi) {
+    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (np <= 0 || nfiles < 0) return fail(ctx, MNW_ERR_ARG, "vec3 limits of an empty cube (the reference indexes vec[0])");
     CU(ctx->in.reserve(12 * (size_t)(np * nfiles) + 16));
     CU(cudaMemcpyAsync(ctx->in.p, aos, 12 * (size_t)(np * nfiles), cudaMemcpyHostToDevice, ctx->L.stream));
