@@ -395,6 +395,44 @@ __global__ void __launch_bounds__(256) k_vec3_limits(const float *__restrict__ a
     }
 }
 
+// The same with 128-bit loads (np a multiple of 4, 16-byte aligned cubes): 192 threads, so that a
+// thread's float4 always starts on the same axis and its 4 floats have fixed axes (a0, a0+1, a0+2, a0).
+constexpr int LIMITS4_THREADS = 192, LIMITS4_PER_THREAD = 16;
+__global__ void __launch_bounds__(LIMITS4_THREADS) k_vec3_limits4(const float *__restrict__ aos, int64_t np, uint32_t *keys) {
+    const int64_t f = blockIdx.y;
+    const float4 *base = (const float4 *)(aos + 3 * f * np);
+    const int64_t n4 = 3 * np / 4;
+    const int64_t c0 = (int64_t)blockIdx.x * (LIMITS4_THREADS * LIMITS4_PER_THREAD);
+    const int a0 = threadIdx.x % 3;   // c0 and the thread stride are multiples of 3
+    const float inf = __int_as_float(0x7f800000);
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};   // relative axis j = actual (a0 + j) % 3
+#pragma unroll 4
+    for (int i = 0; i < LIMITS4_PER_THREAD; i++) {
+        const int64_t g = c0 + threadIdx.x + (int64_t)LIMITS4_THREADS * i;
+        if (g < n4) {
+            const float4 v = __ldcs(base + g);
+            // fminf / fmaxf drop a NaN operand: NaN never wins a comparison in bounds() either
+            mn[0] = fminf(mn[0], fminf(v.x, v.w)); mx[0] = fmaxf(mx[0], fmaxf(v.x, v.w));
+            mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+        }
+    }
+    __shared__ uint32_t s_k[6];
+    if (threadIdx.x < 6) s_k[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int ax = (a0 + j) % 3;
+        if (mn[j] <= mx[j]) {   // at least one non-NaN value seen
+            atomicMin(&s_k[ax], float_key(mn[j]));
+            atomicMax(&s_k[3 + ax], float_key(mx[j]));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(&keys[f * 6 + threadIdx.x], s_k[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(&keys[f * 6 + threadIdx.x], s_k[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------
 // scan: one CTA per chain (= minnow group); exclusive prefix of nbytes
 // ---------------------------------------------------------------------------
@@ -721,9 +759,17 @@ void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int6
     k_limits_init<<<grid_for(nfiles * 6, 256), 256, 0, L.stream>>>(keys, nfiles);
     L.count++;
     if (np_per_file == 0) return;
-    int64_t chunks = (np_per_file + LIMITS_CHUNK - 1) / LIMITS_CHUNK;
-    dim3 grid((unsigned)chunks, (unsigned)nfiles);
-    k_vec3_limits<<<grid, 256, 0, L.stream>>>(aos, np_per_file, keys);
+    if (np_per_file % 4 == 0 && ((uintptr_t)aos & 15) == 0) {
+        const int64_t per_cta = LIMITS4_THREADS * LIMITS4_PER_THREAD;
+        dim3 grid((unsigned)((3 * np_per_file / 4 + per_cta - 1) / per_cta), (unsigned)nfiles);
+        L.begin("k_vec3_limits4");
+        k_vec3_limits4<<<grid, LIMITS4_THREADS, 0, L.stream>>>(aos, np_per_file, keys);
+        L.end();
+    } else {
+        int64_t chunks = (np_per_file + LIMITS_CHUNK - 1) / LIMITS_CHUNK;
+        dim3 grid((unsigned)chunks, (unsigned)nfiles);
+        k_vec3_limits<<<grid, 256, 0, L.stream>>>(aos, np_per_file, keys);
+    }
     L.count++;
 }
 
