@@ -163,9 +163,12 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
 
     ctx->last_path = 0;
     launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks);
+    // contiguous float32 blocks of a periodic group with pixels < 2^31: the vectorised two-pass kernels
+    const bool f32c = !ctx->force_generic && kind == KIND_F32 && (fp.flags & F_PERIODIC) && fp.pixels >= 1 &&
+                      fp.pixels < (1LL << 31);
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
-                          0, out_cap);
+                          0, out_cap, nullptr, f32c);
     CU(cudaGetLastError());
     return MNW_OK;
 }

@@ -39,6 +39,7 @@
 #include "engine.cuh"
 #include "fused.cuh"
 #include "launch.cuh"
+#include "pack.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -129,54 +130,6 @@ __device__ __noinline__ int quantize_rare(float x, float low, float dx, int P, u
     return 0;
 }
 
-// 32 values of B bits -> B words, all shifts resolved at compile time.  The fields do
-// not overlap, so + is | and (v << sh) + o is a single LEA / IMAD.
-template <int B>
-__device__ __forceinline__ void pack32(const unsigned (&v)[32], unsigned (&o)[16]) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) o[j] = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        const int bit = i * B, wd = bit >> 5, sh = bit & 31;
-        o[wd] += v[i] << sh;
-        if (sh + B > 32) o[wd + 1] = v[i] >> (32 - sh);
-    }
-}
-
-// Write the group's 32*B stream words to dst (any byte alignment).  Interior words go
-// out as aligned 32-bit stores, 128 bytes per instruction; the bytes of the first and last
-// partial word are stored one by one, because the neighbouring groups own the rest of
-// those words.  Word j of the stream sits at region[j ^ (j >> 5)].
-template <int B>
-__device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region, int lane) {
-    const int a = (int)((uintptr_t)dst & 3);
-    uint32_t *base = (uint32_t *)(dst - a) + lane;
-    if (a == 0) {
-#pragma unroll
-        for (int m = 0; m < B; m++) base[32 * m] = region[32 * m + (lane ^ m)];
-        return;
-    }
-    const int sh = 32 - 8 * a;
-    // aligned word j (1 <= j < 32*B) = stream words j-1 and j, funnel-shifted
-    unsigned prev = 0;   // stream word 32*m - 1, wanted by lane 0
-#pragma unroll
-    for (int m = 0; m < B; m++) {
-        const unsigned hi = region[32 * m + (lane ^ m)];
-        unsigned lo = __shfl_up_sync(0xffffffffu, hi, 1);
-        if (lane == 0) lo = prev;
-        prev = __shfl_sync(0xffffffffu, hi, 31);
-        if (m > 0 || lane > 0) base[32 * m] = __funnelshift_r(lo, hi, sh);
-        else {   // head: bytes a..3 of aligned word 0 = low bytes of stream word 0
-            uint8_t *bp = (uint8_t *)base;
-            for (int k = a; k < 4; k++) bp[k] = (uint8_t)(hi >> (8 * (k - a)));
-        }
-    }
-    if (lane == 0) {   // tail: bytes 0..a-1 of aligned word 32*B = high bytes of the last stream word
-        uint8_t *bp = (uint8_t *)(base + 32 * B);
-        for (int k = 0; k < a; k++) bp[k] = (uint8_t)(prev >> (8 * (4 - a + k)));
-    }
-}
-
 // One pack group = 1024 consecutive elements of one block = 32 lanes x 32 values ->
 // 32*B words.  The words are transposed in place through the group's own 2 KiB of
 // staging (XOR swizzle: conflict-free both ways) so that the warp can write them out in
@@ -184,7 +137,7 @@ __device__ __forceinline__ void write_group(uint8_t *dst, const unsigned *region
 template <int B>
 __device__ __forceinline__ void pack_group_words(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst0,
                                                  const long long *off, const int *offgen, int gen) {
-    unsigned o[16];
+    unsigned o[B];
     pack32<B>(v, o);
     __syncwarp();
 #pragma unroll
@@ -643,7 +596,7 @@ __device__ __forceinline__ int ld_volatile_i32(const int *p) {
 
 template <int B>
 __device__ __forceinline__ void pack_group_flat(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst) {
-    unsigned o[16];
+    unsigned o[B];
     pack32<B>(v, o);
     __syncwarp();
 #pragma unroll

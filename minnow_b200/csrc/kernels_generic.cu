@@ -19,6 +19,7 @@
 #include "engine.cuh"
 #include "device_math.cuh"
 #include "launch.cuh"
+#include "pack.cuh"
 
 namespace mnw {
 
@@ -734,6 +735,277 @@ k_scan_sizes(const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets, in
 }
 
 // ---------------------------------------------------------------------------
+// Fast path for contiguous float32 blocks of periodic groups with pixels < 2^31 (every
+// FloatGroup the reference's Writer can create, go/writer.go:72-75): the same two passes as
+// k_stats / k_pack, but with 128-bit loads, the division-free quantiser (device_math.cuh
+// quantize_fast, exact IEEE redo for any element it does not vouch for), 32-bit statistics,
+// and the warp-level compile-time packer of pack.cuh.
+// ---------------------------------------------------------------------------
+struct QuantP {
+    float low, high, dx, hi_clamp, rcp, ndx;
+    unsigned P, tmax;
+    int flags;
+    bool fast_ok;
+};
+__device__ __forceinline__ QuantP quant_params(const BlockDesc &d) {
+    QuantP p;
+    p.low = d.low; p.high = d.high; p.dx = d.dx; p.hi_clamp = d.hi_clamp;
+    p.rcp = __frcp_rn(d.dx); p.ndx = -d.dx;
+    p.P = (unsigned)d.pixels;
+    p.tmax = __float_as_uint(__fsub_rn(d.high, d.low));
+    p.flags = d.flags;
+    p.fast_ok = d.dx > 0x1p-60f && d.dx < 0x1p60f && d.pixels >= 2;
+    return p;
+}
+// pixel index of one element, folded into [0, pixels) (pixels -> 0, see k_stats); *raw gets the
+// reference's unfolded int64 when the element is out of range (oob)
+__device__ __forceinline__ unsigned quant_elem(float v, const QuantP &p, bool &oob, long long *raw) {
+    if (p.flags & (F_LOG10 | F_CLAMP)) v = minh_pre(v, p.flags & F_LOG10, p.flags & F_CLAMP, p.low, p.high, p.hi_clamp);
+    const float tt = __fsub_rn(v, p.low);
+    float y = __fmul_rn(tt, p.rcp);
+    float e = __fmaf_rn(p.ndx, y, tt);
+    y = __fmaf_rn(e, p.rcp, y);
+    e = __fmaf_rn(p.ndx, y, tt);
+    y = __fmaf_rn(e, p.rcp, y);
+    unsigned q = (unsigned)__float2int_rd(y);
+    if (!(p.fast_ok && __float_as_uint(tt) <= p.tmax && q < p.P)) {   // rare: the IEEE divide decides
+        const long long qq = quantize_exact(v, p.low, p.dx);
+        if (raw) *raw = qq;
+        if (qq == (long long)p.P) q = 0;
+        else if ((unsigned long long)qq < (unsigned long long)p.P) q = (unsigned)qq;
+        else { oob = true; q = 0; }
+    } else if (raw) {
+        *raw = q;
+    }
+    return q;
+}
+
+constexpr int FSTAT_THREADS = 256;
+__global__ void __launch_bounds__(FSTAT_THREADS)
+k_stats_f32c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh, const int *run_if) {
+    __shared__ unsigned s_r[FSTAT_THREADS / 32][5];
+    if (run_if && *run_if == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t chunk = blockIdx.x; chunk < sh.total_chunks; chunk += gridDim.x) {
+        const int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
+        const int64_t b = find_block(descs, sh, chunk, cpb, false);
+        const BlockDesc d = descs[b];
+        const int64_t first = (chunk - d.chunk0) * STATS_CHUNK;
+        const int count = (int)((first + STATS_CHUNK < d.n ? first + STATS_CHUNK : d.n) - first);
+        const QuantP qp = quant_params(d);
+        const long long q0 = stats[b].q0;
+        const bool q0_ok = (unsigned long long)q0 < (unsigned long long)qp.P;
+        const unsigned C = q0_ok ? (unsigned)arc_rotation(q0, qp.P) : 0u;
+        unsigned wmin = ~0u, wmax = 0u, qmin = ~0u, qmax = 0u;
+        bool oob = !q0_ok;
+        const float *p = (const float *)d.src + first;
+        const int a = (int)(((uintptr_t)p & 15) >> 2);          // elements of the first 16 bytes that precede the chunk
+        const float4 *base4 = (const float4 *)(p - a);
+        const int nvec = (a + count + 3) >> 2;
+#pragma unroll 2
+        for (int iv = threadIdx.x; iv < nvec; iv += FSTAT_THREADS) {
+            const float4 v4 = __ldcs(base4 + iv);
+            const float x[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int el = 4 * iv + c - a;
+                if (el >= 0 && el < count) {
+                    const unsigned q = quant_elem(x[c], qp, oob, nullptr);
+                    unsigned w = q + C;
+                    w = min(w, w - qp.P);
+                    wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
+                }
+            }
+        }
+        wmin = __reduce_min_sync(0xffffffffu, wmin); wmax = __reduce_max_sync(0xffffffffu, wmax);
+        qmin = __reduce_min_sync(0xffffffffu, qmin); qmax = __reduce_max_sync(0xffffffffu, qmax);
+        const unsigned ob = __any_sync(0xffffffffu, oob);
+        if (lane == 0) { s_r[warp][0] = wmin; s_r[warp][1] = wmax; s_r[warp][2] = qmin; s_r[warp][3] = qmax; s_r[warp][4] = ob; }
+        __syncthreads();
+        if (threadIdx.x == 0 && count > 0) {
+            for (int wi = 1; wi < FSTAT_THREADS / 32; wi++) {
+                wmin = min(wmin, s_r[wi][0]); wmax = max(wmax, s_r[wi][1]);
+                qmin = min(qmin, s_r[wi][2]); qmax = max(qmax, s_r[wi][3]);
+            }
+            unsigned o = 0;
+            for (int wi = 0; wi < FSTAT_THREADS / 32; wi++) o |= s_r[wi][4];
+            BlockStat *st = &stats[b];
+            if (wmin <= wmax) {
+                atomicMin(&st->wmin, (unsigned long long)wmin); atomicMax(&st->wmax, (unsigned long long)wmax);
+                atomicMin(&st->qmin, (long long)qmin); atomicMax(&st->qmax, (long long)qmax);
+            }
+            if (o) atomicOr(&st->oob, 1u);
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int FPACK_THREADS = 128;   // 4 warps = the 4 pack groups of a 4096-element tile
+__global__ void __launch_bounds__(FPACK_THREADS, 4)
+k_pack_f32c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats, BatchShape sh,
+            uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err, const int *run_if) {
+    __shared__ __align__(16) unsigned sv[PACK_TILE];   // the tile's packed-to-be values, swizzled by 16-byte chunk
+    if (run_if && *run_if == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
+    for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
+        const int64_t b = find_block(descs, sh, tile, tpb, true);
+        const BlockStat st = stats[b];
+        const int bits = st.bits;
+        if (bits == 0 || bits > 32) continue;   // nothing to write / left to k_pack (not reachable for pixels < 2^31)
+        if (st.out_off + st.nbytes > chain_cap) {
+            if (threadIdx.x == 0) atomicExch(err, 2);
+            continue;
+        }
+        const BlockDesc d = descs[b];
+        const int64_t first = (tile - d.tile0) * PACK_TILE;
+        const int count = (int)(first + PACK_TILE <= d.n ? PACK_TILE : d.n - first);
+        const QuantP qp = quant_params(d);
+        const unsigned mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+        const float *p = (const float *)d.src + first;
+        const int a = (int)(((uintptr_t)p & 15) >> 2);
+        const float4 *base4 = (const float4 *)(p - a);
+        const int nvec = (a + count + 3) >> 2;
+        for (int iv = threadIdx.x; iv < nvec; iv += FPACK_THREADS) {
+            const float4 v4 = __ldcs(base4 + iv);
+            const float x[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int el = 4 * iv + c - a;
+                if (el >= 0 && el < count) {
+                    bool oob = false;
+                    long long raw;
+                    const unsigned q = quant_elem(x[c], qp, oob, &raw);
+                    unsigned v;
+                    if (!st.slow) {   // folded index; bound(q, pmin, pixels) - min (go/group.go:323, :246-247)
+                        const long long qb = (long long)q < st.pmin ? (long long)q + (long long)qp.P : (long long)q;
+                        v = (unsigned)(qb - st.min);
+                    } else {          // the block holds out-of-range indices: the reference's own int64 arithmetic
+                        const long long qb = st.do_bound ? bound1(raw, st.pmin, (long long)qp.P) : raw;
+                        v = (unsigned)((unsigned long long)qb - (unsigned long long)st.min) & mask;
+                    }
+                    const int L = el >> 5, i = el & 31;
+                    sv[(L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3))] = v;
+                }
+            }
+        }
+        for (int el = count + threadIdx.x; el < ((count + 1023) & ~1023); el += FPACK_THREADS) {   // pad the last group
+            const int L = el >> 5, i = el & 31;
+            sv[(L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3))] = 0u;
+        }
+        __syncthreads();
+        const int g = warp;                              // group of 1024 elements
+        if (g * 1024 < count) {
+            unsigned v[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint4 r = *(const uint4 *)&sv[g * 1024 + lane * 32 + ((c ^ (lane & 7)) << 2)];
+                v[4 * c] = r.x; v[4 * c + 1] = r.y; v[4 * c + 2] = r.z; v[4 * c + 3] = r.w;
+            }
+            unsigned *region = sv + g * 1024;
+            const int gcount = count - g * 1024 < 1024 ? count - g * 1024 : 1024;
+            uint8_t *dst = out + (int64_t)d.chain * chain_stride + st.out_off + (((first + g * 1024) * bits) >> 3);
+            switch (bits) {
+#define MNW_CASE(B)                                                                         \
+    case B: {                                                                               \
+        unsigned o[B];                                                                      \
+        pack32<B>(v, o);                                                                    \
+        __syncwarp();                                                                       \
+        _Pragma("unroll") for (int j = 0; j < B; j++) {                                     \
+            const int W = lane * B + j;                                                     \
+            region[W ^ (W >> 5)] = o[j];                                                    \
+        }                                                                                   \
+        __syncwarp();                                                                       \
+        if (gcount == 1024) write_group<B>(dst, region, lane);                              \
+        else write_group_partial(dst, region, (gcount * B + 7) >> 3, lane);                 \
+    } break;
+                MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
+                MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
+                MNW_CASE(17) MNW_CASE(18) MNW_CASE(19) MNW_CASE(20) MNW_CASE(21) MNW_CASE(22) MNW_CASE(23) MNW_CASE(24)
+                MNW_CASE(25) MNW_CASE(26) MNW_CASE(27) MNW_CASE(28) MNW_CASE(29) MNW_CASE(30) MNW_CASE(31) MNW_CASE(32)
+#undef MNW_CASE
+                default: break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Decode of contiguous float32 blocks: one CTA per 4096-element tile of a selected block.  The
+// tile's packed bytes are staged in shared memory with 128-bit loads, every thread then extracts
+// four consecutive values, dequantises them and stores one float4.
+constexpr int FDEC_THREADS = 256;
+__global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
+    __shared__ __align__(16) unsigned spk[DEC_CHUNK + 16];
+    const int64_t tpb = (A.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    const int64_t j = blockIdx.x / tpb;
+    const int64_t tile = blockIdx.x - j * tpb;
+    const int64_t b = A.sel ? A.sel[j] : j;
+    const long long mn = A.mins[b];
+    const int bits = (int)A.bits[b];
+    const FloatParams fp = A.tab[0];
+    const long long P = fp.pixels;
+    const bool periodic = fp.flags & F_PERIODIC;
+    const int64_t first = tile * DEC_CHUNK;
+    const int count = (int)(first + DEC_CHUNK <= A.n ? DEC_CHUNK : A.n - first);
+    const unsigned long long bid = A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b);
+    const unsigned key = jitter_key(A.seed, bid);
+    float *outp = (float *)A.out + j * A.n + first;
+    const unsigned mask = (bits >= 1 && bits <= 32) ? (0xffffffffu >> (32 - bits)) : 0u;
+    // 32-bit path: q = mn + v lies in [0, 2*pixels) (periodic) or [0, 2^23), and float32 holds it exactly
+    const bool fast = bits <= 32 && mn >= 0 && P > 0 && P < (1LL << 23) &&
+                      (periodic ? mn + (long long)mask < 2 * P : mn + (long long)mask < (1LL << 23));
+    if (fast) {
+        unsigned shift0 = 0;
+        if (bits > 0) {
+            const uint8_t *src = A.data + A.offsets[b] + ((first * bits) >> 3);
+            const int a16 = (int)((uintptr_t)src & 15);
+            const uint4 *s16 = (const uint4 *)(src - a16);
+            const int nvec = (a16 + ((count * bits + 7) >> 3) + 15) >> 4;
+            for (int i = threadIdx.x; i < nvec; i += FDEC_THREADS) ((uint4 *)spk)[i] = __ldg(s16 + i);
+            shift0 = 8u * (unsigned)a16;
+        }
+        __syncthreads();
+        const bool vec_ok = (((uintptr_t)outp & 15) == 0);
+        const unsigned Pp = periodic ? (unsigned)P : 0u, mn32 = (unsigned)mn;
+        for (int e4 = threadIdx.x * 4; e4 < count; e4 += FDEC_THREADS * 4) {
+            float o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const unsigned el = (unsigned)(e4 + c);
+                unsigned v = 0;
+                if (bits) {
+                    const unsigned bp = shift0 + el * (unsigned)bits;
+                    v = __funnelshift_r(spk[bp >> 5], spk[(bp >> 5) + 1], bp) & mask;   // Array.Slice, go/bit/bit.go:29-82
+                }
+                unsigned q = mn32 + v;                                                   // go/group.go:262
+                q = min(q, q - Pp);                                                      // bound(q, 0, pixels), :303
+                float t;
+                if (A.jmode == 1) t = __fmaf_rn((float)(jitter_hash_keyed(key, (unsigned)first + el) >> 8), 0x1p-24f, (float)q);
+                else t = __fadd_rn((float)q, 0.5f);
+                o[c] = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);                            // :308
+            }
+            if (vec_ok && e4 + 4 <= count) {
+                __stcs((float4 *)(outp + e4), make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+                for (int c = 0; c < 4; c++) if (e4 + c < count) outp[e4 + c] = o[c];
+            }
+        }
+    } else {   // any width / range: 64-bit arithmetic straight from global memory
+        for (int el = threadIdx.x; el < count; el += FDEC_THREADS) {
+            const int64_t i = first + el;
+            const unsigned long long v = bits ? extract_bits(A.data, A.stream_len, A.offsets[b], i, bits) : 0ULL;
+            long long q = (long long)((unsigned long long)mn + v);
+            if (periodic) q = bound1(q, 0, P);
+            double u = 0.5;
+            if (A.jmode == 1) u = (double)(jitter_hash_keyed(key, (uint32_t)i) >> 8) * 0x1p-24;
+            const float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));
+            outp[el] = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -782,14 +1054,15 @@ static inline unsigned persistent_grid(int64_t units, int per_sm) {
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
-                           int64_t chain_cap, const int *run_if) {
+                           int64_t chain_cap, const int *run_if, bool f32c) {
     if (sh.nblocks == 0) return;
     cudaMemsetAsync(slow_count, 0, sizeof(int), L.stream);
     k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, run_if);
     L.count++;
     if (sh.total_chunks > 0) {
-        if (!run_if) L.begin("k_stats");
-        k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        if (!run_if) L.begin(f32c ? "k_stats_f32c" : "k_stats");
+        if (f32c) k_stats_f32c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        else k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
         if (!run_if) L.end();
         L.count++;
     }
@@ -801,9 +1074,10 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len, run_if);
     L.count++;
     if (sh.total_tiles > 0) {
-        if (!run_if) L.begin("k_pack");
-        k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
-                                                                                   run_if, nullptr, nullptr);
+        if (!run_if) L.begin(f32c ? "k_pack_f32c" : "k_pack");
+        if (f32c) k_pack_f32c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
+        else k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
+                                                                                        run_if, nullptr, nullptr);
         if (!run_if) L.end();
         L.count++;
     }
@@ -858,6 +1132,13 @@ void launch_decode(Launcher &L, const DecodeHost &h) {
     A.sc3 = (int64_t)h.subcells * h.subcells * h.subcells;
     A.out = h.out;
     int64_t cpb = (h.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    if (h.mode == 1 && h.jmode != 2) {   // contiguous float32 blocks: staged, vectorised decode
+        L.begin("k_decode_f32c");
+        k_decode_f32c<<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
+        L.end();
+        L.count++;
+        return;
+    }
     L.begin("k_decode");
     k_decode<<<(unsigned)(h.nsel * cpb), DEC_THREADS, 0, L.stream>>>(A);
     L.end();
