@@ -9,6 +9,8 @@ from .capi import (Context, MinnowError, library_path, load_library, precision_n
                    array_bytes, float_group_pixels, jitter_hash32, FloatDesc, Jitter,
                    JITTER_CENTER, JITTER_HASH, JITTER_STREAM)
 
+from . import minnow, minh, minp, shard  # noqa: F401  (host-side mirrors of the reference's packages)
+
 __all__ = ["Context", "MinnowError", "library_path", "load_library", "precision_needed", "array_bytes",
            "float_group_pixels", "jitter_hash32", "FloatDesc", "Jitter", "JITTER_CENTER", "JITTER_HASH",
            "JITTER_STREAM"]

@@ -1,0 +1,141 @@
+"""Host-side mirror of the reference's halo-catalogue format, package `minh`
+(go/minh/minh.go): same names, argument meaning and on-disk bytes.  Every column of a block
+is its own minnow group with one block (go/minh/minh.go:121-137); Float columns take the
+log10 / clamp pre-transform of processFloatGroup (:141-149) fused into the quantise kernel."""
+import struct
+
+import numpy as np
+
+from . import minnow
+from .capi import FloatDesc, array_bytes
+
+Magic = 0xbaff1ed         # go/minh/minh.go:13-16
+Version = 0
+basicFileType, boundaryFileType = 0, 1                                                       # :18-21
+
+Column = np.dtype([("Type", "<i8"), ("Log", "<i4"), ("Low", "<f4"), ("High", "<f4"), ("Dx", "<f4"),
+                   ("Buffer", "S232")])                                                    # :50-55
+assert Column.itemsize == 256
+
+
+def columns(specs):
+    """specs: (Type[, Log, Low, High, Dx]) per column -> Column array"""
+    a = np.zeros(len(specs), Column)
+    for i, c in enumerate(specs):
+        c = tuple(c) + (0,) * (5 - len(c))
+        a["Type"][i], a["Log"][i], a["Low"][i], a["High"][i], a["Dx"][i] = c
+    return a
+
+
+class Writer:
+    def __init__(self, fname, ctx, file_type=basicFileType):                                 # Create / create, :71-86
+        self.ctx = ctx
+        self.f = minnow.Create(fname, ctx)
+        self.f.Header(struct.pack("<qqq", Magic, Version, file_type))
+        self.blocks, self.block_sizes = 0, []
+        self.l = self.boundary = np.float32(0)
+        self.cells = 0
+
+    def Header(self, names, text, cols):                                                     # :88-93
+        self.cols = cols if isinstance(cols, np.ndarray) else columns(cols)
+        self.f.Header(text.encode("ascii"))
+        self.f.Header("$".join(names).encode("ascii"))
+        self.f.Header(self.cols.tobytes())
+
+    def Geometry(self, L, boundary, cells):                                                  # :95-97
+        self.l, self.boundary, self.cells = np.float32(L), np.float32(boundary), int(cells)
+
+    def Block(self, cols):                                                                   # :99-139
+        if len(cols) != len(self.cols):
+            raise ValueError("Expected %d columns, got %d." % (len(self.cols), len(cols)))
+        N = len(cols[0])
+        for i, x in enumerate(cols):
+            if len(x) != N:
+                raise ValueError("len(cols[%d]) = %d instead of %d" % (i, len(x), N))
+        self.block_sizes.append(N)
+        self.blocks += 1
+        w = self.f
+        for x, col in zip(cols, self.cols):
+            t = int(col["Type"])
+            if t in minnow._FIXED:
+                w.FixedSizeGroup(t, N)
+                w.Data(np.asarray(x, minnow._FIXED[t]))
+            elif t == minnow.IntGroup:
+                w.IntGroup(N)
+                w.Data(np.asarray(x, np.int64))
+            elif t == minnow.FloatGroup:
+                w.FloatGroup(N, (col["Low"], col["High"]), col["Dx"])
+                w.curr.log10 = 1 if col["Log"] != 0 else 0     # processFloatGroup runs inside the quantise kernel
+                w.curr.clamp = 1
+                w.Data(np.asarray(x, np.float32))
+            else:
+                raise ValueError("Unrecognized group type, %d." % t)
+
+    def Close(self):                                                                         # :151-156
+        self.f.Header(struct.pack("<ffq", self.l, self.boundary, self.cells))
+        self.f.Header(struct.pack("<q", self.blocks))
+        self.f.Header(np.asarray(self.block_sizes, "<i8").tobytes())
+        self.f.Close()
+
+
+def Create(fname, ctx):
+    return Writer(fname, ctx)
+
+
+class Reader:
+    def __init__(self, fname, ctx, jitter=None):                                             # Open, :184-226
+        self.f = minnow.Open(fname, ctx, jitter)
+        magic, version, self.file_type = struct.unpack("<qqq", self.f.Header(0))
+        if magic != Magic:
+            raise ValueError("not a minh file. Expected magic number %d, but got %d." % (Magic, magic))
+        if version < Version:
+            raise ValueError("written with minh version %d, but reader is version %d." % (version, Version))
+        self.Text = self.f.Header(1).decode("ascii")
+        self.Names = self.f.Header(2).decode("ascii").split("$")
+        self.Columns = self.f.Header(3, Column)
+        self.L, self.Boundary, self.Cells = struct.unpack("<ffq", self.f.Header(4))
+        self.Blocks = struct.unpack("<q", self.f.Header(5))[0]
+        self.BlockLengths = [int(v) for v in self.f.Header(6, "<i8")]
+        self.Length = sum(self.BlockLengths)
+
+    def _index(self, name, b):                                                               # :267-283
+        if name not in self.Names:
+            raise KeyError("Name %s not in Reader.Names = %s." % (name, self.Names))
+        c = self.Names.index(name)
+        return c, (c + b * len(self.Columns) if self.file_type == basicFileType else c * self.Blocks + b)
+
+    def IntBlock(self, b, names):                                                            # :267-294
+        out = {}
+        for name in names:
+            c, idx = self._index(name, b)
+            if self.f.DataType(idx) == minnow.FloatGroup or self.f.DataType(idx) in (minnow.Float32Group, minnow.Float64Group):
+                raise TypeError("Column '%s' does not hold integers" % name)
+            out[name] = self.f.Data(idx)
+        return out
+
+    def FloatBlock(self, b, names):                                                          # :296-323
+        out = {}
+        for name in names:
+            c, idx = self._index(name, b)
+            x = self.f.Data(idx)
+            if x.dtype != np.float32:
+                raise TypeError("Column '%s' does not hold float32" % name)
+            if self.Columns[c]["Log"] != 0:                   # float32(math.Pow(10, float64(x))), :315-319
+                x = np.power(10.0, x.astype(np.float64)).astype(np.float32)
+            out[name] = x
+        return out
+
+    def Ints(self, names):                                                                   # :228-240
+        parts = [self.IntBlock(b, names) for b in range(self.Blocks)]
+        return {n: np.concatenate([p[n] for p in parts]) if parts else np.zeros(0, np.int64) for n in names}
+
+    def Floats(self, names):                                                                 # :242-254
+        parts = [self.FloatBlock(b, names) for b in range(self.Blocks)]
+        return {n: np.concatenate([p[n] for p in parts]) if parts else np.zeros(0, np.float32) for n in names}
+
+    def Close(self):
+        self.f.Close()
+
+
+def Open(fname, ctx, jitter=None):
+    return Reader(fname, ctx, jitter)
