@@ -119,6 +119,17 @@ MNW_API int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, con
                                    int64_t *mins, int64_t *bits, int64_t *offsets,
                                    uint8_t *out, int64_t out_cap, int64_t *out_len);
 
+/* Gathered blocks: block b holds col[idx[i]] for i in [starts[b], starts[b+1]) -- the per-cell
+ * column gather of BoundaryWriter.Column / boundaryColumn (go/minh/boundary.go:184-256) fused with
+ * the group encode.  col has ncol elements; every idx must lie in [0, ncol). */
+MNW_API int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, const int64_t *idx,
+                                        int64_t nblocks, const int64_t *starts, int64_t *mins, int64_t *bits,
+                                        int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len);
+MNW_API int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, const float *col, int64_t ncol,
+                                          const int64_t *idx, int64_t nblocks, const int64_t *starts,
+                                          int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                                          int64_t out_cap, int64_t *out_len);
+
 /* Decode nsel blocks of one group.  data/offsets/mins/bits describe the whole
  * group (nblocks entries; offsets as produced above); sel lists the block ids
  * to decode (NULL = blocks 0..nsel-1); block sel[j] lands at out + j*n.

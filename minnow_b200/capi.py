@@ -58,6 +58,8 @@ SIGNATURES = {
     "mnw_launch_count": (_i64, [_p]),
     "mnw_selftest_fastdiv": (_int, [_p, _FD, C.c_uint32, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "mnw_minp_encode_vectors": (_int, [_p, _p, _i64, _i64, _int, _f32, _f32, _FD, _p, _p, _p, _p, _i64, _p]),
+    "mnw_encode_int_group_gather": (_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_encode_float_group_gather": (_int, [_p, _FD, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
     "mnw_pack": (_int, [_p, _int, _p, _i64, _p]),
@@ -247,6 +249,26 @@ class Context:
         if starts is not None:
             nblocks, n = len(starts) - 1, 0
         return self._encode_group(self.lib.mnw_encode_float_group, (C.byref(desc),), x, 4, n, nblocks, starts)
+
+    def encode_group_gather(self, col, idx, starts, desc=None):
+        """Blocks gathered from one column (BoundaryWriter.Column, go/minh/boundary.go:184-225):
+        block b = col[idx[starts[b]:starts[b+1]]]; desc = None for an int64 column.
+        -> (mins, bits, offsets, data)"""
+        is_int = desc is None
+        col = _np(col, np.int64 if is_int else np.float32)
+        idx, starts = _np(idx, np.int64), _np(starts, np.int64)
+        nb = len(starts) - 1
+        mins, bits, offs = (np.zeros(nb, np.int64) for _ in range(3))
+        out = np.zeros(8 * len(idx) + 64, np.uint8)
+        ln = _i64(0)
+        if is_int:
+            rc = self.lib.mnw_encode_int_group_gather(self.h, _ptr(col), len(col), _ptr(idx), nb, _ptr(starts), _ptr(mins),
+                                                      _ptr(bits), _ptr(offs), _ptr(out), len(out), C.byref(ln))
+        else:
+            rc = self.lib.mnw_encode_float_group_gather(self.h, C.byref(desc), _ptr(col), len(col), _ptr(idx), nb, _ptr(starts),
+                                                        _ptr(mins), _ptr(bits), _ptr(offs), _ptr(out), len(out), C.byref(ln))
+        self._check(rc)
+        return mins, bits, offs, out[:ln.value].copy()
 
     def decode_int_blocks(self, data, offsets, mins, bits, n, sel=None):
         """intGroup.readData per selected block (go/group.go:257-263)"""

@@ -133,7 +133,7 @@ int check_flags(mnw_ctx *ctx) {
 int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *x, int64_t n,
                      int64_t nblocks, const int64_t *d_starts, const int64_t *d_tile0, const int64_t *d_chunk0,
                      int64_t total_tiles, int64_t total_chunks, int64_t *mins, int64_t *bits, int64_t *offsets,
-                     uint8_t *out, int64_t out_cap, int64_t *out_len) {
+                     uint8_t *out, int64_t out_cap, int64_t *out_len, const int64_t *d_idx = nullptr) {
     if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
     FloatParamsHost fp = {};
     if (kind == KIND_F32) {
@@ -162,9 +162,9 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
         return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
 
     ctx->last_path = 0;
-    launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks);
+    launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks, d_idx);
     // contiguous float32 blocks of a periodic group with pixels < 2^31: the vectorised two-pass kernels
-    const bool f32c = !ctx->force_generic && kind == KIND_F32 && (fp.flags & F_PERIODIC) && fp.pixels >= 1 &&
+    const bool f32c = !ctx->force_generic && !d_idx && kind == KIND_F32 && (fp.flags & F_PERIODIC) && fp.pixels >= 1 &&
                       fp.pixels < (1LL << 31);
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
@@ -176,16 +176,26 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
 // Host-pointer group encode: stage in, run, stage out.
 int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *x, int64_t n,
                       int64_t nblocks, const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets,
-                      uint8_t *out, int64_t out_cap, int64_t *out_len) {
+                      uint8_t *out, int64_t out_cap, int64_t *out_len, const int64_t *idx = nullptr, int64_t ncol = 0) {
     if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
     const size_t esz = kind == KIND_I64 ? 8 : 4;
     int64_t total = starts ? starts[nblocks] - starts[0] : n * nblocks;
     if (starts && starts[0] != 0) return fail(ctx, MNW_ERR_ARG, "starts[0] must be 0");
-    CU(ctx->in.reserve(esz * (size_t)total + 16));
+    const int64_t nsrc = idx ? ncol : total;   // elements to upload: the whole column for a gather
+    const int64_t *d_idx = nullptr;
+    if (idx) {
+        if (!starts) return fail(ctx, MNW_ERR_ARG, "a gather needs starts[]");
+        for (int64_t i = 0; i < total; i++)
+            if (idx[i] < 0 || idx[i] >= ncol) return fail(ctx, MNW_ERR_ARG, "gather index %lld outside the column of %lld", (long long)idx[i], (long long)ncol);
+        CU(ctx->ustream.reserve(8 * (size_t)total + 16));
+        if (total > 0) CU(cudaMemcpyAsync(ctx->ustream.p, idx, 8 * (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
+        d_idx = ctx->ustream.as<int64_t>();
+    }
+    CU(ctx->in.reserve(esz * (size_t)nsrc + 16));
     CU(ctx->out.reserve(8 * (size_t)total + 64));
     int rc = reserve_batch(ctx, nblocks, 1);
     if (rc) return rc;
-    if (total > 0) CU(cudaMemcpyAsync(ctx->in.p, x, esz * (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
+    if (nsrc > 0) CU(cudaMemcpyAsync(ctx->in.p, x, esz * (size_t)nsrc, cudaMemcpyHostToDevice, ctx->L.stream));
 
     const int64_t *d_starts = nullptr, *d_tile0 = nullptr, *d_chunk0 = nullptr;
     int64_t total_tiles = 0, total_chunks = 0;
@@ -211,7 +221,7 @@ int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const 
     int64_t *d_meta = ctx->meta.as<int64_t>();
     int64_t *d_mins = d_meta, *d_bits = d_meta + nblocks, *d_offs = d_meta + 2 * nblocks, *d_len = d_meta + 3 * nblocks;
     rc = encode_group_dev(ctx, kind, desc, ctx->in.p, n, nblocks, d_starts, d_tile0, d_chunk0, total_tiles,
-                          total_chunks, d_mins, d_bits, d_offs, ctx->out.as<uint8_t>(), (int64_t)ctx->out.cap, d_len);
+                          total_chunks, d_mins, d_bits, d_offs, ctx->out.as<uint8_t>(), (int64_t)ctx->out.cap, d_len, d_idx);
     if (rc) return rc;
     std::vector<int64_t> h_meta(3 * (size_t)nblocks + 1);
     CU(cudaMemcpyAsync(h_meta.data(), d_meta, h_meta.size() * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
@@ -445,6 +455,22 @@ int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
     return encode_group_host(ctx, KIND_F32, desc, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, const int64_t *idx, int64_t nblocks,
+                                const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                                int64_t out_cap, int64_t *out_len) {
+    if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
+    return encode_group_host(ctx, KIND_I64, nullptr, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
+}
+
+int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, const float *col, int64_t ncol,
+                                  const int64_t *idx, int64_t nblocks, const int64_t *starts, int64_t *mins,
+                                  int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    int rc = check_desc(ctx, desc);
+    if (rc) return rc;
+    if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
+    return encode_group_host(ctx, KIND_F32, desc, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
 }
 
 int mnw_decode_int_blocks(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,

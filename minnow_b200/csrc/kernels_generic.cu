@@ -83,19 +83,27 @@ __device__ __forceinline__ unsigned long long warp_max_ull(unsigned long long v)
 // ---------------------------------------------------------------------------
 // descriptor builders
 // ---------------------------------------------------------------------------
+// With `idx` given the block is a GATHER: element i of block b is src[idx[first + i]]
+// (BoundaryWriter.Column, go/minh/boundary.go:184-225).
 __global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                                const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                               FloatParams fp, int64_t blocks_per_chain) {
+                               FloatParams fp, int64_t blocks_per_chain, const int64_t *idx) {
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= nb) return;
     BlockDesc d = {};
     int64_t first = starts ? starts[b] : b * n;
     int64_t cnt = starts ? starts[b + 1] - starts[b] : n;
-    d.src = kind == KIND_I64 ? (const void *)((const long long *)src + first)
-                             : (const void *)((const float *)src + first);
+    if (idx) {
+        d.src = src;
+        d.idx = idx + first;
+        d.access = ACC_GATHER;
+    } else {
+        d.src = kind == KIND_I64 ? (const void *)((const long long *)src + first)
+                                 : (const void *)((const float *)src + first);
+        d.access = ACC_CONTIG;
+    }
     d.n = cnt;
     d.kind = kind;
-    d.access = ACC_CONTIG;
     d.flags = fp.flags;
     d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
     d.chain = (int32_t)(b / blocks_per_chain);
@@ -1012,9 +1020,9 @@ static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n +
 
 void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                         const FloatParamsHost &fp, int64_t blocks_per_chain) {
+                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx) {
     if (nb == 0) return;
-    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, fp, blocks_per_chain);
+    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, fp, blocks_per_chain, idx);
     L.count++;
 }
 

@@ -56,7 +56,7 @@ struct DecodeHost {
 // kernels_generic.cu
 void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                         const FloatParamsHost &fp, int64_t blocks_per_chain);
+                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx = nullptr);
 void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
                        int32_t subcells, const FloatParams *tab, int tab_per_file);
 // bounds() of minp.Writer.Vectors (go/minp/minp.go:291-300): keys[f*6 + k] = min, [f*6 + 3 + k] = max,

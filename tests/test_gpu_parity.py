@@ -301,3 +301,23 @@ def test_minp_vectors(anyctx, orc, nside, subcells, periodic):
             assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
         if all(d.pixels > 0 for d in descs) and not periodic:    # vectorsEq, go/minp/minp_test.go:116-126
             assert np.all(np.abs(got - vec) <= dx * 1.001)
+
+
+# ---- gathered blocks (BoundaryWriter.Column, go/minh/boundary.go:184-225) ------------------------
+def test_group_gather_matches_encode_of_gathered_copy(ctx, orc):
+    rng = np.random.default_rng(44)
+    ncol = 20000
+    lens = [0, 5, 4097, 1, 300, 9000]
+    starts = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = rng.integers(0, ncol, starts[-1]).astype(np.int64)          # ghost layers repeat halos: duplicates allowed
+    ids = rng.integers(-10 ** 15, 10 ** 15, ncol).astype(np.int64)
+    pos = rng.uniform(0, 125, ncol).astype(np.float32)
+    mins, bits, offs, data = ctx.encode_group_gather(ids, idx, starts)
+    om, ob, oo, od = oracle_int_group(orc, ids[idx], starts)
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo) and data.tobytes() == od.tobytes()
+    d = mb.FloatDesc.make(0, 125, 125000)
+    mins, bits, offs, data = ctx.encode_group_gather(pos, idx, starts, d)
+    om, ob, oo, od = oracle_float_group(orc, pos[idx], starts, 0, 125, 125000)
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo) and data.tobytes() == od.tobytes()
+    with pytest.raises(mb.MinnowError):
+        ctx.encode_group_gather(ids, np.array([0, ncol], np.int64), np.array([0, 2], np.int64))
