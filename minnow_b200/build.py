@@ -30,7 +30,8 @@ def build_library(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + sources()
+    extra = ["-D" + d for d in os.environ.get("MNW_DEFINES", "").split() if d]   # e.g. MNW_DEFINES=MNW_PIPE_DBG
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + sources()
     subprocess.check_call(cmd)
     return LIB
 

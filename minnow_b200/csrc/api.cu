@@ -589,7 +589,8 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         cudaError_t e;
         if (use_cluster) {
             e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
-                                  ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride);
+                                  ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
+                                  pipe_vec3_supported(fp.data(), ndesc));
         } else {
             CU(ctx->flat_ws.reserve(flat_work_bytes(nfiles * sc3)));
             CU(ctx->flat_scratch.reserve(flat_scratch_bytes()));

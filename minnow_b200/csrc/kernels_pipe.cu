@@ -1,0 +1,63 @@
+// kernels_pipe.cu -- k_pipe_vec3: the warp-specialised, software-pipelined minp encode for 64^3
+// sub-cells (see pipe_vec3.cuh), and its launcher.
+#include <climits>
+
+#include "fused_detail.cuh"
+
+namespace mnw {
+
+#include "pipe_vec3.cuh"
+
+cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
+    auto kern = k_pipe_vec3;
+    const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
+    static bool configured = false;
+    static int max_clusters = 0;
+    cudaError_t e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PIPE_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(PIPE_NT); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!configured) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cfg.gridDim = dim3(PIPE_CS);
+        e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3: %d co-resident clusters, %zu B dynamic smem\n", max_clusters, smem);
+        configured = true;
+    }
+    const long long clusters = A.nunits < max_clusters ? A.nunits : max_clusters;
+    cfg.gridDim = dim3((unsigned)(clusters * PIPE_CS));
+    L.begin("k_pipe_vec3");
+    e = cudaLaunchKernelEx(&cfg, kern, A);
+    L.end();
+    L.count++;
+#ifdef MNW_PIPE_DBG
+    if (getenv("MNW_PIPE_DBG")) {
+        cudaDeviceSynchronize();
+        static unsigned long long h[32 * 64 * 8];
+        cudaMemcpyFromSymbol(h, g_pipe_dbg, sizeof(h));
+        for (int c = 0; c < 15; c += 7)
+            for (int it = 0; it < 40; it++) {
+                const unsigned long long *r = h + (c * 64 + it) * 8, t0 = h[(c * 64) * 8];
+                fprintf(stderr, "c%d it%2d top %7.1f | load %5.1f | stats +%5.1f | fin +%5.1f | lb0 +%5.1f lb1 +%5.1f lb2 +%5.1f | packed +%5.1f\n", c, it,
+                        (r[0] - t0) / 1e3, (r[1] - r[0]) / 1e3, (r[2] - r[1]) / 1e3, (r[3] - r[2]) / 1e3, (r[4] - r[3]) / 1e3,
+                        (r[5] - r[4]) / 1e3, (r[6] - r[5]) / 1e3, (r[7] - r[6]) / 1e3);
+            }
+    }
+#endif
+    return e;
+}
+
+bool pipe_vec3_supported(const FloatParamsHost *fp, int64_t nparams) {
+    for (int64_t i = 0; i < nparams; i++)
+        if (fp[i].pixels > (1LL << 22)) return false;   // q + rotation must stay below 2^23 (float-exact floor)
+    return true;
+}
+
+
+}  // namespace mnw

@@ -236,3 +236,91 @@ def test_minp_encode_vectors_single_upload(ctx, orc, periodic):
     for k in range(3):
         want = b"".join(packed[t * stride:t * stride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
         assert streams[k].tobytes() == want
+
+
+# ---- 64^3 sub-cells: the warp-specialised k_pipe_vec3 path -------------------------------------
+def test_pipe_edges_64(ctx, orc):
+    """64^3 blocks over several units per file: 0-bit blocks, index == pixels folding (thread-local
+    exact redo), a wrap-around arc and a first element at index == pixels (generic redo)"""
+    rng = np.random.default_rng(64)
+    L, nfile, subcells, dx = 1000.0, 128, 2, 0.005
+    px = mb.float_group_pixels(0.0, L, dx)
+    vec = lagrangian(rng, nfile, L, 2.0)
+    vec[:, 1] = 321.125                                   # y: 0 bits everywhere
+    top = np.nextafter(np.float32(L), np.float32(0))      # quantises to index == pixels
+    vec[5::9973, 2] = top
+    vec[11::8191, 2] = 0.0
+    mins, bits = check(ctx, orc, vec, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, L)
+    sc3 = subcells ** 3
+    assert (bits[sc3:2 * sc3] == 0).all()
+    vec2 = vec.copy()
+    vec2[0, 2] = top
+    check(ctx, orc, vec2, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, L)
+
+
+@pytest.mark.parametrize("bad", [np.nan, -np.inf, -3.0, 2500.0])
+def test_pipe_bad_values_64(ctx, orc, bad):
+    rng = np.random.default_rng(65)
+    L, nfile, subcells, dx = 1000.0, 64, 1, 0.005
+    px = mb.float_group_pixels(0.0, L, dx)
+    vec = lagrangian(rng, nfile, L, 2.0)
+    vec[77777, 0] = bad
+    vec[200000, 2] = bad
+    descs = [mb.FloatDesc.make(0.0, L, px) for _ in range(3)]
+    mins, bits, offs, streams = ctx.encode_vec3_subcells(descs, vec, nfile, subcells)
+    omins, obits, onbytes, packed, stride, total = orc.bench_minp_encode(vec, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3)
+    assert np.array_equal(mins, omins) and np.array_equal(bits, obits)
+    for k in range(3):
+        assert streams[k].tobytes() == packed[k * stride:k * stride + onbytes[k]].tobytes()
+
+
+@pytest.mark.parametrize("dx,sigma", [(0.05, 3.0), (0.0005, 0.5), (2.0, 30.0), (30.0, 60.0)])
+def test_pipe_bit_widths_64(ctx, orc, dx, sigma):
+    """narrow and wide arcs, > 16 bit blocks (repack list) and tiny pixel counts on 64^3 blocks"""
+    rng = np.random.default_rng(int(dx * 1e4) + 66)
+    L, nfile, subcells = 100.0, 128, 2
+    vec = lagrangian(rng, nfile, L, sigma)
+    px = mb.float_group_pixels(0.0, L, dx)
+    mins, bits = check(ctx, orc, vec, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, L)
+    if dx == 0.0005:
+        assert bits.max() > 16
+
+
+def test_pipe_many_files_dev_64(ctx, orc):
+    """device entry point, 3 files x 8 units of 64^3 with per-file limits: ticket order, look-back chains
+    across clusters and units, non-periodic wide blocks"""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(67)
+    nfile, subcells, nfiles = 128, 2, 3
+    sc3, n3 = subcells ** 3, nfile ** 3
+    vecs = [(150.0 * (f + 1) * rng.standard_normal((n3, 3))).astype(np.float32) for f in range(nfiles)]
+    dev = torch.device("cuda:0")
+    aos = torch.from_numpy(np.concatenate(vecs)).to(dev)
+    lo, hi = ctx.vec3_limits(aos, nfiles, dev=True)
+    descs, pxs = [], []
+    for f in range(nfiles):
+        for k in range(3):
+            px = mb.float_group_pixels(float(lo[f, k]), float(hi[f, k]), 1.0)
+            descs.append(mb.FloatDesc.make(lo[f, k], hi[f, k], px))
+            pxs.append(px)
+    nb = nfiles * 3 * sc3
+    stride = 4 * (nfile // subcells) ** 3 * sc3
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = torch.zeros(nb, **i64), torch.zeros(nb, **i64), torch.zeros(nb, **i64)
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    ctx.encode_vec3_subcells_dev(descs, aos, nfile, subcells, nfiles, mins, bits, offs, out, stride, out_len)
+    torch.cuda.synchronize()
+    mins, bits, offs, out_len, out = (t.cpu().numpy() for t in (mins, bits, offs, out_len, out))
+    for f in range(nfiles):
+        lo3 = [d.low for d in descs[3 * f:3 * f + 3]]
+        hi3 = [d.high for d in descs[3 * f:3 * f + 3]]
+        om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(vecs[f], nfile, subcells, lo3, hi3, pxs[3 * f:3 * f + 3])
+        sl = slice(f * 3 * sc3, (f + 1) * 3 * sc3)
+        assert np.array_equal(mins[sl], om) and np.array_equal(bits[sl], ob)
+        for k in range(3):
+            want = b"".join(packed[t * ostride:t * ostride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
+            assert out_len[3 * f + k] == len(want)
+            got = out[(3 * f + k) * stride:(3 * f + k) * stride + len(want)].tobytes()
+            assert got == want
+            assert np.array_equal(offs[sl][k * sc3:(k + 1) * sc3], np.concatenate([[0], np.cumsum(onb[k * sc3:(k + 1) * sc3])[:-1]]))
