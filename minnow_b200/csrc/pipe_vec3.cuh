@@ -41,11 +41,16 @@ __device__ __forceinline__ void pipe_dbg(int cluster, int it, int ev) {
 #define PIPE_DBG(it, ev) do { } while (0)
 #endif
 
+#ifndef MNW_PIPE_EXP
+#define MNW_PIPE_EXP 0
+#endif
+
 namespace {
 
 constexpr unsigned FMAGIC = 0x4B000000u;   // float bits of 2^23
 constexpr int PIPE_LW = 8, PIPE_PW = 7, PIPE_NT = 32 * (PIPE_LW + PIPE_PW + 1);   // + 1 scanner warp
-constexpr int PIPE_TBUF = 560;   // words of one packer warp's transposition buffer (33 * 16 + 1, rounded up)
+constexpr int PIPE_TBUF = 560;
+constexpr int PIPE_LREGS = 152, PIPE_PREGS = 104;   // registers per thread of the loader / packer warpgroups (2 x 128 in all)   // words of one packer warp's transposition buffer (33 * 16 + 1, rounded up)
 constexpr int PIPE_CS = 8, PIPE_CHUNK = 32768, PIPE_STEPS = 32, PIPE_USLOTS = 8;
 
 struct PipePar {   // per-axis parameters of one unit (written once per unit, read by all threads)
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     unsigned *tbuf = (unsigned *)(smem_raw + 6 * CHUNK);  // [PIPE_PW][PIPE_TBUF] transposition buffers
     __shared__ __align__(8) unsigned long long bar_unit[PIPE_USLOTS];   // 1 arrival: rank 0 posted s_unit[slot]
     __shared__ __align__(8) unsigned long long bar_stats[2];            // CS arrivals: every CTA posted its XStat
-    __shared__ __align__(8) unsigned long long bar_empty[PIPE_STEPS];   // 3 arrivals: slot (16 rows) read by the packers
+    __shared__ __align__(8) unsigned long long bar_empty[PIPE_STEPS / 2];   // 6 arrivals: two slots (32 rows) read by the packers
     __shared__ long long s_unit[PIPE_USLOTS];
     __shared__ __align__(16) PipePar s_par[2][3];
     __shared__ __align__(8) unsigned long long s_pp[2][3][3];   // [slot][low, rcp, ndx][pair (x,y) (z,x) (y,z)]
@@ -287,8 +292,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     __shared__ unsigned s_red[PIPE_LW][13];
     __shared__ unsigned s_cta[13];
     __shared__ Fin s_fin[3];
-    __shared__ __align__(8) unsigned long long bar_off[2][3];           // 1 arrival: rank 0 posted s_off[slot][axis]
-    __shared__ long long s_off[2][3];   // byte offset of the unit's blocks (-1: does not fit the output)
+    __shared__ __align__(8) unsigned long long bar_off[3][3];           // 1 arrival: rank 0 posted s_off[slot][axis]
+    __shared__ long long s_off[3][3];   // byte offset of the unit's blocks
     __shared__ int s_gctr;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,8 +343,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     if (tid == 0) {
         for (int i = 0; i < PIPE_USLOTS; i++) mbar_init(&bar_unit[i], 1);
         mbar_init(&bar_stats[0], CS); mbar_init(&bar_stats[1], CS);
-        for (int i = 0; i < PIPE_STEPS; i++) mbar_init(&bar_empty[i], 3);
-        for (int i = 0; i < 6; i++) mbar_init(&bar_off[0][0] + i, 1);
+        for (int i = 0; i < PIPE_STEPS / 2; i++) mbar_init(&bar_empty[i], 6);
+        for (int i = 0; i < 9; i++) mbar_init(&bar_off[0][0] + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all<CS>();
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 
     if (warp < PIPE_LW) {
         // =========================== loaders ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_LREGS));
         // lane geometry: step t covers rows 16 t .. 16 t + 15 of the CTA's 512; warp w rows 2 w, 2 w + 1
         // of those, lane l particles 4 (l & 15) .. + 3 of row (l >> 4)
         const unsigned toff = rank * 8u * G.plane4 + (unsigned)(2 * warp + (lane >> 4)) * G.row4 + 3u * (unsigned)(lane & 15);
@@ -363,10 +369,35 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         const unsigned sbyte = (unsigned)((((e_thread >> 3) ^ ((e_thread >> 6) & 7)) << 4) + ((lane & 1) << 3));
         auto step_off = [&](int t) { return (unsigned)(t >> 2) * G.plane4 + (unsigned)(t & 3) * 16u * G.row4; };
 
+        const size_t inc_rows = (size_t)16u * G.row4, inc_plane = (size_t)G.plane4 - (size_t)48u * G.row4;   // step t -> t + 1
         float4 buf[4][3];
+        const float4 *pr = nullptr;   // where the next refill comes from
         long long unit = s_unit[0];
         long long f; unsigned sc;
         const float4 *cur = nullptr;
+        // per-axis parameters as pairs in the order the 12 floats of a step arrive: (x,y) (z,x) (y,z) (x,y) (z,x) (y,z)
+        unsigned long long lowp[3], rcpp[3], ndxp[3];
+        auto load_pairs = [&](int slot) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                lowp[j] = ld_shared_u64_pinned(&s_pp[slot][0][j]);
+                rcpp[j] = ld_shared_u64_pinned(&s_pp[slot][1][j]);
+                ndxp[j] = ld_shared_u64_pinned(&s_pp[slot][2][j]);
+            }
+        };
+        // the float half of a step: raw bits of RM(quotient + 2^23) of the 12 floats in buffer u -> bb[particle][axis]
+        auto quant12 = [&](int u, unsigned (&bb)[4][3]) {
+            const float4 v0 = buf[u][0], v1 = buf[u][1], v2 = buf[u][2];
+            const unsigned long long r0 = quantize2(f2_pack(v0.x, v0.y), lowp[0], rcpp[0], ndxp[0]);
+            const unsigned long long r1 = quantize2(f2_pack(v0.z, v0.w), lowp[1], rcpp[1], ndxp[1]);
+            const unsigned long long r2 = quantize2(f2_pack(v1.x, v1.y), lowp[2], rcpp[2], ndxp[2]);
+            const unsigned long long r3 = quantize2(f2_pack(v1.z, v1.w), lowp[0], rcpp[0], ndxp[0]);
+            const unsigned long long r4 = quantize2(f2_pack(v2.x, v2.y), lowp[1], rcpp[1], ndxp[1]);
+            const unsigned long long r5 = quantize2(f2_pack(v2.z, v2.w), lowp[2], rcpp[2], ndxp[2]);
+            f2_bits(r0, bb[0][0], bb[0][1]); f2_bits(r1, bb[0][2], bb[1][0]); f2_bits(r2, bb[1][1], bb[1][2]);
+            f2_bits(r3, bb[2][0], bb[2][1]); f2_bits(r4, bb[2][2], bb[3][0]); f2_bits(r5, bb[3][1], bb[3][2]);
+        };
+        unsigned bc[4][3];   // float half of the step whose integer half comes next (software pipeline, one step deep)
         if (unit < A.nunits) {
             cur = G.origin(A.aos, unit, f, sc) + toff;
 #pragma unroll
@@ -374,23 +405,21 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 const float4 *p = cur + step_off(u);
                 buf[u][0] = ld_stream_pinned(p); buf[u][1] = ld_stream_pinned(p + 1); buf[u][2] = ld_stream_pinned(p + 2);
             }
+            pr = cur + step_off(4);
+            load_pairs(0);
+            quant12(0, bc);
+            buf[0][0] = ld_stream_pinned(pr); buf[0][1] = ld_stream_pinned(pr + 1); buf[0][2] = ld_stream_pinned(pr + 2);
+            pr += inc_rows;
         }
         for (int it = 0; unit < A.nunits; it++) {
             if (warp == 0) PIPE_DBG(it, 0);
             long long next = A.nunits;
             const float4 *nxt = nullptr;
-
-            // per-axis parameters as pairs in the order the 12 floats of a step arrive:
-            // (x,y) (z,x) (y,z) (x,y) (z,x) (y,z)
             const PipePar *par = s_par[it & 1];
-            unsigned long long lowp[3], rcpp[3], ndxp[3];
             unsigned Cm[3], nP[3];
             bool fast = true;
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                lowp[j] = ld_shared_u64_pinned(&s_pp[it & 1][0][j]);
-                rcpp[j] = ld_shared_u64_pinned(&s_pp[it & 1][1][j]);
-                ndxp[j] = ld_shared_u64_pinned(&s_pp[it & 1][2][j]);
                 Cm[j] = par[j].Cm; nP[j] = 0u - par[j].P;
                 fast = fast && par[j].fast;
             }
@@ -399,7 +428,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 
 #pragma unroll 1
             for (int t0 = 0; t0 < PIPE_STEPS; t0 += 4) {
-                if (t0 == 16) {   // the next unit: its origin, its parameters, its rows towards L2
+                if (t0 == 16) {   // the next unit: its origin and its parameters
                     mbar_wait_cluster(&bar_unit[(it + 1) & UM], ((it + 1) / PIPE_USLOTS) & 1);
                     next = s_unit[(it + 1) & UM];
                     if (next < A.nunits) {
@@ -414,54 +443,52 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int t = t0 + u;
-                    unsigned b[4][3];   // [particle][axis]
-                    const float4 v0 = buf[u][0], v1 = buf[u][1], v2 = buf[u][2];
-                    // pull the rows of step t + 8 (of this unit, or of the next one) towards L2: lanes 0 and 16
-                    // sit at the start of the warp's two rows
-                    if (A.prefetch && (lane & 15) == 0) {
-                        const float4 *pp = ((t0 + 8 < PIPE_STEPS) ? cur + step_off(t + 8) : nxt + step_off(t + 8 - PIPE_STEPS));
-                        if (t0 + 8 < PIPE_STEPS || nxt)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(64 * 12) : "memory");
-                    }
-                    // refill this buffer: step t + 4 of this unit, or the first steps of the next one
-                    {
-                        const float4 *p = (t0 + 4 < PIPE_STEPS) ? cur + step_off(t + 4) : nxt + step_off(u);
-                        if (t0 + 4 < PIPE_STEPS || nxt) {
-                            buf[u][0] = ld_stream_pinned(p); buf[u][1] = ld_stream_pinned(p + 1); buf[u][2] = ld_stream_pinned(p + 2);
+                for (int u2 = 0; u2 < 4; u2 += 2) {
+                    uint2 pk[2][3];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int u = u2 + h, un = (u + 1) & 3;
+                        // ---- float half of step t + 1 (buffer un), then that buffer goes back to step t + 5; the last
+                        // one of a unit is step 0 of the NEXT unit and takes that unit's parameters ----
+                        unsigned bn[4][3];
+                        if (u == 3 && t0 == PIPE_STEPS - 4) {
+                            bar_named(4, LT);   // s_pp of the next unit is complete (written by warp 0 since t0 == 16)
+                            if (nxt) load_pairs((it + 1) & 1);
                         }
-                    }
-                    {
-                        const unsigned long long r0 = quantize2(f2_pack(v0.x, v0.y), lowp[0], rcpp[0], ndxp[0]);
-                        const unsigned long long r1 = quantize2(f2_pack(v0.z, v0.w), lowp[1], rcpp[1], ndxp[1]);
-                        const unsigned long long r2 = quantize2(f2_pack(v1.x, v1.y), lowp[2], rcpp[2], ndxp[2]);
-                        const unsigned long long r3 = quantize2(f2_pack(v1.z, v1.w), lowp[0], rcpp[0], ndxp[0]);
-                        const unsigned long long r4 = quantize2(f2_pack(v2.x, v2.y), lowp[1], rcpp[1], ndxp[1]);
-                        const unsigned long long r5 = quantize2(f2_pack(v2.z, v2.w), lowp[2], rcpp[2], ndxp[2]);
-                        f2_bits(r0, b[0][0], b[0][1]); f2_bits(r1, b[0][2], b[1][0]); f2_bits(r2, b[1][1], b[1][2]);
-                        f2_bits(r3, b[2][0], b[2][1]); f2_bits(r4, b[2][2], b[3][0]); f2_bits(r5, b[3][1], b[3][2]);
-                    }
-                    uint2 pk[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        unsigned w[4];
-#pragma unroll
-                        for (int pi = 0; pi < 4; pi++) {
-                            const unsigned tt = b[pi][k] + Cm[k];      // q + rotation
-                            w[pi] = min(tt, tt + nP[k]);               // mod pixels
+                        quant12(un, bn);
+                        if (u == 3 && t0 == PIPE_STEPS - 8) pr = nxt;   // step t + 5 == 32: the refills move on to the next unit
+                        if (t0 + u + 5 < PIPE_STEPS || nxt != nullptr) {
+                            buf[un][0] = ld_stream_pinned(pr); buf[un][1] = ld_stream_pinned(pr + 1); buf[un][2] = ld_stream_pinned(pr + 2);
                         }
-                        bmin[k] = __vimin3_u32(bmin[k], b[0][k], b[1][k]); bmin[k] = __vimin3_u32(bmin[k], b[2][k], b[3][k]);
-                        bmax[k] = __vimax3_u32(bmax[k], b[0][k], b[1][k]); bmax[k] = __vimax3_u32(bmax[k], b[2][k], b[3][k]);
-                        wmin[k] = __vimin3_u32(wmin[k], w[0], w[1]); wmin[k] = __vimin3_u32(wmin[k], w[2], w[3]);
-                        wmax[k] = __vimax3_u32(wmax[k], w[0], w[1]); wmax[k] = __vimax3_u32(wmax[k], w[2], w[3]);
-                        pk[k].x = __byte_perm(w[0], w[1], 0x5410);
-                        pk[k].y = __byte_perm(w[2], w[3], 0x5410);
-                    }
-                    if (it > 0) mbar_wait(&bar_empty[t], (unsigned)(it - 1) & 1u);   // the packers have read this slot
+                        pr += u == 2 ? inc_plane : inc_rows;
+                        // ---- integer half of step t ----
 #pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        *(uint2 *)(smem_raw + k * (2 * CHUNK) + 2048 * t + sbyte) = pk[k];
+                        for (int k = 0; k < 3; k++) {
+                            unsigned w[4];
+#pragma unroll
+                            for (int pi = 0; pi < 4; pi++) {
+                                const unsigned tt = bc[pi][k] + Cm[k];      // q + rotation
+                                w[pi] = min(tt, tt + nP[k]);                // mod pixels
+                            }
+                            bmin[k] = __vimin3_u32(bmin[k], bc[0][k], bc[1][k]); bmin[k] = __vimin3_u32(bmin[k], bc[2][k], bc[3][k]);
+                            bmax[k] = __vimax3_u32(bmax[k], bc[0][k], bc[1][k]); bmax[k] = __vimax3_u32(bmax[k], bc[2][k], bc[3][k]);
+                            wmin[k] = __vimin3_u32(wmin[k], w[0], w[1]); wmin[k] = __vimin3_u32(wmin[k], w[2], w[3]);
+                            wmax[k] = __vimax3_u32(wmax[k], w[0], w[1]); wmax[k] = __vimax3_u32(wmax[k], w[2], w[3]);
+                            pk[h][k].x = __byte_perm(w[0], w[1], 0x5410);
+                            pk[h][k].y = __byte_perm(w[2], w[3], 0x5410);
+                        }
+#pragma unroll
+                        for (int pi = 0; pi < 4; pi++)
+#pragma unroll
+                            for (int k = 0; k < 3; k++) bc[pi][k] = bn[pi][k];
+                    }
+                    const int t = t0 + u2;
+                    if (it > 0) mbar_wait(&bar_empty[t >> 1], (unsigned)(it - 1) & 1u);   // the packers have read these two slots
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            *(uint2 *)(smem_raw + k * (2 * CHUNK) + 2048 * (t + h) + sbyte) = pk[h][k];
                 }
             }
 
@@ -513,29 +540,35 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         }
     } else {
         // ====================== packers (7 warps) and the scanner (1 warp) ======================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PIPE_PREGS));
         const int pw = warp - PIPE_LW;
         const bool scanner = pw == PIPE_PW;
         unsigned *mybuf = tbuf + (scanner ? 0 : pw) * PIPE_TBUF;
+        long long pre_off = 0;      // scanner of rank 0: this unit's offsets were posted one unit ago
+        bool pre_posted = false;
         for (int it = 0;; it++) {
             mbar_wait_cluster(&bar_unit[it & UM], (it / PIPE_USLOTS) & 1);
             const long long unit = s_unit[it & UM];
             if (unit >= A.nunits) break;
             const long long f = unit / A.sc3, sc = unit - f * A.sc3;
             const int par_i = it & 1;
-            long long nb_mine = 0;   // scanner: lane k < 3 keeps ArrayBytes of axis k
             if (scanner) {
                 mbar_wait_cluster(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
                 PIPE_DBG(it, 2);
-                // ---- finalise the three axis blocks from the cluster's statistics (every CTA, redundantly) ----
-#pragma unroll 1
-                for (int k = 0; k < 3; k++) {
-                    const long long f_b = f * 3 * A.sc3 + k * A.sc3 + sc;   // block id in the batch
+                // ---- finalise: lane k < 3 combines the cluster's statistics of axis k (every CTA, redundantly) ----
+                const int k = lane < 3 ? lane : 0;
+                const long long f_b = f * 3 * A.sc3 + k * A.sc3 + sc;   // block id in the batch
+                long long nbytes = 0;
+                if (lane < 3) {
                     XStat x;
                     x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
-                    if (lane < CS) x = s_x[par_i][lane][k];
-                    x.wmin = __reduce_min_sync(0xffffffffu, x.wmin); x.wmax = __reduce_max_sync(0xffffffffu, x.wmax);
-                    x.qmin = __reduce_min_sync(0xffffffffu, x.qmin); x.qmax = __reduce_max_sync(0xffffffffu, x.qmax);
-                    x.oob = __reduce_or_sync(0xffffffffu, x.oob);
+#pragma unroll
+                    for (int r = 0; r < CS; r++) {
+                        const uint4 a = *(const uint4 *)&s_x[par_i][r][k];
+                        x.wmin = min(x.wmin, a.x); x.wmax = max(x.wmax, a.y);
+                        x.qmin = min(x.qmin, (int)a.z); x.qmax = max(x.qmax, (int)a.w);
+                        x.oob |= s_x[par_i][r][k].oob;
+                    }
                     const PipePar pp = s_par[par_i][k];
                     const long long Pk = (long long)pp.P, half = Pk / 2, K = Pk - half - 1;
                     const long long q0k = pp.q0;
@@ -556,82 +589,105 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         base = x.wmin; padj = 0;
                     }
                     int bits = 64 - __clzll((long long)maxoff);   // bit.PrecisionNeeded (maxoff < 2^32 here)
-                    long long nbytes = array_bytes(bits, N);
+                    nbytes = array_bytes(bits, N);
                     const bool slow = x.oob != 0 || pp.oob0 != 0;
                     if (slow) { bits = 0; nbytes = 0; }
-                    if (lane == k) nb_mine = nbytes;
-                    if (rank == 0 && lane == 0) st_relaxed(A.W.pub + f_b, PUB_AGG | (unsigned long long)nbytes);
+                    if (rank == 0) st_relaxed(A.W.pub + f_b, PUB_AGG | (unsigned long long)nbytes);
                     // staged values are the low 16 bits of w: enough when the packed value has <= 16 bits
                     // and (wide arcs) w itself fits, i.e. pixels <= 65536
                     const int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
-                    if (lane == 0) {
-                        Fin fin;
-                        fin.off = 0; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj;
-                        s_fin[k] = fin;
-                        if (rank == 0) {
-                            if (!slow && bits > 0 && mode == 0) A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = f_b;
-                            if (slow) atomicExch(A.W.abort_flag, 1);
-                            BlockStat bs = {};
-                            bs.pmin = pmin; bs.min = mn; bs.nbytes = nbytes; bs.out_off = 0; bs.do_bound = 1; bs.bits = bits;
-                            bs.q0 = q0k; bs.oob = slow;
-                            A.stats[f_b] = bs;
-                            if (A.mins) A.mins[f_b] = mn;
-                            if (A.bits) A.bits[f_b] = bits;
-                        }
+                    Fin fin;
+                    fin.off = nbytes; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj;
+                    s_fin[k] = fin;
+                    if (rank == 0) {
+                        if (!slow && bits > 0 && mode == 0) A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = f_b;
+                        if (slow) atomicExch(A.W.abort_flag, 1);
+                        BlockStat bs = {};
+                        bs.pmin = pmin; bs.min = mn; bs.nbytes = nbytes; bs.out_off = 0; bs.do_bound = 1; bs.bits = bits;
+                        bs.q0 = q0k; bs.oob = slow;
+                        A.stats[f_b] = bs;
+                        if (A.mins) A.mins[f_b] = mn;
+                        if (A.bits) A.bits[f_b] = bits;
                     }
                 }
                 if (lane == 0) s_gctr = 0;
-            }
-            bar_named(2, PT);   // s_fin is final, the staged indices of the unit are visible
-            if (scanner) PIPE_DBG(it, 3);
-            // the unit after next for the whole cluster (the loaders want it half way through the next one)
-            if (scanner && rank == 0 && lane == 0) claim((it + 2) & UM);
+                __syncwarp();
+                bar_named(2, PT);   // s_fin is final, the staged indices of the unit are visible
+                PIPE_DBG(it, 3);
 
-            if (scanner) {
-                // ---- byte offsets by decoupled look-back over the earlier sub-cells of the group (rank 0 only:
-                // one poller per cluster), broadcast to the cluster while the packers already pack; a group is
-                // written out once its block's offset is posted ----
                 if (rank == 0) {
-                    // lane k < 3 owns axis k.  Fast path: the previous sub-cell of the file has published its
-                    // inclusive prefix (always, when tickets walk many files round-robin): one load per axis.
-                    const int k = lane < 3 ? lane : 0;
-                    const long long f_b = f * 3 * A.sc3 + k * A.sc3 + sc;
-                    long long off = 0;
-                    bool have = true;
-                    if (lane < 3 && sc > 0) {
-                        const unsigned long long v = ld_relaxed(A.W.pub + f_b - 1);
-                        have = (v >> 62) == 2;
-                        off = (long long)(v & PUB_VALUE);
-                    }
-                    if (!__all_sync(0xffffffffu, have)) {
+                    // the unit after next for the whole cluster (the loaders want it half way through the next one)
+                    if (lane == 0) claim((it + 2) & UM);
+                    // ---- byte offsets (rank 0 only: one poller per cluster).  The offset of a block is the inclusive
+                    // prefix of the previous sub-cell of its file, which does not depend on this unit at all: it was
+                    // fetched and broadcast one unit ago if it had been published by then (always, when tickets walk
+                    // many files round-robin); otherwise the decoupled look-back runs now, while the packers pack. ----
+                    long long off = pre_off;
+                    if (!pre_posted) {
+                        bool have = true;
+                        off = 0;
+                        if (lane < 3 && sc > 0) {
+                            const unsigned long long v = ld_relaxed(A.W.pub + f_b - 1);
+                            have = (v >> 62) == 2;
+                            off = (long long)(v & PUB_VALUE);
+                        }
+                        if (!__all_sync(0xffffffffu, have)) {
 #pragma unroll 1
+                            for (int kk = 0; kk < 3; kk++) {
+                                const long long fb = f * 3 * A.sc3 + kk * A.sc3 + sc;
+                                const long long o = lookback(A.W.pub, fb - sc, fb);
+                                if (lane == kk) off = o;
+                            }
+                        }
+#pragma unroll
                         for (int kk = 0; kk < 3; kk++) {
-                            const long long fb = f * 3 * A.sc3 + kk * A.sc3 + sc;
-                            const long long o = lookback(A.W.pub, fb - sc, fb);
-                            if (lane == kk) off = o;
+                            const long long o = __shfl_sync(0xffffffffu, off, kk);
+                            if (lane < CS) {
+                                st_remote_u64(&s_off[it % 3][kk], (unsigned)lane, (unsigned long long)o);
+                                mbar_arrive_remote(&bar_off[it % 3][kk], (unsigned)lane);
+                            }
                         }
                     }
                     PIPE_DBG(it, 4);
-                    const bool fits = off + nb_mine <= A.axis_stride;   // never write past the caller's buffer
                     if (lane < 3) {
-                        st_relaxed(A.W.pub + f_b, PUB_PREFIX | (unsigned long long)(off + nb_mine));
-                        if (!fits) atomicExch(A.W.err, 2);
+                        st_relaxed(A.W.pub + f_b, PUB_PREFIX | (unsigned long long)(off + nbytes));
+                        if (off + nbytes > A.axis_stride) atomicExch(A.W.err, 2);   // the packers skip such a block
                         A.stats[f_b].out_off = off;
                         if (A.offsets) A.offsets[f_b] = off;
-                        if (A.out_len && sc == A.sc3 - 1) A.out_len[f * 3 + k] = off + nb_mine;
+                        if (A.out_len && sc == A.sc3 - 1) A.out_len[f * 3 + k] = off + nbytes;
                     }
-                    const long long post = fits ? off : -1LL;
+                    // ---- the next unit's offsets, if its predecessors are already through ----
+                    pre_posted = false;
+                    {
+                        mbar_wait_cluster(&bar_unit[(it + 1) & UM], ((it + 1) / PIPE_USLOTS) & 1);
+                        const long long nu = s_unit[(it + 1) & UM];   // claimed one unit ago (or in the prologue)
+                        bool have = nu < A.nunits;
+                        long long noff = 0;
+                        if (have && lane < 3) {
+                            const long long nf = nu / A.sc3, nsc = nu - nf * A.sc3;
+                            if (nsc > 0) {
+                                const unsigned long long v = ld_relaxed(A.W.pub + (nf * 3 * A.sc3 + k * A.sc3 + nsc) - 1);
+                                have = (v >> 62) == 2;
+                                noff = (long long)(v & PUB_VALUE);
+                            }
+                        }
+                        if (__all_sync(0xffffffffu, have)) {
+                            pre_posted = true;
+                            pre_off = noff;
 #pragma unroll
-                    for (int kk = 0; kk < 3; kk++) {
-                        const long long o = __shfl_sync(0xffffffffu, post, kk);
-                        if (lane < CS) {
-                            st_remote_u64(&s_off[par_i][kk], (unsigned)lane, (unsigned long long)o);
-                            mbar_arrive_remote(&bar_off[par_i][kk], (unsigned)lane);
+                            for (int kk = 0; kk < 3; kk++) {
+                                const long long o = __shfl_sync(0xffffffffu, noff, kk);
+                                if (lane < CS) {
+                                    st_remote_u64(&s_off[(it + 1) % 3][kk], (unsigned)lane, (unsigned long long)o);
+                                    mbar_arrive_remote(&bar_off[(it + 1) % 3][kk], (unsigned)lane);
+                                }
+                            }
                         }
                     }
                     PIPE_DBG(it, 6);
                 }
             } else {
+                bar_named(2, PT);   // s_fin is final, the staged indices of the unit are visible
                 // ---- pack groups of 1024 elements in row order; a slot (16 rows, one group per axis) goes
                 // back to the loaders as soon as its three groups are in registers ----
                 for (;;) {
@@ -642,7 +698,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                     const int gi = g / 3, k = g - 3 * gi;
                     const Fin fin = s_fin[k];
                     if (fin.mode == 0) {
-                        if (lane == 0) mbar_arrive(&bar_empty[gi]);
+                        if (lane == 0) mbar_arrive(&bar_empty[gi >> 1]);
                         continue;
                     }
                     const int eb = gi * 1024 + 32 * lane;   // this lane's first element within the CTA's chunk
@@ -651,7 +707,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 #pragma unroll
                     for (int s = 0; s < 4; s++) r[s] = *(const uint4 *)(stage + k * CHUNK + ((((eb >> 3) + s) ^ sw) << 3));
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_empty[gi]);
+                    if (lane == 0) mbar_arrive(&bar_empty[gi >> 1]);
                     const unsigned rr[16] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w,
                                              r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
                     unsigned fld[16];   // two values per field: v[2 i] | v[2 i + 1] << bits
@@ -678,10 +734,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                             fld[i] = min(lo, lo + fin.padj) + (min(hi, hi + fin.padj) << fin.bits);
                         }
                     }
-                    // the block's byte offset is posted by the scanner of rank 0
-                    mbar_wait_cluster(&bar_off[par_i][k], (unsigned)(it >> 1) & 1u);
-                    const long long o64 = s_off[par_i][k];
-                    if (o64 >= 0) {
+                    // the block's byte offset is posted by the scanner of rank 0 (never write past the caller's buffer)
+                    mbar_wait_cluster(&bar_off[it % 3][k], (unsigned)(it / 3) & 1u);
+                    const long long o64 = s_off[it % 3][k];
+                    if (o64 + fin.off <= A.axis_stride) {
                         const long long e0 = (long long)rank * CHUNK + (long long)gi * 1024;   // element index in the block
                         uint8_t *dst = A.out + (f * 3 + k) * A.axis_stride + o64 + ((e0 * fin.bits) >> 3);
                         switch (fin.bits) {
