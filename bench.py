@@ -319,7 +319,7 @@ def run_gpu(args):
     pk_total = packed_bytes["x"] + packed_bytes["v"]
     algo = {  # algorithmic bytes per step, summed over both fields (DESIGN.md "Kernels")
         "k_stats": 2 * field_bytes, "k_pack": 2 * field_bytes + pk_total,
-        "k_fused_vec3": 2 * field_bytes + pk_total, "k_decode": pk_total + 2 * field_bytes,
+        "k_fused_vec3": 2 * field_bytes + pk_total, "k_pipe_vec3": 2 * field_bytes + pk_total, "k_decode": pk_total + 2 * field_bytes,
         "k_decode_vec3": pk_total + 2 * field_bytes, "k_vec3_limits4": field_bytes}
     traffic = {}
     try:   # DRAM bytes per particle and launch from the committed ncu --set full capture (profiles/)

@@ -246,6 +246,8 @@ int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, i
     std::vector<FloatParams> host;
     rc = upload_params(ctx, desc, ndesc, host, &h.tab);
     if (rc) return rc;
+    h.low_nonneg = true;   // every decoded value dx * t + low is then >= +0: the periodic wrap needs one test only
+    for (const FloatParams &p : host) h.low_nonneg = h.low_nonneg && p.low >= 0.0f && p.dx > 0.0f;
     if (jitter) {
         if (jitter->mode < 0 || jitter->mode > 2) return fail(ctx, MNW_ERR_ARG, "unknown jitter mode %d", jitter->mode);
         h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0;

@@ -900,7 +900,9 @@ __device__ __noinline__ float decode_rare(const SlabAxis &h, long long e, int jm
 // uniform over the slab, while the CTA decodes the current one; every thread then
 // produces whole float4 pieces of AoS rows, so each output row is written once with
 // coalesced 128-bit stores and no axis ever touches a sector alone.
-template <int NSUB, int NT, int MINB, bool HASH, bool WRAP>
+// WRAP: 0 no periodic wrap, 1 both tests of go/minp/minp.go:195-203, 2 only `x >= L` (every group has
+// low >= +0, so no decoded value is negative).
+template <int NSUB, int NT, int MINB, bool HASH, int WRAP>
 __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
     constexpr int N = NSUB * NSUB * NSUB;
     constexpr int SLAB = N < 4096 ? N : 4096;   // elements per slab and axis
@@ -1042,9 +1044,12 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
                         t = __fadd_rn((float)q, 0.5f);   // q < 2^23: exact
                     }
                     float x = __fadd_rn(__fmul_rn(dx[j], t), low[j]);
-                    if constexpr (WRAP) {                                            // go/minp/minp.go:195-203
+                    if constexpr (WRAP == 1) {                                       // go/minp/minp.go:195-203
                         const float xp = __fadd_rn(x, A.wrap_L), xm = __fsub_rn(x, A.wrap_L);
                         x = x < 0.0f ? xp : (x >= A.wrap_L ? xm : x);
+                    } else if constexpr (WRAP == 2) {
+                        const float xm = __fsub_rn(x, A.wrap_L);
+                        x = x >= A.wrap_L ? xm : x;
                     }
                     o[c] = x;
                 }
@@ -1056,7 +1061,7 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
                 for (int c = 0; c < 4; c++) {
                     const int k = (a0 + c) % 3;
                     const long long e = (long long)info.e0 + rl * NSUB + ecol[c];
-                    o[c] = decode_rare(s_hdr[st][k], e, HASH ? 1 : 0, WRAP ? A.wrap_L : 0.0f);
+                    o[c] = decode_rare(s_hdr[st][k], e, HASH ? 1 : 0, WRAP != 0 ? A.wrap_L : 0.0f);
                 }
                 __stcs(pbase + ((unsigned)(rl / NSUB) * plane4 + (unsigned)(rl % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));
             }
@@ -1278,7 +1283,7 @@ bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out) {
     return ((uintptr_t)aos_out & 15) == 0;
 }
 
-template <int NSUB, bool HASH, bool WRAP>
+template <int NSUB, bool HASH, int WRAP>
 static cudaError_t launch_decode_vec3_t(Launcher &L, const DecVec3Args &A) {
     constexpr int NT = 384, MINB = 3;
     constexpr int N = NSUB * NSUB * NSUB, SLAB = N < 4096 ? N : 4096;
@@ -1308,9 +1313,13 @@ static cudaError_t launch_decode_vec3_t(Launcher &L, const DecVec3Args &A) {
 }
 
 template <int NSUB>
-static cudaError_t launch_decode_vec3_n(Launcher &L, const DecVec3Args &A, bool hash, bool wrap) {
-    if (hash) return wrap ? launch_decode_vec3_t<NSUB, true, true>(L, A) : launch_decode_vec3_t<NSUB, true, false>(L, A);
-    return wrap ? launch_decode_vec3_t<NSUB, false, true>(L, A) : launch_decode_vec3_t<NSUB, false, false>(L, A);
+static cudaError_t launch_decode_vec3_n(Launcher &L, const DecVec3Args &A, bool hash, int wrap) {
+    if (hash) {
+        if (wrap == 2) return launch_decode_vec3_t<NSUB, true, 2>(L, A);
+        return wrap ? launch_decode_vec3_t<NSUB, true, 1>(L, A) : launch_decode_vec3_t<NSUB, true, 0>(L, A);
+    }
+    if (wrap == 2) return launch_decode_vec3_t<NSUB, false, 2>(L, A);
+    return wrap ? launch_decode_vec3_t<NSUB, false, 1>(L, A) : launch_decode_vec3_t<NSUB, false, 0>(L, A);
 }
 
 cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t nfiles) {
@@ -1326,7 +1335,8 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
     const long long n = (long long)nsub * nsub * nsub;
     A.nslabs = units * (n < 4096 ? 1 : n / 4096);
     if (A.nslabs >= (1LL << 31)) return cudaErrorInvalidValue;
-    const bool hash = h.jmode == 1, wrap = h.wrap_L > 0.0f;
+    const bool hash = h.jmode == 1;
+    const int wrap = h.wrap_L > 0.0f ? (h.low_nonneg ? 2 : 1) : 0;
     switch (nsub) {
         case 64: return launch_decode_vec3_n<64>(L, A, hash, wrap);
         case 32: return launch_decode_vec3_n<32>(L, A, hash, wrap);

@@ -46,6 +46,7 @@ struct DecodeHost {
     const FloatParams *tab = nullptr;  // device table: 1 entry (group), 3 (vec3) or 3*nfiles (vec3, per file)
     int tab_per_file = 0;
     float wrap_L = 0;
+    bool low_nonneg = false;   // all groups have low >= +0 and dx > 0
     int jmode = 0;
     unsigned long long seed = 0, block_id0 = 0;
     const double *u = nullptr;

@@ -50,6 +50,7 @@ namespace {
 constexpr unsigned FMAGIC = 0x4B000000u;   // float bits of 2^23
 constexpr int PIPE_LW = 8, PIPE_PW = 7, PIPE_NT = 32 * (PIPE_LW + PIPE_PW + 1);   // + 1 scanner warp
 constexpr int PIPE_TBUF = 560;
+constexpr int PIPE_PFD = 8;   // L2 prefetch distance beyond the register pipeline, in steps (a multiple of 4)
 constexpr int PIPE_LREGS = 152, PIPE_PREGS = 104;   // registers per thread of the loader / packer warpgroups (2 x 128 in all)   // words of one packer warp's transposition buffer (33 * 16 + 1, rounded up)
 constexpr int PIPE_CS = 8, PIPE_CHUNK = 32768, PIPE_STEPS = 32, PIPE_USLOTS = 8;
 
@@ -371,7 +372,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 
         const size_t inc_rows = (size_t)16u * G.row4, inc_plane = (size_t)G.plane4 - (size_t)48u * G.row4;   // step t -> t + 1
         float4 buf[4][3];
-        const float4 *pr = nullptr;   // where the next refill comes from
+        const float4 *pr = nullptr;   // where the next refill comes from (step t + 5)
+        const float4 *pq = nullptr;   // the same, PIPE_PFD steps further: what is pulled towards L2 now
         long long unit = s_unit[0];
         long long f; unsigned sc;
         const float4 *cur = nullptr;
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             quant12(0, bc);
             buf[0][0] = ld_stream_pinned(pr); buf[0][1] = ld_stream_pinned(pr + 1); buf[0][2] = ld_stream_pinned(pr + 2);
             pr += inc_rows;
+            pq = pr + (size_t)(PIPE_PFD / 4) * G.plane4;
         }
         for (int it = 0; unit < A.nunits; it++) {
             if (warp == 0) PIPE_DBG(it, 0);
@@ -457,6 +460,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         }
                         quant12(un, bn);
                         if (u == 3 && t0 == PIPE_STEPS - 8) pr = nxt;   // step t + 5 == 32: the refills move on to the next unit
+                        if (u == 3 && t0 == PIPE_STEPS - 8 - PIPE_PFD) pq = nxt;   // and so does the L2 prefetch, PIPE_PFD steps earlier
+                        if (A.prefetch && (lane & 15) == 0 && (t0 + u + 5 + PIPE_PFD < PIPE_STEPS || nxt != nullptr))
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pq), "r"(64 * 12) : "memory");
+                        pq += u == 2 ? inc_plane : inc_rows;
                         if (t0 + u + 5 < PIPE_STEPS || nxt != nullptr) {
                             buf[un][0] = ld_stream_pinned(pr); buf[un][1] = ld_stream_pinned(pr + 1); buf[un][2] = ld_stream_pinned(pr + 2);
                         }
