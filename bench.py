@@ -479,4 +479,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner at
+    # communicator creation) is sent to stderr instead
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_stdout_fd, "w")
     main()
+    sys.stdout.flush()
