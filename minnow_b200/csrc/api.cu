@@ -590,9 +590,10 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         static const bool use_cluster = !(getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "flat"));   // tuning knob
         cudaError_t e;
         if (use_cluster) {
+            CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
             e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
                                   ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
-                                  pipe_vec3_supported(fp.data(), ndesc));
+                                  pipe_vec3_supported(fp.data(), ndesc), ctx->flat_ws.p);
         } else {
             CU(ctx->flat_ws.reserve(flat_work_bytes(nfiles * sc3)));
             CU(ctx->flat_scratch.reserve(flat_scratch_bytes()));

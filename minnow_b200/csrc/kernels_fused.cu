@@ -33,6 +33,7 @@
 #include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "fused_detail.cuh"
@@ -1159,11 +1160,12 @@ static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
 }
 
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A);   // kernels_pipe.cu
+cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws);
 
 cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams *tab, int tab_per_file,
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
                               int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
-                              int64_t out_axis_stride, bool pipe_ok) {
+                              int64_t out_axis_stride, bool pipe_ok, void *coop_ws) {
     FusedArgs A = {};
     A.aos = aos; A.tab = tab; A.tab_per_file = tab_per_file; A.nfile = nfile; A.subcells = subcells;
     A.sc3 = (long long)subcells * subcells * subcells;
@@ -1179,6 +1181,14 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
             // (pipelined loads / 8-deep batches) or 768 threads; 0 = 16-CTA cluster, 2 CTAs per SM
             static int variant = getenv("MNW_FUSED_NT") ? atoi(getenv("MNW_FUSED_NT")) : 1;
             if (variant == 1) {   // warp-specialised pipeline (default); needs pixels <= 2^22
+                // cooperative, cluster-free schedule on all SMs when the caller brought a workspace (MNW_PIPE=cluster
+                // keeps the 8-CTA cluster schedule); it falls back to the clusters when the device refuses the launch
+                static const bool coop = !(getenv("MNW_PIPE") && !strcmp(getenv("MNW_PIPE"), "cluster"));
+                if (pipe_ok && coop && coop_ws) {
+                    const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws);
+                    if (e == cudaSuccess) return e;
+                    (void)cudaGetLastError();
+                }
                 if (pipe_ok) return launch_pipe_vec3(L, A);
                 return launch_fused_vec3_t<64, 8, 384, 4, 1, true>(L, A);
             }

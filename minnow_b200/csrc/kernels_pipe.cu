@@ -9,7 +9,7 @@ namespace mnw {
 #include "pipe_vec3.cuh"
 
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
-    auto kern = k_pipe_vec3;
+    auto kern = k_pipe_vec3<false>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
     static bool configured = false;
     static int max_clusters = 0;
@@ -50,6 +50,43 @@ cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
             }
     }
 #endif
+    return e;
+}
+
+// Cluster-free variant: cooperative launch of one CTA per SM (rounded down to a multiple of 8, so that the eight
+// parts of a unit are always items of the same round), statistics records in `ustat` (16 words per unit, zeroed
+// here).  Returns cudaErrorCooperativeLaunchTooLarge / NotSupported when the device cannot hold the grid; the
+// caller then takes the cluster kernel.
+size_t pipe_coop_ws_bytes(int64_t nunits) { return (size_t)nunits * 64; }
+
+cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws) {
+    auto kern = k_pipe_vec3<true>;
+    const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
+    static int grid_max = -1;
+    cudaError_t e;
+    if (grid_max < 0) {
+        int dev = 0, sms = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_NT, smem);
+        if (e != cudaSuccess) return e;
+        grid_max = (coop && per_sm >= 1) ? (sms / 8) * 8 : 0;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop>: grid %d, %zu B dynamic smem\n", grid_max, smem);
+    }
+    if (grid_max < 8) return cudaErrorNotSupported;
+    const long long items = 8 * A.nunits;
+    const unsigned grid = (unsigned)(items < grid_max ? items : grid_max);   // >= 8: no CTA ever holds two parts of a unit
+    A.ustat = (unsigned *)ws;
+    e = cudaMemsetAsync(ws, 0, pipe_coop_ws_bytes(A.nunits), L.stream);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&A};
+    L.begin("k_pipe_vec3");
+    e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(PIPE_NT), args, smem, L.stream);
+    L.end();
+    L.count++;
     return e;
 }
 

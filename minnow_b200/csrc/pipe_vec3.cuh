@@ -36,7 +36,7 @@ __device__ __forceinline__ void pipe_dbg(int cluster, int it, int ev) {
         g_pipe_dbg[(cluster * 64 + it) * 8 + ev] = t;
     }
 }
-#define PIPE_DBG(it, ev) do { if (rank == 0 && lane == 0) pipe_dbg((int)(blockIdx.x / PIPE_CS), it, ev); } while (0)
+#define PIPE_DBG(it, ev) do { if ((blockIdx.x & 7) == 0 && lane == 0) pipe_dbg((int)(blockIdx.x / PIPE_CS), it, ev); } while (0)
 #else
 #define PIPE_DBG(it, ev) do { } while (0)
 #endif
@@ -274,6 +274,13 @@ __device__ __forceinline__ void emit_group(const unsigned (&f)[16], unsigned *bu
 
 }  // namespace
 
+// COOP = false: one 8-CTA cluster per unit, statistics through distributed shared memory (above).
+// COOP = true : no clusters.  The grid is launched cooperatively (all CTAs co-resident), CTA b works on the
+// items g = b + gridDim.x * i, item g being part g % 8 of unit g / 8 (same file-round-robin order), and the
+// eight parts of a unit meet through a 64-byte record in global memory (atomicMax on the statistics, a
+// counter, ld.acquire polling).  Every CTA looks its offsets up itself.  This uses all SMs (144 of 148)
+// instead of the 120 that 8-CTA clusters reach; a part only ever waits for items with a smaller g.
+template <bool COOP>
 __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     constexpr int N = 64 * 64 * 64, CHUNK = PIPE_CHUNK, CS = PIPE_CS;
     constexpr int LT = 32 * PIPE_LW, PT = 32 * (PIPE_PW + 1);   // loader threads; packer + scanner threads
@@ -298,7 +305,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     __shared__ int s_gctr;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned rank = cg::this_cluster().block_rank();
+    unsigned crank = 0;
+    if constexpr (!COOP) crank = cg::this_cluster().block_rank();
     PipeGeom G;
     G.S = A.subcells; G.nfile = A.nfile; G.sc3 = A.sc3;
     G.row4 = 3u * (unsigned)A.nfile / 4u; G.plane4 = G.row4 * (unsigned)A.nfile;
@@ -341,6 +349,21 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         }
     };
 
+    // unit and part of this CTA's it-th piece of work
+    auto unit_at = [&](int i, unsigned &rk) -> long long {
+        if constexpr (COOP) {
+            const long long g = (long long)blockIdx.x + (long long)gridDim.x * i;
+            rk = (unsigned)(g & 7);
+            if (g >= 8 * A.nunits) return A.nunits;
+            const long long up = g >> 3;
+            return (up % nfiles) * A.sc3 + up / nfiles;
+        } else {
+            mbar_wait_cluster(&bar_unit[i & UM], (i / PIPE_USLOTS) & 1);
+            rk = crank;
+            return s_unit[i & UM];
+        }
+    };
+
     if (tid == 0) {
         for (int i = 0; i < PIPE_USLOTS; i++) mbar_init(&bar_unit[i], 1);
         mbar_init(&bar_stats[0], CS); mbar_init(&bar_stats[1], CS);
@@ -348,11 +371,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         for (int i = 0; i < 9; i++) mbar_init(&bar_off[0][0] + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    cluster_sync_all<CS>();
-    if (rank == 0 && tid == 0) { claim(0); claim(1); }
-    mbar_wait_cluster(&bar_unit[0], 0);
+    if constexpr (COOP) __syncthreads(); else cluster_sync_all<CS>();
+    if constexpr (!COOP) { if (crank == 0 && tid == 0) { claim(0); claim(1); } }
     {
-        const long long u0 = s_unit[0];
+        unsigned rk0;
+        const long long u0 = unit_at(0, rk0);
         if (tid < 3 && u0 < A.nunits) prepare(u0, 0, tid);
         __syncwarp();
         if (tid < 9 && u0 < A.nunits) prepare_pairs(0, tid);
@@ -364,7 +387,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_LREGS));
         // lane geometry: step t covers rows 16 t .. 16 t + 15 of the CTA's 512; warp w rows 2 w, 2 w + 1
         // of those, lane l particles 4 (l & 15) .. + 3 of row (l >> 4)
-        const unsigned toff = rank * 8u * G.plane4 + (unsigned)(2 * warp + (lane >> 4)) * G.row4 + 3u * (unsigned)(lane & 15);
+        const unsigned toff0 = (unsigned)(2 * warp + (lane >> 4)) * G.row4 + 3u * (unsigned)(lane & 15);
+        auto toff = [&](unsigned rk) { return rk * 8u * G.plane4 + toff0; };   // rk: which eighth of the unit
         const int e_thread = 128 * warp + 4 * lane;   // element of the thread's first particle at step 0
         // byte offset of that element's 8-byte piece in an axis' staging array (chunk swizzle c ^ ((c >> 3) & 7))
         const unsigned sbyte = (unsigned)((((e_thread >> 3) ^ ((e_thread >> 6) & 7)) << 4) + ((lane & 1) << 3));
@@ -374,7 +398,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         float4 buf[4][3];
         const float4 *pr = nullptr;   // where the next refill comes from (step t + 5)
         const float4 *pq = nullptr;   // the same, PIPE_PFD steps further: what is pulled towards L2 now
-        long long unit = s_unit[0];
+        unsigned rank = 0, nrank = 0;
+        long long unit = unit_at(0, rank);
         long long f; unsigned sc;
         const float4 *cur = nullptr;
         // per-axis parameters as pairs in the order the 12 floats of a step arrive: (x,y) (z,x) (y,z) (x,y) (z,x) (y,z)
@@ -401,7 +426,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         };
         unsigned bc[4][3];   // float half of the step whose integer half comes next (software pipeline, one step deep)
         if (unit < A.nunits) {
-            cur = G.origin(A.aos, unit, f, sc) + toff;
+            cur = G.origin(A.aos, unit, f, sc) + toff(rank);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const float4 *p = cur + step_off(u);
@@ -432,12 +457,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 #pragma unroll 1
             for (int t0 = 0; t0 < PIPE_STEPS; t0 += 4) {
                 if (t0 == 16) {   // the next unit: its origin and its parameters
-                    mbar_wait_cluster(&bar_unit[(it + 1) & UM], ((it + 1) / PIPE_USLOTS) & 1);
-                    next = s_unit[(it + 1) & UM];
+                    next = unit_at(it + 1, nrank);
                     if (next < A.nunits) {
                         long long nf; unsigned nsc;
                         const float4 *nb = G.origin(A.aos, next, nf, nsc);
-                        nxt = nb + toff;
+                        nxt = nb + toff(nrank);
                         if (warp == 0) {
                             if (lane < 3) prepare(next, (it + 1) & 1, lane);
                             __syncwarp();
@@ -529,7 +553,23 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 s_cta[tid] = m;
             }
             __syncwarp();
-            if (tid < CS) {   // post this CTA's statistics to CTA `tid` and tell it
+            if constexpr (COOP) {
+                // the unit's record in global memory: [4 k + {0, 1, 2, 3}] = ~wmin, wmax, ~qmin, qmax of axis k (atomicMax
+                // from zero), [12] oob, [13] parts arrived
+                unsigned *us = A.ustat + 16 * unit;
+                if (tid < 13) {
+                    const unsigned m = s_cta[tid];
+                    if (tid < 12) {
+                        const unsigned v = (tid & 2) ? m - FMAGIC : m;
+                        atomicMax(us + tid, (tid & 1) ? v : ~v);
+                    } else if (m) {
+                        atomicOr(us + 12, 1u);
+                    }
+                    __threadfence();
+                }
+                __syncwarp();
+                if (tid == 0) atomicAdd(us + 13, 1u);
+            } else if (tid < CS) {   // post this CTA's statistics to CTA `tid` and tell it
                 const int par_i = it & 1;
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
@@ -544,6 +584,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             }
             cur = nxt;
             unit = next;
+            rank = nrank;
         }
     } else {
         // ====================== packers (7 warps) and the scanner (1 warp) ======================
@@ -554,13 +595,22 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         long long pre_off = 0;      // scanner of rank 0: this unit's offsets were posted one unit ago
         bool pre_posted = false;
         for (int it = 0;; it++) {
-            mbar_wait_cluster(&bar_unit[it & UM], (it / PIPE_USLOTS) & 1);
-            const long long unit = s_unit[it & UM];
+            unsigned rank;
+            const long long unit = unit_at(it, rank);
             if (unit >= A.nunits) break;
             const long long f = unit / A.sc3, sc = unit - f * A.sc3;
             const int par_i = it & 1;
             if (scanner) {
-                mbar_wait_cluster(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
+                if constexpr (COOP) {   // all eight parts of the unit have posted their statistics
+                    const unsigned *cnt = A.ustat + 16 * unit + 13;
+                    unsigned c;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt) : "memory");
+                        if (c < 8u) __nanosleep(64);
+                    } while (c < 8u);
+                } else {
+                    mbar_wait_cluster(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
+                }
                 PIPE_DBG(it, 2);
                 // ---- finalise: lane k < 3 combines the cluster's statistics of axis k (every CTA, redundantly) ----
                 const int k = lane < 3 ? lane : 0;
@@ -569,12 +619,19 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 if (lane < 3) {
                     XStat x;
                     x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
+                    if constexpr (COOP) {
+                        const unsigned *us = A.ustat + 16 * unit;
+                        x.wmin = ~__ldcg(us + 4 * k); x.wmax = __ldcg(us + 4 * k + 1);
+                        x.qmin = (int)~__ldcg(us + 4 * k + 2); x.qmax = (int)__ldcg(us + 4 * k + 3);
+                        x.oob = __ldcg(us + 12);
+                    } else {
 #pragma unroll
-                    for (int r = 0; r < CS; r++) {
-                        const uint4 a = *(const uint4 *)&s_x[par_i][r][k];
-                        x.wmin = min(x.wmin, a.x); x.wmax = max(x.wmax, a.y);
-                        x.qmin = min(x.qmin, (int)a.z); x.qmax = max(x.qmax, (int)a.w);
-                        x.oob |= s_x[par_i][r][k].oob;
+                        for (int r = 0; r < CS; r++) {
+                            const uint4 a = *(const uint4 *)&s_x[par_i][r][k];
+                            x.wmin = min(x.wmin, a.x); x.wmax = max(x.wmax, a.y);
+                            x.qmin = min(x.qmin, (int)a.z); x.qmax = max(x.qmax, (int)a.w);
+                            x.oob |= s_x[par_i][r][k].oob;
+                        }
                     }
                     const PipePar pp = s_par[par_i][k];
                     const long long Pk = (long long)pp.P, half = Pk / 2, K = Pk - half - 1;
@@ -622,9 +679,18 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 bar_named(2, PT);   // s_fin is final, the staged indices of the unit are visible
                 PIPE_DBG(it, 3);
 
-                if (rank == 0) {
+                // offsets reach the packers of the cluster (broadcast by rank 0) or of this CTA (COOP)
+                auto post_off = [&](int slot, int kk, long long o) {
+                    if constexpr (COOP) {
+                        if (lane == 0) { s_off[slot][kk] = o; mbar_arrive(&bar_off[slot][kk]); }
+                    } else if (lane < CS) {
+                        st_remote_u64(&s_off[slot][kk], (unsigned)lane, (unsigned long long)o);
+                        mbar_arrive_remote(&bar_off[slot][kk], (unsigned)lane);
+                    }
+                };
+                if (COOP || rank == 0) {
                     // the unit after next for the whole cluster (the loaders want it half way through the next one)
-                    if (lane == 0) claim((it + 2) & UM);
+                    if constexpr (!COOP) { if (lane == 0) claim((it + 2) & UM); }
                     // ---- byte offsets (rank 0 only: one poller per cluster).  The offset of a block is the inclusive
                     // prefix of the previous sub-cell of its file, which does not depend on this unit at all: it was
                     // fetched and broadcast one unit ago if it had been published by then (always, when tickets walk
@@ -649,14 +715,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 #pragma unroll
                         for (int kk = 0; kk < 3; kk++) {
                             const long long o = __shfl_sync(0xffffffffu, off, kk);
-                            if (lane < CS) {
-                                st_remote_u64(&s_off[it % 3][kk], (unsigned)lane, (unsigned long long)o);
-                                mbar_arrive_remote(&bar_off[it % 3][kk], (unsigned)lane);
-                            }
+                            post_off(it % 3, kk, o);
                         }
                     }
                     PIPE_DBG(it, 4);
-                    if (lane < 3) {
+                    if (lane < 3 && rank == 0) {
                         st_relaxed(A.W.pub + f_b, PUB_PREFIX | (unsigned long long)(off + nbytes));
                         if (off + nbytes > A.axis_stride) atomicExch(A.W.err, 2);   // the packers skip such a block
                         A.stats[f_b].out_off = off;
@@ -666,8 +729,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                     // ---- the next unit's offsets, if its predecessors are already through ----
                     pre_posted = false;
                     {
-                        mbar_wait_cluster(&bar_unit[(it + 1) & UM], ((it + 1) / PIPE_USLOTS) & 1);
-                        const long long nu = s_unit[(it + 1) & UM];   // claimed one unit ago (or in the prologue)
+                        unsigned nrk;
+                        const long long nu = unit_at(it + 1, nrk);   // claimed one unit ago (or in the prologue)
                         bool have = nu < A.nunits;
                         long long noff = 0;
                         if (have && lane < 3) {
@@ -684,10 +747,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 #pragma unroll
                             for (int kk = 0; kk < 3; kk++) {
                                 const long long o = __shfl_sync(0xffffffffu, noff, kk);
-                                if (lane < CS) {
-                                    st_remote_u64(&s_off[(it + 1) % 3][kk], (unsigned)lane, (unsigned long long)o);
-                                    mbar_arrive_remote(&bar_off[(it + 1) % 3][kk], (unsigned)lane);
-                                }
+                                post_off((it + 1) % 3, kk, o);
                             }
                         }
                     }
@@ -763,5 +823,5 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     }
     // nobody leaves while a peer may still store into its shared memory
     __syncthreads();
-    cluster_sync_all<CS>();
+    if constexpr (!COOP) cluster_sync_all<CS>();
 }
