@@ -590,10 +590,17 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         static const bool use_cluster = !(getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "flat"));   // tuning knob
         cudaError_t e;
         if (use_cluster) {
-            CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
+            // The cooperative schedule owns the whole GPU while it runs: right for large batches, but calls on a
+            // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
+            void *coop_ws = nullptr;
+            const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
+            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256)) {
+                CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
+                coop_ws = ctx->flat_ws.p;
+            }
             e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
                                   ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
-                                  pipe_vec3_supported(fp.data(), ndesc), ctx->flat_ws.p);
+                                  pipe_vec3_supported(fp.data(), ndesc), coop_ws);
         } else {
             CU(ctx->flat_ws.reserve(flat_work_bytes(nfiles * sc3)));
             CU(ctx->flat_scratch.reserve(flat_scratch_bytes()));

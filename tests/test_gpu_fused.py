@@ -324,3 +324,57 @@ def test_pipe_many_files_dev_64(ctx, orc):
             got = out[(3 * f + k) * stride:(3 * f + k) * stride + len(want)].tobytes()
             assert got == want
             assert np.array_equal(offs[sl][k * sc3:(k + 1) * sc3], np.concatenate([[0], np.cumsum(onb[k * sc3:(k + 1) * sc3])[:-1]]))
+
+
+@pytest.mark.parametrize("case", ["edges", "bad", "widths", "files"])
+def test_pipe_cooperative_schedule_64(ctx, orc, case, monkeypatch):
+    """the cluster-free cooperative schedule of k_pipe_vec3 (default only for batches of >= 256 units) on the small
+    parity cases: forced with MNW_PIPE_COOP_MIN=1"""
+    monkeypatch.setenv("MNW_PIPE_COOP_MIN", "1")
+    if case == "edges":
+        test_pipe_edges_64(ctx, orc)
+    elif case == "bad":
+        test_pipe_bad_values_64(ctx, orc, np.nan)
+        test_pipe_bad_values_64(ctx, orc, 2500.0)
+    elif case == "widths":
+        test_pipe_bit_widths_64(ctx, orc, 0.05, 3.0)
+        test_pipe_bit_widths_64(ctx, orc, 30.0, 60.0)
+    else:
+        test_pipe_many_files_dev_64(ctx, orc)
+
+
+def test_pipe_cooperative_large_batch_roundtrip(ctx):
+    """a batch large enough for the cooperative schedule by default (4 files x 64 units of 64^3): encode, decode
+    with CENTER jitter, and check the domain's size-independent properties: every decoded value within dx/2 of
+    its input, offsets = running sum of ArrayBytes(bits, n), out_len = last offset + size"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    nfile, subcells, nfiles, L, dx = 256, 4, 4, 1000.0, 0.005
+    sc3, n3, nsub3 = subcells ** 3, nfile ** 3, (nfile // subcells) ** 3
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    aos = torch.rand((nfiles, n3, 3), generator=g, device=dev, dtype=torch.float32) * 3.0
+    j = torch.arange(nfile, device=dev, dtype=torch.float32) * (L / nfile)
+    grid = torch.stack(torch.meshgrid(j, j, j, indexing="ij")[::-1], dim=-1).reshape(n3, 3)
+    aos = torch.remainder(aos + grid[None], L).contiguous()
+    aos[aos >= L] = 0.0
+    px = mb.float_group_pixels(0.0, L, dx)
+    descs = [mb.FloatDesc.make(0.0, L, px) for _ in range(3)]
+    nb = nfiles * 3 * sc3
+    stride = 4 * nsub3 * sc3
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    ctx.encode_vec3_subcells_dev(descs, aos, nfile, subcells, nfiles, mins, bits, offs, out, stride, out_len)
+    dec = torch.empty_like(aos)
+    ctx.decode_vec3_subcells_dev(descs, out, stride, offs, mins, bits, nfile, subcells, nfiles, L, mb.Jitter.make(mb.JITTER_CENTER, 0), dec)
+    torch.cuda.synchronize()
+    assert ctx.last_path == 1
+    d = (dec - aos).abs()
+    d = torch.minimum(d, L - d)
+    assert float(d.max()) <= 0.5 * dx * 1.01 + 1e-4
+    nbytes = (bits * nsub3 + 7) // 8
+    o = offs.reshape(3 * nfiles, sc3); nbs = nbytes.reshape(3 * nfiles, sc3)
+    assert torch.equal(o, torch.cumsum(nbs, 1) - nbs)
+    assert torch.equal(out_len, o[:, -1] + nbs[:, -1])
+    assert int(bits.max()) <= 16 and int(bits.min()) >= 1
