@@ -1018,26 +1018,39 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
                 mask[j] = h.mask; key[j] = h.key + info.e0 * 0x9E3779B1U;   // hash(key, e0 + el) = f(el * M + key')
                 low[j] = h.low; dx[j] = h.dx;
             }
+            // From one of this thread's rows to the next (RPP rows on) the bit position of its four values moves by
+            // RPP * NSUB * bits, a whole number of 32-bit words: the shift within the word never changes and the word
+            // address, the hash argument and the output pointer all advance by constants.
+            unsigned addr[4], sh[4], hx[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int j = c % 3;
+                const unsigned el0 = (unsigned)(rsub * NSUB + ecol[c]);
+                const unsigned bp0 = shift[j] + el0 * bits[j];
+                addr[c] = buf[j] + ((bp0 >> 5) << 2);
+                sh[c] = bp0 & 31u;
+                hx[c] = el0 * 0x9E3779B1U + key[j];
+            }
+            const unsigned dA[3] = {(RPP * NSUB / 8) * bits[0], (RPP * NSUB / 8) * bits[1], (RPP * NSUB / 8) * bits[2]};
 #pragma unroll 2
             for (int rl = rsub; rl < ROWS; rl += RPP) {
                 float o[4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int j = c % 3;
-                    const unsigned el = (unsigned)(rl * NSUB + ecol[c]);            // element within the slab
-                    const unsigned bp = shift[j] + el * bits[j];
                     unsigned w0, w1;
-                    const unsigned addr = buf[j] + ((bp >> 5) << 2);
-                    asm("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(addr));
-                    asm("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(addr));
-                    const unsigned v = __funnelshift_r(w0, w1, bp) & mask[j];       // Array.Slice, go/bit/bit.go:29-82
+                    asm("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(addr[c]));
+                    asm("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(addr[c]));
+                    addr[c] += dA[j];
+                    const unsigned v = __funnelshift_r(w0, w1, sh[c]) & mask[j];    // Array.Slice, go/bit/bit.go:29-82
                     unsigned q = mn[j] + v;                                          // go/group.go:262
                     q = min(q, q - P[j]);                                            // bound(q, 0, pixels), :303 (P = 0: not periodic)
                     float t;
                     if constexpr (HASH) {
                         // u = h24 * 2^-24 is exact in float32 and q + u needs at most 47 bits: the FMA
                         // rounds once, exactly like float32(float64(q) + u) (go/group.go:308)
-                        unsigned x = el * 0x9E3779B1U + key[j];
+                        unsigned x = hx[c];                                          // = el * M + key
+                        hx[c] += (unsigned)(RPP * NSUB) * 0x9E3779B1U;
                         x ^= x >> 16; x *= 0x7feb352dU;
                         x ^= x >> 15; x *= 0x846ca68bU;
                         t = __fmaf_rn((float)(x >> 8), 0x1p-24f, (float)q);
