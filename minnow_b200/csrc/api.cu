@@ -166,9 +166,11 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
     // contiguous float32 blocks of a periodic group with pixels < 2^31: the vectorised two-pass kernels
     const bool f32c = !ctx->force_generic && !d_idx && kind == KIND_F32 && (fp.flags & F_PERIODIC) && fp.pixels >= 1 &&
                       fp.pixels < (1LL << 31);
+    // contiguous int64 blocks: the vectorised two-pass kernels (blocks wider than 32 bits fall to k_pack)
+    const bool i64c = !ctx->force_generic && !d_idx && kind == KIND_I64;
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
-                          0, out_cap, nullptr, f32c);
+                          0, out_cap, nullptr, f32c, i64c);
     CU(cudaGetLastError());
     return MNW_OK;
 }

@@ -528,7 +528,7 @@ __device__ __forceinline__ void store_stream(uint8_t *dst, const uint32_t *s, in
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats, BatchShape sh,
        uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err, const int *run_if,
-       const int64_t *list, const int *list_count) {
+       const int64_t *list, const int *list_count, int only_above = 0) {
     __shared__ uint32_t s_out[PACK_THREADS * 64 + 4];
     if (run_if && *run_if == 0) return;
     const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
@@ -545,6 +545,7 @@ k_pack(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats,
         const BlockStat st = stats[b];
         const int bits = st.bits;
         if (bits == 0) continue;  // ArrayBuffer.Write returns at once, go/bit/bit.go:162
+        if (bits <= only_above) continue;   // narrower blocks were packed by the vectorised kernel
         if (st.out_off + st.nbytes > chain_cap) {  // never write past the caller's buffer
             if (threadIdx.x == 0) atomicExch(err, 2);
             continue;
@@ -788,6 +789,28 @@ __device__ __forceinline__ unsigned quant_elem(float v, const QuantP &p, bool &o
     return q;
 }
 
+// The unchecked form of the same quantiser for whole float4s: raw bits of RM(y + 2^23), y the correctly rounded
+// quotient (x - low) / dx; for 0 <= y < 2^23 they are FQ_MAGIC + floor(y).  The caller vouches for the result by a
+// range test on the bits ([FQ_MAGIC, FQ_MAGIC + pixels) rejects negative, NaN, infinite and too large quotients) and
+// falls back to quant_elem otherwise.  Needs pixels <= 2^22 and no log10 pre-transform; the clamp is applied here.
+constexpr unsigned FQ_MAGIC = 0x4B000000u;
+__device__ __forceinline__ unsigned quant_bits(float v, const QuantP &p, bool clamp) {
+    if (clamp) {   // go/minh/minh.go:144-147
+        v = v < p.low ? p.low : v;
+        v = v >= p.high ? p.hi_clamp : v;
+    }
+    const float tt = __fsub_rn(v, p.low);
+    float y = __fmul_rn(tt, p.rcp);
+    float e = __fmaf_rn(p.ndx, y, tt);
+    y = __fmaf_rn(e, p.rcp, y);
+    e = __fmaf_rn(p.ndx, y, tt);
+    y = __fmaf_rn(e, p.rcp, y);
+    return __float_as_uint(__fadd_rd(y, 8388608.0f));
+}
+__device__ __forceinline__ bool quant_bits_ok(const QuantP &p) {
+    return p.fast_ok && !(p.flags & F_LOG10) && p.P <= (1u << 22);
+}
+
 constexpr int FSTAT_THREADS = 256;
 __global__ void __launch_bounds__(FSTAT_THREADS)
 k_stats_f32c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh, const int *run_if) {
@@ -810,20 +833,63 @@ k_stats_f32c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape s
         const int a = (int)(((uintptr_t)p & 15) >> 2);          // elements of the first 16 bytes that precede the chunk
         const float4 *base4 = (const float4 *)(p - a);
         const int nvec = (a + count + 3) >> 2;
-#pragma unroll 2
-        for (int iv = threadIdx.x; iv < nvec; iv += FSTAT_THREADS) {
-            const float4 v4 = __ldcs(base4 + iv);
-            const float x[4] = {v4.x, v4.y, v4.z, v4.w};
+        // checked path for vectors [v0, v1) of this thread (any element may lie outside the chunk)
+        auto checked = [&](int v0, int v1) {
+            for (int iv = v0 + threadIdx.x; iv < v1; iv += FSTAT_THREADS) {
+                const float4 v4 = __ldcs(base4 + iv);
+                const float x[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int el = 4 * iv + c - a;
-                if (el >= 0 && el < count) {
-                    const unsigned q = quant_elem(x[c], qp, oob, nullptr);
-                    unsigned w = q + C;
-                    w = min(w, w - qp.P);
-                    wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
+                for (int c = 0; c < 4; c++) {
+                    const int el = 4 * iv + c - a;
+                    if (el >= 0 && el < count) {
+                        const unsigned q = quant_elem(x[c], qp, oob, nullptr);
+                        unsigned w = q + C;
+                        w = min(w, w - qp.P);
+                        wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
+                    }
                 }
             }
+        };
+        if (quant_bits_ok(qp) && q0_ok) {
+            // whole vectors [v_lo, v_hi): unchecked quantiser, ONE range test per thread on the min/max of the raw
+            // bits; a thread that fails it (rare) takes its vectors again through the checked path
+            const int v_lo = a ? 1 : 0, v_hi = (a + count) >> 2;
+            const bool clamp = qp.flags & F_CLAMP;
+            const unsigned Cm = C - FQ_MAGIC, nP = 0u - qp.P;
+            unsigned bmin = ~0u, bmax = 0u, fwmin = ~0u, fwmax = 0u;
+#pragma unroll 2
+            for (int iv = v_lo + threadIdx.x; iv < v_hi; iv += FSTAT_THREADS) {
+                const float4 v4 = __ldcs(base4 + iv);
+                const unsigned b0 = quant_bits(v4.x, qp, clamp), b1 = quant_bits(v4.y, qp, clamp);
+                const unsigned b2 = quant_bits(v4.z, qp, clamp), b3 = quant_bits(v4.w, qp, clamp);
+                const unsigned t0 = b0 + Cm, t1 = b1 + Cm, t2 = b2 + Cm, t3 = b3 + Cm;
+                const unsigned w0 = min(t0, t0 + nP), w1 = min(t1, t1 + nP), w2 = min(t2, t2 + nP), w3 = min(t3, t3 + nP);
+                bmin = __vimin3_u32(bmin, b0, b1); bmin = __vimin3_u32(bmin, b2, b3);
+                bmax = __vimax3_u32(bmax, b0, b1); bmax = __vimax3_u32(bmax, b2, b3);
+                fwmin = __vimin3_u32(fwmin, w0, w1); fwmin = __vimin3_u32(fwmin, w2, w3);
+                fwmax = __vimax3_u32(fwmax, w0, w1); fwmax = __vimax3_u32(fwmax, w2, w3);
+            }
+            if (bmin <= bmax) {   // this thread saw whole vectors
+                if (bmin >= FQ_MAGIC && bmax < FQ_MAGIC + qp.P) {
+                    wmin = fwmin; wmax = fwmax; qmin = bmin - FQ_MAGIC; qmax = bmax - FQ_MAGIC;
+                } else {
+                    for (int iv = v_lo + threadIdx.x; iv < v_hi; iv += FSTAT_THREADS) {
+                        const float4 v4 = __ldcs(base4 + iv);
+                        const float x[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const unsigned q = quant_elem(x[c], qp, oob, nullptr);
+                            unsigned w = q + C;
+                            w = min(w, w - qp.P);
+                            wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
+                        }
+                    }
+                }
+            }
+            checked(0, v_lo);        // the partial first / last vector of the chunk
+            checked(v_hi, nvec);
+        } else {
+            checked(0, nvec);
         }
         wmin = __reduce_min_sync(0xffffffffu, wmin); wmax = __reduce_max_sync(0xffffffffu, wmax);
         qmin = __reduce_min_sync(0xffffffffu, qmin); qmax = __reduce_max_sync(0xffffffffu, qmax);
@@ -874,26 +940,52 @@ k_pack_f32c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
         const int a = (int)(((uintptr_t)p & 15) >> 2);
         const float4 *base4 = (const float4 *)(p - a);
         const int nvec = (a + count + 3) >> 2;
-        for (int iv = threadIdx.x; iv < nvec; iv += FPACK_THREADS) {
-            const float4 v4 = __ldcs(base4 + iv);
-            const float x[4] = {v4.x, v4.y, v4.z, v4.w};
+        // one element through the checked quantiser into its swizzled staging slot
+        auto stage_elem = [&](float xv, int el) {
+            bool oob = false;
+            long long raw;
+            const unsigned q = quant_elem(xv, qp, oob, &raw);
+            unsigned v;
+            if (!st.slow) {   // folded index; bound(q, pmin, pixels) - min (go/group.go:323, :246-247)
+                const long long qb = (long long)q < st.pmin ? (long long)q + (long long)qp.P : (long long)q;
+                v = (unsigned)(qb - st.min);
+            } else {          // the block holds out-of-range indices: the reference's own int64 arithmetic
+                const long long qb = st.do_bound ? bound1(raw, st.pmin, (long long)qp.P) : raw;
+                v = (unsigned)((unsigned long long)qb - (unsigned long long)st.min) & mask;
+            }
+            const int L = el >> 5, i = el & 31;
+            sv[(L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3))] = v;
+        };
+        if (a == 0 && count == PACK_TILE && !st.slow && st.do_bound && quant_bits_ok(qp)) {
+            // whole aligned tile of a block whose indices all lie in [0, pixels]: unchecked quantiser, range test per
+            // float4, 32-bit bound / subtract, one 128-bit staging store per float4
+            const bool clamp = qp.flags & F_CLAMP;
+            const unsigned dsub = 0u - FQ_MAGIC - (unsigned)st.pmin, cadd = (unsigned)(st.pmin - st.min);
+#pragma unroll 2
+            for (int iv = threadIdx.x; iv < PACK_TILE / 4; iv += FPACK_THREADS) {
+                const float4 v4 = __ldcs(base4 + iv);
+                const unsigned b0 = quant_bits(v4.x, qp, clamp), b1 = quant_bits(v4.y, qp, clamp);
+                const unsigned b2 = quant_bits(v4.z, qp, clamp), b3 = quant_bits(v4.w, qp, clamp);
+                const unsigned lo = __vimin3_u32(b0, b1, min(b2, b3)), hi = __vimax3_u32(b0, b1, max(b2, b3));
+                if (lo >= FQ_MAGIC && hi < FQ_MAGIC + qp.P) {
+                    const unsigned d0 = b0 + dsub, d1 = b1 + dsub, d2 = b2 + dsub, d3 = b3 + dsub;   // q - pmin
+                    uint4 r;
+                    r.x = min(d0, d0 + qp.P) + cadd; r.y = min(d1, d1 + qp.P) + cadd;
+                    r.z = min(d2, d2 + qp.P) + cadd; r.w = min(d3, d3 + qp.P) + cadd;
+                    const int L = iv >> 3;
+                    *(uint4 *)&sv[(L << 5) + (((iv & 7) ^ (L & 7)) << 2)] = r;
+                } else {
+                    stage_elem(v4.x, 4 * iv); stage_elem(v4.y, 4 * iv + 1); stage_elem(v4.z, 4 * iv + 2); stage_elem(v4.w, 4 * iv + 3);
+                }
+            }
+        } else {
+            for (int iv = threadIdx.x; iv < nvec; iv += FPACK_THREADS) {
+                const float4 v4 = __ldcs(base4 + iv);
+                const float x[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int el = 4 * iv + c - a;
-                if (el >= 0 && el < count) {
-                    bool oob = false;
-                    long long raw;
-                    const unsigned q = quant_elem(x[c], qp, oob, &raw);
-                    unsigned v;
-                    if (!st.slow) {   // folded index; bound(q, pmin, pixels) - min (go/group.go:323, :246-247)
-                        const long long qb = (long long)q < st.pmin ? (long long)q + (long long)qp.P : (long long)q;
-                        v = (unsigned)(qb - st.min);
-                    } else {          // the block holds out-of-range indices: the reference's own int64 arithmetic
-                        const long long qb = st.do_bound ? bound1(raw, st.pmin, (long long)qp.P) : raw;
-                        v = (unsigned)((unsigned long long)qb - (unsigned long long)st.min) & mask;
-                    }
-                    const int L = el >> 5, i = el & 31;
-                    sv[(L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3))] = v;
+                for (int c = 0; c < 4; c++) {
+                    const int el = 4 * iv + c - a;
+                    if (el >= 0 && el < count) stage_elem(x[c], el);
                 }
             }
         }
@@ -901,6 +993,126 @@ k_pack_f32c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
             const int L = el >> 5, i = el & 31;
             sv[(L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3))] = 0u;
         }
+        __syncthreads();
+        const int g = warp;                              // group of 1024 elements
+        if (g * 1024 < count) {
+            unsigned v[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint4 r = *(const uint4 *)&sv[g * 1024 + lane * 32 + ((c ^ (lane & 7)) << 2)];
+                v[4 * c] = r.x; v[4 * c + 1] = r.y; v[4 * c + 2] = r.z; v[4 * c + 3] = r.w;
+            }
+            unsigned *region = sv + g * 1024;
+            const int gcount = count - g * 1024 < 1024 ? count - g * 1024 : 1024;
+            uint8_t *dst = out + (int64_t)d.chain * chain_stride + st.out_off + (((first + g * 1024) * bits) >> 3);
+            switch (bits) {
+#define MNW_CASE(B)                                                                         \
+    case B: {                                                                               \
+        unsigned o[B];                                                                      \
+        pack32<B>(v, o);                                                                    \
+        __syncwarp();                                                                       \
+        _Pragma("unroll") for (int j = 0; j < B; j++) {                                     \
+            const int W = lane * B + j;                                                     \
+            region[W ^ (W >> 5)] = o[j];                                                    \
+        }                                                                                   \
+        __syncwarp();                                                                       \
+        if (gcount == 1024) write_group<B>(dst, region, lane);                              \
+        else write_group_partial(dst, region, (gcount * B + 7) >> 3, lane);                 \
+    } break;
+                MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
+                MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
+                MNW_CASE(17) MNW_CASE(18) MNW_CASE(19) MNW_CASE(20) MNW_CASE(21) MNW_CASE(22) MNW_CASE(23) MNW_CASE(24)
+                MNW_CASE(25) MNW_CASE(26) MNW_CASE(27) MNW_CASE(28) MNW_CASE(29) MNW_CASE(30) MNW_CASE(31) MNW_CASE(32)
+#undef MNW_CASE
+                default: break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fast path for contiguous int64 blocks (intGroup.writeData, go/group.go:242-255): the same two passes with
+// coalesced 128-bit loads.  k_stats_i64c = int64Min + the max of ArrayBuffer.Bits; k_pack_i64c subtracts the
+// minimum (the difference of a block of <= 32 bits fits 32 bits) and packs with the warp packer of pack.cuh.
+// Blocks wider than 32 bits are left to k_pack.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FSTAT_THREADS)
+k_stats_i64c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape sh, const int *run_if) {
+    __shared__ long long s_r[FSTAT_THREADS / 32][2];
+    if (run_if && *run_if == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t chunk = blockIdx.x; chunk < sh.total_chunks; chunk += gridDim.x) {
+        const int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
+        const int64_t b = find_block(descs, sh, chunk, cpb, false);
+        const BlockDesc d = descs[b];
+        const int64_t first = (chunk - d.chunk0) * STATS_CHUNK;
+        const int count = (int)((first + STATS_CHUNK < d.n ? first + STATS_CHUNK : d.n) - first);
+        const long long *p = (const long long *)d.src + first;
+        const int a = (int)(((uintptr_t)p & 15) >> 3);          // 1: the chunk starts in the upper half of a 16-byte pair
+        const longlong2 *base2 = (const longlong2 *)(p - a);
+        const int nvec = (a + count + 1) >> 1;
+        long long mn = LLONG_MAX, mx = LLONG_MIN;
+#pragma unroll 4
+        for (int iv = threadIdx.x; iv < nvec; iv += FSTAT_THREADS) {
+            const longlong2 v = __ldcs(base2 + iv);
+            const int e0 = 2 * iv - a;
+            if (e0 >= 0) { mn = v.x < mn ? v.x : mn; mx = v.x > mx ? v.x : mx; }
+            if (e0 + 1 < count) { mn = v.y < mn ? v.y : mn; mx = v.y > mx ? v.y : mx; }
+        }
+        mn = warp_min_ll(mn); mx = warp_max_ll(mx);
+        if (lane == 0) { s_r[warp][0] = mn; s_r[warp][1] = mx; }
+        __syncthreads();
+        if (threadIdx.x == 0 && count > 0) {
+            for (int wi = 1; wi < FSTAT_THREADS / 32; wi++) {
+                mn = s_r[wi][0] < mn ? s_r[wi][0] : mn;
+                mx = s_r[wi][1] > mx ? s_r[wi][1] : mx;
+            }
+            atomicMin(&stats[b].qmin, mn);
+            atomicMax(&stats[b].qmax, mx);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(FPACK_THREADS, 4)
+k_pack_i64c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ stats, BatchShape sh,
+            uint8_t *out, int64_t chain_stride, int64_t chain_cap, int *err, const int *run_if) {
+    __shared__ __align__(16) unsigned sv[PACK_TILE];   // the tile's packed-to-be values, swizzled by 16-byte chunk
+    if (run_if && *run_if == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
+    for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
+        const int64_t b = find_block(descs, sh, tile, tpb, true);
+        const BlockStat st = stats[b];
+        const int bits = st.bits;
+        if (bits == 0 || bits > 32) continue;   // nothing to write / k_pack's
+        if (st.out_off + st.nbytes > chain_cap) {
+            if (threadIdx.x == 0) atomicExch(err, 2);
+            continue;
+        }
+        const BlockDesc d = descs[b];
+        const int64_t first = (tile - d.tile0) * PACK_TILE;
+        const int count = (int)(first + PACK_TILE <= d.n ? PACK_TILE : d.n - first);
+        const long long *p = (const long long *)d.src + first;
+        const int a = (int)(((uintptr_t)p & 15) >> 3);
+        const longlong2 *base2 = (const longlong2 *)(p - a);
+        const int nvec = (a + count + 1) >> 1;
+        const unsigned long long mn = (unsigned long long)st.min;
+        auto slot = [](int el) { const int L = el >> 5, i = el & 31; return (L << 5) + ((((i >> 2) ^ (L & 7)) << 2) | (i & 3)); };
+#pragma unroll 4
+        for (int iv = threadIdx.x; iv < nvec; iv += FPACK_THREADS) {
+            const longlong2 v = __ldcs(base2 + iv);
+            const int e0 = 2 * iv - a;
+            const unsigned v0 = (unsigned)((unsigned long long)v.x - mn), v1 = (unsigned)((unsigned long long)v.y - mn);   // go/group.go:246-247
+            if (a == 0 && e0 + 1 < count) {
+                *(uint2 *)&sv[slot(e0)] = make_uint2(v0, v1);   // an aligned pair shares a 16-byte chunk
+            } else {
+                if (e0 >= 0) sv[slot(e0)] = v0;
+                if (e0 + 1 < count) sv[slot(e0 + 1)] = v1;
+            }
+        }
+        for (int el = count + threadIdx.x; el < ((count + 1023) & ~1023); el += FPACK_THREADS) sv[slot(el)] = 0u;   // pad the last group
         __syncthreads();
         const int g = warp;                              // group of 1024 elements
         if (g * 1024 < count) {
@@ -1062,14 +1274,15 @@ static inline unsigned persistent_grid(int64_t units, int per_sm) {
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
-                           int64_t chain_cap, const int *run_if, bool f32c) {
+                           int64_t chain_cap, const int *run_if, bool f32c, bool i64c) {
     if (sh.nblocks == 0) return;
     cudaMemsetAsync(slow_count, 0, sizeof(int), L.stream);
     k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, run_if);
     L.count++;
     if (sh.total_chunks > 0) {
-        if (!run_if) L.begin(f32c ? "k_stats_f32c" : "k_stats");
+        if (!run_if) L.begin(f32c ? "k_stats_f32c" : (i64c ? "k_stats_i64c" : "k_stats"));
         if (f32c) k_stats_f32c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        else if (i64c) k_stats_i64c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
         else k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
         if (!run_if) L.end();
         L.count++;
@@ -1082,12 +1295,18 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     k_scan<<<(unsigned)sh.nchains, 1024, 0, L.stream>>>(stats, sh, mins, bits, offsets, out_len, run_if);
     L.count++;
     if (sh.total_tiles > 0) {
-        if (!run_if) L.begin(f32c ? "k_pack_f32c" : "k_pack");
+        if (!run_if) L.begin(f32c ? "k_pack_f32c" : (i64c ? "k_pack_i64c" : "k_pack"));
         if (f32c) k_pack_f32c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
+        else if (i64c) k_pack_i64c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
         else k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
                                                                                         run_if, nullptr, nullptr);
         if (!run_if) L.end();
         L.count++;
+        if (i64c) {   // blocks wider than 32 bits (k_pack skips the rest at once)
+            k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
+                                                                                       run_if, nullptr, nullptr, 32);
+            L.count++;
+        }
     }
 }
 
@@ -1121,6 +1340,58 @@ void launch_umax(Launcher &L, const unsigned long long *x, int64_t n, unsigned l
     L.count++;
 }
 
+// Decode of contiguous int64 blocks (Array.Slice + intGroup.readData, go/bit/bit.go:29-82, go/group.go:257-263): one
+// CTA per 4096-element tile; the tile's packed bytes are staged in shared memory with 128-bit loads, every thread
+// extracts four consecutive values and stores two 16-byte pairs.  Blocks wider than 32 bits take the 64-bit
+// extraction straight from global memory.
+__global__ void __launch_bounds__(FDEC_THREADS) k_decode_i64c(DecodeArgs A) {
+    __shared__ __align__(16) unsigned spk[DEC_CHUNK + 16];
+    const int64_t tpb = (A.n + DEC_CHUNK - 1) / DEC_CHUNK;
+    const int64_t j = blockIdx.x / tpb;
+    const int64_t tile = blockIdx.x - j * tpb;
+    const int64_t b = A.sel ? A.sel[j] : j;
+    const unsigned long long mn = (unsigned long long)A.mins[b];
+    const int bits = (int)A.bits[b];
+    const int64_t first = tile * DEC_CHUNK;
+    const int count = (int)(first + DEC_CHUNK <= A.n ? DEC_CHUNK : A.n - first);
+    long long *outp = (long long *)A.out + j * A.n + first;
+    if (bits <= 32) {
+        const unsigned mask = bits >= 1 ? (0xffffffffu >> (32 - bits)) : 0u;
+        unsigned shift0 = 0;
+        if (bits > 0) {
+            const uint8_t *src = A.data + A.offsets[b] + ((first * bits) >> 3);
+            const int a16 = (int)((uintptr_t)src & 15);
+            const uint4 *s16 = (const uint4 *)(src - a16);
+            const int nvec = (a16 + ((count * bits + 7) >> 3) + 15) >> 4;
+            for (int i = threadIdx.x; i < nvec; i += FDEC_THREADS) ((uint4 *)spk)[i] = __ldg(s16 + i);
+            shift0 = 8u * (unsigned)a16;
+        }
+        __syncthreads();
+        const bool vec_ok = (((uintptr_t)outp & 15) == 0);
+        for (int e4 = threadIdx.x * 4; e4 < count; e4 += FDEC_THREADS * 4) {
+            long long o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                unsigned v = 0;
+                if (bits) {
+                    const unsigned bp = shift0 + (unsigned)(e4 + c) * (unsigned)bits;
+                    v = __funnelshift_r(spk[bp >> 5], spk[(bp >> 5) + 1], bp) & mask;
+                }
+                o[c] = (long long)(mn + v);   // wrapping, like Go's int64 add
+            }
+            if (vec_ok && e4 + 4 <= count) {
+                __stcs((longlong2 *)(outp + e4), make_longlong2(o[0], o[1]));
+                __stcs((longlong2 *)(outp + e4 + 2), make_longlong2(o[2], o[3]));
+            } else {
+                for (int c = 0; c < 4; c++) if (e4 + c < count) outp[e4 + c] = o[c];
+            }
+        }
+    } else {
+        for (int el = threadIdx.x; el < count; el += FDEC_THREADS)
+            outp[el] = (long long)(mn + extract_bits(A.data, A.stream_len, A.offsets[b], first + el, bits));
+    }
+}
+
 cudaError_t launch_scan_sizes(Launcher &L, const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets,
                               int64_t *total) {
     k_scan_sizes<<<1, 1024, 0, L.stream>>>(sizes, n, base, offsets, total);
@@ -1143,6 +1414,13 @@ void launch_decode(Launcher &L, const DecodeHost &h) {
     if (h.mode == 1 && h.jmode != 2) {   // contiguous float32 blocks: staged, vectorised decode
         L.begin("k_decode_f32c");
         k_decode_f32c<<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
+        L.end();
+        L.count++;
+        return;
+    }
+    if (h.mode == 0) {   // contiguous int64 blocks: staged, vectorised decode
+        L.begin("k_decode_i64c");
+        k_decode_i64c<<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
         L.end();
         L.count++;
         return;

@@ -66,7 +66,7 @@ void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int6
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
-                           int64_t chain_cap, const int *run_if = nullptr, bool f32c = false);
+                           int64_t chain_cap, const int *run_if = nullptr, bool f32c = false, bool i64c = false);
 void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
                       const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,
                       int64_t chain_cap, int *err);
