@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
         }
 
         // ---- finalise: warp k combines the cluster's statistics of axis k (every CTA, redundantly) ----
-        long long f_off = 0, f_nbytes = 0, f_b = 0;   // warps 0..2 only
+        long long f_nbytes = 0, f_b = 0;   // warps 0..2 only
         if (warp < 3) {
             const int k = warp;
             f_b = f * 3 * A.sc3 + k * A.sc3 + sc;                    // block id in the batch

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         auto step_off = [&](int t) { return (unsigned)(t >> 2) * G.plane4 + (unsigned)(t & 3) * 16u * G.row4; };
 
         const size_t inc_rows = (size_t)16u * G.row4, inc_plane = (size_t)G.plane4 - (size_t)48u * G.row4;   // step t -> t + 1
-        float4 buf[4][3];
+        float4 buf[4][3] = {};
         const float4 *pr = nullptr;   // where the next refill comes from (step t + 5)
         const float4 *pq = nullptr;   // the same, PIPE_PFD steps further: what is pulled towards L2 now
         unsigned rank = 0, nrank = 0;
