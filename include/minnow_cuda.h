@@ -130,6 +130,20 @@ MNW_API int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *de
                                           int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
                                           int64_t out_cap, int64_t *out_len);
 
+/* All IntGroup / FloatGroup columns of ONE minh block in one call: the per-column loop of
+ * minh.Writer.Block (go/minh/minh.go:99-139, processFloatGroup :141-149 through desc.log10 / desc.clamp).
+ * Column c holds n values at data[c] (int64 when is_float == 0, float32 otherwise) and becomes one block of
+ * its own minnow group: mins[c], bits[c], nbytes[c] = what intGroup / floatGroup.writeData record, packed
+ * bytes at out + c * out_col_stride.  FloatGroup columns must be periodic (Writer.FloatGroup always is). */
+typedef struct {
+    int32_t is_float;
+    int32_t reserved;
+    mnw_float_desc desc;   /* FloatGroup columns only */
+} mnw_column;
+MNW_API int mnw_encode_columns(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const void *const *data,
+                               int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
+                               int64_t out_col_stride);
+
 /* Decode nsel blocks of one group.  data/offsets/mins/bits describe the whole
  * group (nblocks entries; offsets as produced above); sel lists the block ids
  * to decode (NULL = blocks 0..nsel-1); block sel[j] lands at out + j*n.

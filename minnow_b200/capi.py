@@ -30,6 +30,11 @@ class FloatDesc(C.Structure):
         return d
 
 
+class Column(C.Structure):
+    """mnw_column"""
+    _fields_ = [("is_float", C.c_int32), ("reserved", C.c_int32), ("desc", FloatDesc)]
+
+
 class Jitter(C.Structure):
     """mnw_jitter"""
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("block_id0", C.c_uint64),
@@ -59,6 +64,7 @@ SIGNATURES = {
     "mnw_selftest_fastdiv": (_int, [_p, _FD, C.c_uint32, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "mnw_minp_encode_vectors": (_int, [_p, _p, _i64, _i64, _int, _f32, _f32, _FD, _p, _p, _p, _p, _i64, _p]),
     "mnw_encode_int_group_gather": (_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_encode_columns": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64]),
     "mnw_encode_float_group_gather": (_int, [_p, _FD, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
@@ -269,6 +275,28 @@ class Context:
                                                         _ptr(mins), _ptr(bits), _ptr(offs), _ptr(out), len(out), C.byref(ln))
         self._check(rc)
         return mins, bits, offs, out[:ln.value].copy()
+
+    def encode_columns(self, columns):
+        """All quantised columns of one minh block in one call (minh.Writer.Block, go/minh/minh.go:99-139).
+        columns: list of (x, desc) with desc = None for an IntGroup column (x int64) or a FloatDesc (x float32);
+        all of one length.  -> mins, bits (int64 arrays) and the list of packed byte arrays, one per column."""
+        nc = len(columns)
+        arrs = [_np(x, np.float32 if d is not None else np.int64).reshape(-1) for x, d in columns]
+        n = len(arrs[0]) if nc else 0
+        if any(len(a) != n for a in arrs):
+            raise ValueError("columns of one block must have one length")
+        cols = (Column * max(nc, 1))()
+        ptrs = (C.c_void_p * max(nc, 1))()
+        for i, ((x, d), a) in enumerate(zip(columns, arrs)):
+            cols[i].is_float = 0 if d is None else 1
+            if d is not None:
+                cols[i].desc = d
+            ptrs[i] = a.ctypes.data if n else None
+        stride = 8 * n + 16
+        mins, bits, nbytes = (np.zeros(nc, np.int64) for _ in range(3))
+        out = np.zeros(max(nc * stride, 1), np.uint8)
+        self._check(self.lib.mnw_encode_columns(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), stride))
+        return mins, bits, [out[i * stride:i * stride + int(nbytes[i])].copy() for i in range(nc)]
 
     def decode_int_blocks(self, data, offsets, mins, bits, n, sel=None):
         """intGroup.readData per selected block (go/group.go:257-263)"""

@@ -242,6 +242,84 @@ int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const 
     return MNW_OK;
 }
 
+// minh.Writer.Block: every quantised column of one block in one batch (one chain per column, one block per chain).
+int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const void *const *data, int64_t n,
+                        int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out, int64_t out_col_stride) {
+    if (ncols < 0 || n < 0 || out_col_stride < 0) return fail(ctx, MNW_ERR_ARG, "negative column count, length or stride");
+    if (ncols == 0) return MNW_OK;
+    if (!cols || !data) return fail(ctx, MNW_ERR_ARG, "null column table");
+    const int64_t tpb = (n + PACK_TILE - 1) / PACK_TILE, cpb = (n + STATS_CHUNK - 1) / STATS_CHUNK;
+    if (ncols * tpb >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
+    std::vector<size_t> off((size_t)ncols);
+    size_t tot = 0;
+    bool any_f = false, any_i = false;
+    for (int64_t c = 0; c < ncols; c++) {
+        off[(size_t)c] = tot;
+        tot += ((size_t)(cols[c].is_float ? 4 : 8) * (size_t)n + 15) & ~(size_t)15;
+        if (!data[c] && n > 0) return fail(ctx, MNW_ERR_ARG, "column %lld has no data", (long long)c);
+        if (cols[c].is_float) {
+            int rc = check_desc(ctx, &cols[c].desc);
+            if (rc) return rc;
+            if (!cols[c].desc.periodic || cols[c].desc.pixels >= (1LL << 31))
+                return fail(ctx, MNW_ERR_ARG, "column %lld: mnw_encode_columns takes periodic FloatGroups with pixels < 2^31", (long long)c);
+            any_f = true;
+        } else {
+            any_i = true;
+        }
+    }
+    const size_t dstride = (((size_t)8 * (size_t)n + 15) & ~(size_t)15) + 16;   // ArrayBytes(bits <= 64, n) fits
+    CU(ctx->in.reserve(tot + 16));
+    CU(ctx->out.reserve(dstride * (size_t)ncols + 64));
+    int rc = reserve_batch(ctx, ncols, ncols);
+    if (rc) return rc;
+    int *d_flags = ctx->flags.as<int>();
+    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    std::vector<BlockDesc> hd((size_t)ncols);
+    for (int64_t c = 0; c < ncols; c++) {
+        BlockDesc d = {};
+        d.src = (const uint8_t *)ctx->in.p + off[(size_t)c];
+        d.n = n; d.access = ACC_CONTIG; d.chain = (int32_t)c;
+        d.tile0 = c * tpb; d.chunk0 = c * cpb;
+        if (cols[c].is_float) {
+            const FloatParamsHost fp = to_params(cols[c].desc);
+            d.kind = KIND_F32; d.flags = fp.flags;
+            d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
+        } else {
+            d.kind = KIND_I64;
+        }
+        hd[(size_t)c] = d;
+        if (n > 0) CU(cudaMemcpyAsync((uint8_t *)ctx->in.p + off[(size_t)c], data[c], (size_t)(cols[c].is_float ? 4 : 8) * (size_t)n,
+                                      cudaMemcpyHostToDevice, ctx->L.stream));
+    }
+    CU(cudaMemcpyAsync(ctx->descs.p, hd.data(), sizeof(BlockDesc) * (size_t)ncols, cudaMemcpyHostToDevice, ctx->L.stream));
+    BatchShape sh = {};
+    sh.nblocks = ncols; sh.nchains = ncols; sh.blocks_per_chain = 1; sh.uniform_n = n;
+    sh.total_tiles = ncols * tpb; sh.total_chunks = ncols * cpb;
+    ctx->last_path = 0;
+    int64_t *d_meta = ctx->meta.as<int64_t>();
+    int64_t *d_mins = d_meta, *d_bits = d_meta + ncols, *d_offs = d_meta + 2 * ncols, *d_len = d_meta + 3 * ncols;
+    const bool fast = !ctx->force_generic;
+    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
+                          d_flags, d_flags + 1, d_mins, d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride,
+                          (int64_t)dstride, nullptr, fast && any_f, fast && any_i);
+    CU(cudaGetLastError());
+    std::vector<int64_t> h_meta(4 * (size_t)ncols);
+    CU(cudaMemcpyAsync(h_meta.data(), d_meta, h_meta.size() * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    rc = check_flags(ctx);   // synchronises
+    if (rc) return rc;
+    for (int64_t c = 0; c < ncols; c++) {
+        const int64_t len = h_meta[3 * (size_t)ncols + (size_t)c];
+        if (mins) mins[c] = h_meta[(size_t)c];
+        if (bits) bits[c] = h_meta[(size_t)ncols + (size_t)c];
+        if (nbytes) nbytes[c] = len;
+        if (len > out_col_stride) return fail(ctx, MNW_ERR_CAPACITY, "column %lld needs %lld bytes, stride is %lld", (long long)c, (long long)len, (long long)out_col_stride);
+        if (len > 0) CU(cudaMemcpyAsync(out + c * out_col_stride, ctx->out.as<uint8_t>() + (size_t)c * dstride, (size_t)len,
+                                        cudaMemcpyDeviceToHost, ctx->L.stream));
+    }
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
 int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, int64_t ndesc, const mnw_jitter *jitter) {
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
@@ -459,6 +537,13 @@ int mnw_encode_float_group(mnw_ctx *ctx, const mnw_float_desc *desc, const float
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
     return encode_group_host(ctx, KIND_F32, desc, x, n, nblocks, starts, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_encode_columns(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const void *const *data, int64_t n,
+                       int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out, int64_t out_col_stride) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
+    return encode_columns_host(ctx, ncols, cols, data, n, mins, bits, nbytes, out, out_col_stride);
 }
 
 int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, const int64_t *idx, int64_t nblocks,

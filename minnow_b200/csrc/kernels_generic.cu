@@ -821,6 +821,7 @@ k_stats_f32c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape s
         const int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
         const int64_t b = find_block(descs, sh, chunk, cpb, false);
         const BlockDesc d = descs[b];
+        if (d.kind != KIND_F32) continue;   // a column batch mixes kinds: int64 blocks are k_stats_i64c's
         const int64_t first = (chunk - d.chunk0) * STATS_CHUNK;
         const int count = (int)((first + STATS_CHUNK < d.n ? first + STATS_CHUNK : d.n) - first);
         const QuantP qp = quant_params(d);
@@ -924,6 +925,7 @@ k_pack_f32c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
     const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
     for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
         const int64_t b = find_block(descs, sh, tile, tpb, true);
+        if (descs[b].kind != KIND_F32) continue;   // int64 blocks of a column batch are k_pack_i64c's
         const BlockStat st = stats[b];
         const int bits = st.bits;
         if (bits == 0 || bits > 32) continue;   // nothing to write / left to k_pack (not reachable for pixels < 2^31)
@@ -1046,6 +1048,7 @@ k_stats_i64c(const BlockDesc *__restrict__ descs, BlockStat *stats, BatchShape s
         const int64_t cpb = sh.uniform_n > 0 ? (sh.uniform_n + STATS_CHUNK - 1) / STATS_CHUNK : 0;
         const int64_t b = find_block(descs, sh, chunk, cpb, false);
         const BlockDesc d = descs[b];
+        if (d.kind != KIND_I64) continue;
         const int64_t first = (chunk - d.chunk0) * STATS_CHUNK;
         const int count = (int)((first + STATS_CHUNK < d.n ? first + STATS_CHUNK : d.n) - first);
         const long long *p = (const long long *)d.src + first;
@@ -1084,6 +1087,7 @@ k_pack_i64c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
     const int64_t tpb = sh.uniform_n > 0 ? (sh.uniform_n + PACK_TILE - 1) / PACK_TILE : 0;
     for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
         const int64_t b = find_block(descs, sh, tile, tpb, true);
+        if (descs[b].kind != KIND_I64) continue;
         const BlockStat st = stats[b];
         const int bits = st.bits;
         if (bits == 0 || bits > 32) continue;   // nothing to write / k_pack's
@@ -1280,10 +1284,12 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     k_init<<<grid_for(sh.nblocks, 256), 256, 0, L.stream>>>(descs, stats, sh.nblocks, run_if);
     L.count++;
     if (sh.total_chunks > 0) {
+        // f32c and i64c together: a batch of columns of both kinds, each kernel skips the other's blocks
         if (!run_if) L.begin(f32c ? "k_stats_f32c" : (i64c ? "k_stats_i64c" : "k_stats"));
         if (f32c) k_stats_f32c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
-        else if (i64c) k_stats_i64c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
-        else k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        if (i64c) k_stats_i64c<<<persistent_grid(sh.total_chunks, 8), FSTAT_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
+        if (f32c && i64c) L.count++;
+        if (!f32c && !i64c) k_stats<<<persistent_grid(sh.total_chunks, 16), STATS_THREADS, 0, L.stream>>>(descs, stats, sh, run_if);
         if (!run_if) L.end();
         L.count++;
     }
@@ -1297,8 +1303,9 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
     if (sh.total_tiles > 0) {
         if (!run_if) L.begin(f32c ? "k_pack_f32c" : (i64c ? "k_pack_i64c" : "k_pack"));
         if (f32c) k_pack_f32c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
-        else if (i64c) k_pack_i64c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
-        else k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
+        if (i64c) k_pack_i64c<<<persistent_grid(sh.total_tiles, 12), FPACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err, run_if);
+        if (f32c && i64c) L.count++;
+        if (!f32c && !i64c) k_pack<<<persistent_grid(sh.total_tiles, 12), PACK_THREADS, 0, L.stream>>>(descs, stats, sh, out, chain_stride, chain_cap, err,
                                                                                         run_if, nullptr, nullptr);
         if (!run_if) L.end();
         L.count++;

@@ -7,7 +7,7 @@ import struct
 import numpy as np
 
 from . import minnow
-from .capi import FloatDesc, array_bytes
+from .capi import FloatDesc, array_bytes, float_group_pixels
 
 Magic = 0xbaff1ed         # go/minh/minh.go:13-16
 Version = 0
@@ -55,21 +55,38 @@ class Writer:
         self.block_sizes.append(N)
         self.blocks += 1
         w = self.f
-        for x, col in zip(cols, self.cols):
+        # every IntGroup / FloatGroup column of the block goes to the GPU in ONE call (mnw_encode_columns);
+        # processFloatGroup (:141-149) runs inside the quantise kernels (desc.log10, desc.clamp)
+        quant, descs = [], {}
+        for i, (x, col) in enumerate(zip(cols, self.cols)):
+            t = int(col["Type"])
+            if t == minnow.IntGroup:
+                quant.append((i, (np.asarray(x, np.int64), None)))
+            elif t == minnow.FloatGroup:
+                lo, hi = np.float32(col["Low"]), np.float32(col["High"])
+                d = FloatDesc.make(lo, hi, float_group_pixels(lo, hi, np.float32(col["Dx"])), 1, 1 if col["Log"] != 0 else 0, 1)
+                quant.append((i, (np.asarray(x, np.float32), d)))
+            elif t not in minnow._FIXED:
+                raise ValueError("Unrecognized group type, %d." % t)
+        enc = {}
+        if quant and N > 0:
+            mins, bits, packed = self.ctx.encode_columns([q for _, q in quant])
+            enc = {i: (mins[j], bits[j], packed[j]) for j, (i, _) in enumerate(quant)}
+        for i, (x, col) in enumerate(zip(cols, self.cols)):
             t = int(col["Type"])
             if t in minnow._FIXED:
                 w.FixedSizeGroup(t, N)
                 w.Data(np.asarray(x, minnow._FIXED[t]))
             elif t == minnow.IntGroup:
                 w.IntGroup(N)
-                w.Data(np.asarray(x, np.int64))
-            elif t == minnow.FloatGroup:
-                w.FloatGroup(N, (col["Low"], col["High"]), col["Dx"])
-                w.curr.log10 = 1 if col["Log"] != 0 else 0     # processFloatGroup runs inside the quantise kernel
-                w.curr.clamp = 1
-                w.Data(np.asarray(x, np.float32))
+                if i in enc: w.EncodedBlock(*enc[i])
+                else: w.Data(np.asarray(x, np.int64))
             else:
-                raise ValueError("Unrecognized group type, %d." % t)
+                w.FloatGroup(N, (col["Low"], col["High"]), col["Dx"])
+                w.curr.log10 = 1 if col["Log"] != 0 else 0
+                w.curr.clamp = 1
+                if i in enc: w.EncodedBlock(*enc[i])
+                else: w.Data(np.asarray(x, np.float32))
 
     def Close(self):                                                                         # :151-156
         self.f.Header(struct.pack("<ffq", self.l, self.boundary, self.cells))

@@ -136,6 +136,18 @@ class Writer:
         self.group_blocks[-1] += k
         self.blocks += k
 
+    def EncodedBlock(self, mn, bits, data):
+        """One block of the current IntGroup / FloatGroup that was encoded elsewhere (minh.Writer.Block encodes all
+        columns of a block in one GPU call): what writeData records, go/group.go:249-254."""
+        g = self.curr
+        if g is None or g.gt in _FIXED:
+            raise RuntimeError("EncodedBlock needs a current IntGroup or FloatGroup")
+        self.f.write(bytes(data))
+        g.mins.append(int(mn)); g.bits.append(int(bits)); g.sizes.append(array_bytes(int(bits), g.N))
+        self.group_blocks[-1] += 1
+        self.blocks += 1
+        return self.blocks - 1
+
     def _write_int_array_tail(self, x):
         """`write` closure of intGroup.writeTail, go/group.go:216-224: min, bits, packed (x - min)."""
         x = np.asarray(x, np.int64)

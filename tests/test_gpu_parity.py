@@ -321,3 +321,29 @@ def test_group_gather_matches_encode_of_gathered_copy(ctx, orc):
     assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo) and data.tobytes() == od.tobytes()
     with pytest.raises(mb.MinnowError):
         ctx.encode_group_gather(ids, np.array([0, ncol], np.int64), np.array([0, 2], np.int64))
+
+
+def test_encode_columns_matches_per_column_calls(ctx):
+    """mnw_encode_columns (one call per minh.Writer.Block) = the per-column group encodes, byte for byte: mixed int64 /
+    float32 columns, a log10 + clamp column, a constant column (0 bits), an int column wider than 32 bits"""
+    rng = np.random.default_rng(77)
+    for n in (1, 4097, 70001):
+        px = mb.float_group_pixels(0.0, 125.0, 0.001)
+        cols = [
+            (rng.integers(10 ** 9, 10 ** 9 + 10 ** 6, n).astype(np.int64), None),
+            ((rng.random(n) * 125.0).astype(np.float32), mb.FloatDesc.make(0.0, 125.0, px)),
+            (np.power(10.0, 10.0 + 5.0 * rng.random(n)).astype(np.float32),
+             mb.FloatDesc.make(10.0, 15.0, mb.float_group_pixels(10.0, 15.0, 0.01), 1, 1, 1)),
+            (np.full(n, 7, np.int64), None),
+            (rng.integers(-2 ** 60, 2 ** 60, n).astype(np.int64), None),
+            ((rng.random(n) * 300.0 - 100.0).astype(np.float32), mb.FloatDesc.make(0.0, 125.0, px, 1, 0, 1)),   # clamped
+        ]
+        mins, bits, packed = ctx.encode_columns(cols)
+        for c, (x, d) in enumerate(cols):
+            if d is None:
+                m, b, o, data = ctx.encode_int_group(x, n, 1)
+            else:
+                m, b, o, data = ctx.encode_float_group(d, x, n, 1)
+            assert (int(mins[c]), int(bits[c])) == (int(m[0]), int(b[0])), (n, c)
+            assert packed[c].tobytes() == data.tobytes(), (n, c)
+    assert ctx.encode_columns([])[2] == []

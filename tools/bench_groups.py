@@ -91,6 +91,29 @@ def main():
     ms_e = timed(enc); ms_d = timed(de)
     report("C1 FloatGroup, 2^20 halos as 16 blocks x 65536 (L2 resident, launch bound)", n1 * nb1, 4, int(out_len.item()), ms_e, ms_d)
 
+    # ---- C3: one minh block, the 30 quantised columns of the text_to_minh type menu (6 IntGroup, 12 position
+    # FloatGroups, 12 log10 FloatGroups) x 2^22 rows, host buffers: one mnw_encode_columns call vs 30 group calls ----
+    import time
+    n3 = 1 << 22
+    rng = np.random.default_rng(3)
+    px = mb.float_group_pixels(0.0, 125.0, 0.001)
+    dpos = mb.FloatDesc.make(0.0, 125.0, px, 1, 0, 1)
+    dlog = mb.FloatDesc.make(10.0, 15.0, mb.float_group_pixels(10.0, 15.0, 0.01), 1, 1, 1)
+    ids0 = (np.arange(n3, dtype=np.int64) * 3 + rng.integers(0, 3, n3)) + 10 ** 9
+    pos0 = (rng.random(n3) * 125.0).astype(np.float32)
+    mass0 = np.power(10.0, 10.0 + 5.0 * rng.random(n3)).astype(np.float32)
+    cols3 = [(ids0 + k, None) for k in range(6)] + [(np.roll(pos0, k), dpos) for k in range(12)] + [(np.roll(mass0, k), dlog) for k in range(12)]
+    raw_bytes = sum(a.nbytes for a, _ in cols3)
+    def per_column():
+        for a, d in cols3:
+            if d is None: ctx.encode_int_group(a, n3, 1)
+            else: ctx.encode_float_group(d, a, n3, 1)
+    for name, fn in (("30 group calls", per_column), ("one mnw_encode_columns call", lambda: ctx.encode_columns(cols3))):
+        fn()
+        t0 = time.perf_counter(); fn(); fn(); dt = (time.perf_counter() - t0) / 2
+        print(json.dumps({"case": "C3 minh block, 30 quantised columns x 2^22 rows, host buffers (pageable): " + name,
+                          "ms": dt * 1e3, "GBs_uncompressed_e2e": raw_bytes / dt / 1e9}))
+
     # ---- C4: random access, 10^4 selected blocks of 4096 values out of 98304 ----
     n4, nb4, nsel = 4096, 3 * 32768, 10000
     x4 = (torch.rand(n4 * nb4, generator=g, device=dev, dtype=torch.float32) * 0.3 +
