@@ -26,13 +26,25 @@ def headers():
 
 
 def build_library(force=False, verbose=False):
+    """nvcc -> libminnow_b200.so; the translation units are compiled in parallel (one nvcc each) and linked."""
     deps = sources() + headers() + [os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-D" + d for d in os.environ.get("MNW_DEFINES", "").split() if d]   # e.g. MNW_DEFINES=MNW_PIPE_DBG
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + sources()
-    subprocess.check_call(cmd)
+    flags = NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
+    objdir = os.path.join(CSRC, "_build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        subprocess.check_call([nvcc] + flags + ["-c", "-o", obj, src])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    subprocess.check_call([nvcc] + flags + ["-shared", "-o", LIB] + objs)
     return LIB
 
 
