@@ -1192,21 +1192,36 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
         __syncthreads();
         const bool vec_ok = (((uintptr_t)outp & 15) == 0);
         const unsigned Pp = periodic ? (unsigned)P : 0u, mn32 = (unsigned)mn;
+        // A thread's four values move on by FDEC_THREADS * 4 elements per iteration = a whole number of 32-bit words:
+        // the shift within the word is constant, the word index and the hash argument advance by constants.
+        unsigned wi[4], sh[4], hx[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const unsigned el0 = (unsigned)(threadIdx.x * 4 + c);
+            const unsigned bp0 = shift0 + el0 * (unsigned)bits;
+            wi[c] = bp0 >> 5; sh[c] = bp0 & 31u;
+            hx[c] = ((unsigned)first + el0) * 0x9E3779B1U + key;
+        }
+        const unsigned dW = (unsigned)(FDEC_THREADS * 4 / 32) * (unsigned)bits;
+        const bool hash = A.jmode == 1;
         for (int e4 = threadIdx.x * 4; e4 < count; e4 += FDEC_THREADS * 4) {
             float o[4];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const unsigned el = (unsigned)(e4 + c);
-                unsigned v = 0;
-                if (bits) {
-                    const unsigned bp = shift0 + el * (unsigned)bits;
-                    v = __funnelshift_r(spk[bp >> 5], spk[(bp >> 5) + 1], bp) & mask;   // Array.Slice, go/bit/bit.go:29-82
-                }
+                const unsigned v = __funnelshift_r(spk[wi[c]], spk[wi[c] + 1], sh[c]) & mask;   // Array.Slice, go/bit/bit.go:29-82
+                wi[c] += dW;
                 unsigned q = mn32 + v;                                                   // go/group.go:262
                 q = min(q, q - Pp);                                                      // bound(q, 0, pixels), :303
                 float t;
-                if (A.jmode == 1) t = __fmaf_rn((float)(jitter_hash_keyed(key, (unsigned)first + el) >> 8), 0x1p-24f, (float)q);
-                else t = __fadd_rn((float)q, 0.5f);
+                if (hash) {
+                    unsigned x = hx[c];
+                    hx[c] += (unsigned)(FDEC_THREADS * 4) * 0x9E3779B1U;
+                    x ^= x >> 16; x *= 0x7feb352dU;                                      // jitter_hash_keyed (device_math.cuh)
+                    x ^= x >> 15; x *= 0x846ca68bU;
+                    t = __fmaf_rn((float)(x >> 8), 0x1p-24f, (float)q);
+                } else {
+                    t = __fadd_rn((float)q, 0.5f);
+                }
                 o[c] = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);                            // :308
             }
             if (vec_ok && e4 + 4 <= count) {
