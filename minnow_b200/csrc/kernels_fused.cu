@@ -42,6 +42,20 @@ namespace mnw {
 
 namespace {
 
+// Tickets walk the files round-robin in chunks of G consecutive sub-cells (ticket t -> chunk t / G, sub-cell
+// (chunk / nfiles) * G + t % G of file chunk % nfiles): the predecessor of a unit in its look-back chain (the previous
+// sub-cell of its file) is then about G * nfiles tickets old for the first unit of a chunk instead of the ticket just
+// before it -- and still always claimed earlier (running or done) -- while the G units of a chunk, neighbours in x
+// whose rows are contiguous in memory, are read at the same time.  G = sc3 is the plain file-by-file order.
+// Tickets beyond the batch map to themselves.
+__device__ __forceinline__ long long claim_unit(const FusedArgs &A) {
+    const long long t = (long long)atomicAdd(A.W.ticket, 1u);
+    if (t >= A.nunits) return t;
+    const long long nfiles = A.nunits / A.sc3, G = A.ticket_chunk;
+    const long long c = t / G, w = t - c * G;
+    return (c % nfiles) * A.sc3 + (c / nfiles) * G + w;
+}
+
 // Batch-local statistics of phase 1, in the thread's relative axis order.
 struct LocalStat {
     unsigned wmin[3], wmax[3];
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     int par = 0, gen = 1;
     if (tid < 3) s_offgen[tid] = 0;
     if (rank == 0 && tid == 0) {
-        const long long u = (long long)atomicAdd(A.W.ticket, 1u);
+        const long long u = claim_unit(A);
         if constexpr (CS > 1) {
             for (unsigned r = 0; r < CS; r++) *cg::this_cluster().map_shared_rank(&s_unit[0], r) = u;
         } else {
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
             else s_x[par][0][k] = x;
         }
         if (rank == 0 && tid == 32) {   // claim the next unit for the whole cluster
-            const long long u = (long long)atomicAdd(A.W.ticket, 1u);
+            const long long u = claim_unit(A);
             if constexpr (CS > 1) {
                 for (unsigned r = 0; r < CS; r++) *cg::this_cluster().map_shared_rank(&s_unit[par ^ 1], r) = u;
             } else {
@@ -1185,6 +1199,12 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
     A.nunits = nfiles * A.sc3;
     A.stats = stats; A.mins = mins; A.bits = bits; A.offsets = offsets; A.out_len = out_len; A.out = out;
     A.axis_stride = out_axis_stride; A.W = W;
+    {   // chunk of the ticket order (claim_unit)
+        static const int knob = getenv("MNW_TICKET_CHUNK") ? atoi(getenv("MNW_TICKET_CHUNK")) : 0;   // tuning knob
+        long long G = knob > 0 ? knob : 1;   // measured best on 16^3 and 32^3 sub-cells (tools/bench_subcells.py): plain round-robin
+        if (G < 1 || A.sc3 % G != 0) G = 1;
+        A.ticket_chunk = (int)G;
+    }
     static const int prefetch = getenv("MNW_PREFETCH") ? atoi(getenv("MNW_PREFETCH")) : 1;   // tuning knob
     A.prefetch = prefetch;
     if (A.nunits == 0) return cudaSuccess;
@@ -1216,7 +1236,14 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
             return launch_fused_vec3_t<64, 8, 384, 4, 1, true>(L, A);
         }
         case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
-        case 16: return launch_fused_vec3_t<16, 1, 384, 4, 1, true>(L, A);
+        case 16: {
+            // a 16^3 unit stages 24 KB only: several CTAs per SM hide each other's read -> barrier -> pack phases
+            static const int minb = getenv("MNW_FUSED16_MINB") ? atoi(getenv("MNW_FUSED16_MINB")) : 1;   // tuning knob
+            if (minb == 2) return launch_fused_vec3_t<16, 1, 384, 4, 2, true>(L, A);
+            if (minb == 3) return launch_fused_vec3_t<16, 1, 384, 4, 3, false>(L, A);
+            if (minb == 4) return launch_fused_vec3_t<16, 1, 384, 2, 4, false>(L, A);
+            return launch_fused_vec3_t<16, 1, 384, 4, 1, true>(L, A);
+        }
     }
     return cudaErrorNotSupported;
 }
