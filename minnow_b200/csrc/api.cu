@@ -681,7 +681,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
             // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
             void *coop_ws = nullptr;
             const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
-            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256)) {
+            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32) {   // 32^3 units are single CTAs: no exclusivity to worry about
                 CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
                 coop_ws = ctx->flat_ws.p;
             }

@@ -1187,7 +1187,7 @@ static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
 }
 
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A);   // kernels_pipe.cu
-cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws);
+cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws, int nsub);
 
 cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams *tab, int tab_per_file,
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
@@ -1218,7 +1218,7 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
                 // keeps the 8-CTA cluster schedule); it falls back to the clusters when the device refuses the launch
                 static const bool coop = !(getenv("MNW_PIPE") && !strcmp(getenv("MNW_PIPE"), "cluster"));
                 if (pipe_ok && coop && coop_ws) {
-                    const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws);
+                    const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 64);
                     if (e == cudaSuccess) return e;
                     (void)cudaGetLastError();
                 }
@@ -1235,7 +1235,16 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
             if (variant == 385) return launch_fused_vec3_t<64, 8, 384, 8, 1, false>(L, A);
             return launch_fused_vec3_t<64, 8, 384, 4, 1, true>(L, A);
         }
-        case 32: return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
+        case 32: {
+            // a 32^3 sub-cell is one CTA's worth of the pipeline (k_pipe_vec3<COOP, 32>, one part per unit)
+            static const bool pipe32 = !(getenv("MNW_PIPE") && !strcmp(getenv("MNW_PIPE"), "cluster"));
+            if (pipe_ok && pipe32 && coop_ws) {
+                const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 32);
+                if (e == cudaSuccess) return e;
+                (void)cudaGetLastError();
+            }
+            return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
+        }
         case 16: {
             // a 16^3 unit stages 24 KB only: several CTAs per SM hide each other's read -> barrier -> pack phases
             static const int minb = getenv("MNW_FUSED16_MINB") ? atoi(getenv("MNW_FUSED16_MINB")) : 1;   // tuning knob

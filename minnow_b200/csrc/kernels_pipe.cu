@@ -9,7 +9,7 @@ namespace mnw {
 #include "pipe_vec3.cuh"
 
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
-    auto kern = k_pipe_vec3<false>;
+    auto kern = k_pipe_vec3<false, 64>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
     static bool configured = false;
     static int max_clusters = 0;
@@ -59,8 +59,10 @@ cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
 // caller then takes the cluster kernel.
 size_t pipe_coop_ws_bytes(int64_t nunits) { return (size_t)nunits * 64; }
 
-cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws) {
-    auto kern = k_pipe_vec3<true>;
+template <int NSUB>
+static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
+    constexpr int PARTS = NSUB == 64 ? 8 : 1;
+    auto kern = k_pipe_vec3<true, NSUB>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
     static int grid_max = -1;
     cudaError_t e;
@@ -73,12 +75,12 @@ cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws) {
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_NT, smem);
         if (e != cudaSuccess) return e;
-        grid_max = (coop && per_sm >= 1) ? (sms / 8) * 8 : 0;
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop>: grid %d, %zu B dynamic smem\n", grid_max, smem);
+        grid_max = (coop && per_sm >= 1) ? (sms / PARTS) * PARTS : 0;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop, %d>: grid %d, %zu B dynamic smem\n", NSUB, grid_max, smem);
     }
-    if (grid_max < 8) return cudaErrorNotSupported;
-    const long long items = 8 * A.nunits;
-    const unsigned grid = (unsigned)(items < grid_max ? items : grid_max);   // >= 8: no CTA ever holds two parts of a unit
+    if (grid_max < PARTS) return cudaErrorNotSupported;
+    const long long items = PARTS * A.nunits;
+    const unsigned grid = (unsigned)(items < grid_max ? items : grid_max);   // >= PARTS: no CTA ever holds two parts of a unit
     A.ustat = (unsigned *)ws;
     e = cudaMemsetAsync(ws, 0, pipe_coop_ws_bytes(A.nunits), L.stream);
     if (e != cudaSuccess) return e;
@@ -88,6 +90,10 @@ cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws) {
     L.end();
     L.count++;
     return e;
+}
+
+cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws, int nsub) {
+    return nsub == 32 ? launch_pipe_vec3_coop_t<32>(L, A, ws) : launch_pipe_vec3_coop_t<64>(L, A, ws);
 }
 
 bool pipe_vec3_supported(const FloatParamsHost *fp, int64_t nparams) {

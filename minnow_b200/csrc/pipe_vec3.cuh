@@ -155,12 +155,13 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // Where a unit (file f, sub-cell sc) starts in the AoS input, in float4 units within its file.
 struct PipeGeom {
     int S, nfile;
+    unsigned nsub;   // 64 or 32
     unsigned row4, plane4;
     long long sc3;
     __device__ __forceinline__ const float4 *origin(const float *aos, long long unit, long long &f, unsigned &sc) const {
         f = unit / sc3;
         sc = (unsigned)(unit - f * sc3);
-        const unsigned ix0 = 64u * (sc % (unsigned)S), iy0 = 64u * ((sc / (unsigned)S) % (unsigned)S), iz0 = 64u * (sc / (unsigned)(S * S));
+        const unsigned ix0 = nsub * (sc % (unsigned)S), iy0 = nsub * ((sc / (unsigned)S) % (unsigned)S), iz0 = nsub * (sc / (unsigned)(S * S));
         return (const float4 *)(aos + 3 * f * (long long)nfile * nfile * nfile) + (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4);
     }
 };
@@ -169,7 +170,7 @@ struct PipeGeom {
 // fast quantiser).  The warp works on one such thread at a time, lane j redoing step j (4 particles) with
 // the IEEE divide, so the 384 elements cost a couple of memory round trips instead of 384.  The thread's
 // statistics come back in the same form as the fast path (raw-bit domain: FMAGIC + q).
-__device__ __noinline__ void pipe_redo_warp(unsigned bad_mask, const float4 *tbase, unsigned row4, unsigned plane4,
+__device__ __noinline__ void pipe_redo_warp(unsigned bad_mask, const float4 *tbase, unsigned step_lo, unsigned step_hi, int steps_per_hi,
                                             const PipePar *par, unsigned short *stage, int e_thread,
                                             unsigned *st /*[12]*/, unsigned *oob_out) {
     const int lane = threadIdx.x & 31;
@@ -187,7 +188,7 @@ __device__ __noinline__ void pipe_redo_warp(unsigned bad_mask, const float4 *tba
             if (par[k].oob0) oob = 1;
         }
         const int t = lane;
-        const float4 *src4 = tb + ((unsigned)(t >> 2) * plane4 + (unsigned)(t & 3) * 16u * row4);
+        const float4 *src4 = tb + ((unsigned)(t / steps_per_hi) * step_hi + (unsigned)(t % steps_per_hi) * step_lo);
         const float4 v0 = __ldg(src4), v1 = __ldg(src4 + 1), v2 = __ldg(src4 + 2);
         const float x[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
@@ -280,9 +281,15 @@ __device__ __forceinline__ void emit_group(const unsigned (&f)[16], unsigned *bu
 // eight parts of a unit meet through a 64-byte record in global memory (atomicMax on the statistics, a
 // counter, ld.acquire polling).  Every CTA looks its offsets up itself.  This uses all SMs (144 of 148)
 // instead of the 120 that 8-CTA clusters reach; a part only ever waits for items with a smaller g.
-template <bool COOP>
+// NSUB = 32 (COOP only): a 32^3 sub-cell is exactly one CTA's 32768 particles, PARTS = 1: rows of 32 particles, 8 lanes per row,
+// one z-plane per step; the staging layout, the packers and the look-back are the same.
+template <bool COOP, int NSUB>
 __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
-    constexpr int N = 64 * 64 * 64, CHUNK = PIPE_CHUNK, CS = PIPE_CS;
+    static_assert(NSUB == 64 || (NSUB == 32 && COOP), "32^3 sub-cells run one CTA per unit");
+    constexpr int N = NSUB * NSUB * NSUB, CHUNK = PIPE_CHUNK, CS = PIPE_CS;
+    constexpr int PARTS = NSUB == 64 ? 8 : 1;                 // CTAs per unit
+    constexpr int LPR = NSUB / 4;                             // lanes per row (4 particles each): 16 or 8
+    constexpr int SPP = NSUB / (8 * 32 / LPR);                // steps per z-plane: 4 or 1
     constexpr int LT = 32 * PIPE_LW, PT = 32 * (PIPE_PW + 1);   // loader threads; packer + scanner threads
     constexpr int NGROUPS = 3 * (CHUNK / 1024);   // pack groups per CTA and unit
     constexpr int UM = PIPE_USLOTS - 1;
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     unsigned crank = 0;
     if constexpr (!COOP) crank = cg::this_cluster().block_rank();
     PipeGeom G;
-    G.S = A.subcells; G.nfile = A.nfile; G.sc3 = A.sc3;
+    G.S = A.subcells; G.nfile = A.nfile; G.sc3 = A.sc3; G.nsub = NSUB;
     G.row4 = 3u * (unsigned)A.nfile / 4u; G.plane4 = G.row4 * (unsigned)A.nfile;
 
     // x[0] of every axis block of `unit`, its rotation constant and the quantiser parameters
@@ -353,9 +360,9 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     auto unit_at = [&](int i, unsigned &rk) -> long long {
         if constexpr (COOP) {
             const long long g = (long long)blockIdx.x + (long long)gridDim.x * i;
-            rk = (unsigned)(g & 7);
-            if (g >= 8 * A.nunits) return A.nunits;
-            const long long up = g >> 3;
+            rk = (unsigned)(g % PARTS);
+            if (g >= PARTS * A.nunits) return A.nunits;
+            const long long up = g / PARTS;
             return (up % nfiles) * A.sc3 + up / nfiles;
         } else {
             mbar_wait_cluster(&bar_unit[i & UM], (i / PIPE_USLOTS) & 1);
@@ -387,14 +394,16 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_LREGS));
         // lane geometry: step t covers rows 16 t .. 16 t + 15 of the CTA's 512; warp w rows 2 w, 2 w + 1
         // of those, lane l particles 4 (l & 15) .. + 3 of row (l >> 4)
-        const unsigned toff0 = (unsigned)(2 * warp + (lane >> 4)) * G.row4 + 3u * (unsigned)(lane & 15);
-        auto toff = [&](unsigned rk) { return rk * 8u * G.plane4 + toff0; };   // rk: which eighth of the unit
+        const unsigned toff0 = (unsigned)((32 / LPR) * warp + lane / LPR) * G.row4 + 3u * (unsigned)(lane % LPR);
+        auto toff = [&](unsigned rk) { return rk * 8u * G.plane4 + toff0; };   // rk: which eighth of the unit (64^3)
         const int e_thread = 128 * warp + 4 * lane;   // element of the thread's first particle at step 0
         // byte offset of that element's 8-byte piece in an axis' staging array (chunk swizzle c ^ ((c >> 3) & 7))
         const unsigned sbyte = (unsigned)((((e_thread >> 3) ^ ((e_thread >> 6) & 7)) << 4) + ((lane & 1) << 3));
-        auto step_off = [&](int t) { return (unsigned)(t >> 2) * G.plane4 + (unsigned)(t & 3) * 16u * G.row4; };
+        const unsigned step_lo = (unsigned)(8 * 32 / LPR) * G.row4;   // rows of one step: 16 (64^3) or 32 = a whole plane (32^3)
+        auto step_off = [&](int t) { return (unsigned)(t / SPP) * G.plane4 + (unsigned)(t % SPP) * step_lo; };
 
-        const size_t inc_rows = (size_t)16u * G.row4, inc_plane = (size_t)G.plane4 - (size_t)48u * G.row4;   // step t -> t + 1
+        // step t -> t + 1: the next rows of the plane, or (every SPP-th step) on to the next plane
+        const size_t inc_rows = SPP == 1 ? (size_t)G.plane4 : (size_t)step_lo, inc_plane = (size_t)G.plane4 - (size_t)(SPP - 1) * step_lo;
         float4 buf[4][3] = {};
         const float4 *pr = nullptr;   // where the next refill comes from (step t + 5)
         const float4 *pq = nullptr;   // the same, PIPE_PFD steps further: what is pulled towards L2 now
@@ -437,7 +446,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             quant12(0, bc);
             buf[0][0] = ld_stream_pinned(pr); buf[0][1] = ld_stream_pinned(pr + 1); buf[0][2] = ld_stream_pinned(pr + 2);
             pr += inc_rows;
-            pq = pr + (size_t)(PIPE_PFD / 4) * G.plane4;
+            pq = pr + (size_t)(PIPE_PFD / SPP) * G.plane4;
         }
         for (int it = 0; unit < A.nunits; it++) {
             if (warp == 0) PIPE_DBG(it, 0);
@@ -485,8 +494,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         quant12(un, bn);
                         if (u == 3 && t0 == PIPE_STEPS - 8) pr = nxt;   // step t + 5 == 32: the refills move on to the next unit
                         if (u == 3 && t0 == PIPE_STEPS - 8 - PIPE_PFD) pq = nxt;   // and so does the L2 prefetch, PIPE_PFD steps earlier
-                        if (A.prefetch && (lane & 15) == 0 && (t0 + u + 5 + PIPE_PFD < PIPE_STEPS || nxt != nullptr))
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pq), "r"(64 * 12) : "memory");
+                        if (A.prefetch && (lane % LPR) == 0 && (t0 + u + 5 + PIPE_PFD < PIPE_STEPS || nxt != nullptr))
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pq), "r"(NSUB * 12) : "memory");
                         pq += u == 2 ? inc_plane : inc_rows;
                         if (t0 + u + 5 < PIPE_STEPS || nxt != nullptr) {
                             buf[un][0] = ld_stream_pinned(pr); buf[un][1] = ld_stream_pinned(pr + 1); buf[un][2] = ld_stream_pinned(pr + 2);
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             }
             {
                 const unsigned bad = __ballot_sync(0xffffffffu, !ok);
-                if (bad) pipe_redo_warp(bad, cur, G.row4, G.plane4, par, stage, e_thread, st, &oob);
+                if (bad) pipe_redo_warp(bad, cur, step_lo, G.plane4, SPP, par, stage, e_thread, st, &oob);
             }
 #pragma unroll
             for (int s = 0; s < 12; s++) {
@@ -606,8 +615,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                     unsigned c;
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt) : "memory");
-                        if (c < 8u) __nanosleep(64);
-                    } while (c < 8u);
+                        if (c < (unsigned)PARTS) __nanosleep(64);
+                    } while (c < (unsigned)PARTS);
                 } else {
                     mbar_wait_cluster(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
                 }
