@@ -304,7 +304,8 @@ def run_gpu(args):
     field_bytes = 12 * NSIDE ** 3
     mean_bits = {k: float(meta[k][1].double().mean().item()) for k in ("x", "v")}
     packed_bytes = {k: int(out_len[k].sum().item()) for k in ("x", "v")}
-    phases = {"encode_x_ms": ph[0], "encode_v_ms": ph[1],   # encode_x_ms includes the velocity limits kernel "decode_x_ms": ph[2], "decode_v_ms": ph[3],
+    # encode_x_ms includes the velocity limits kernel (bounds() runs first, see step())
+    phases = {"encode_x_ms": ph[0], "encode_v_ms": ph[1], "decode_x_ms": ph[2], "decode_v_ms": ph[3],
               "encode_gbs": 2 * field_bytes / ((ph[0] + ph[1]) * 1e-3) / 1e9,
               "decode_gbs": 2 * field_bytes / ((ph[2] + ph[3]) * 1e-3) / 1e9,
               "mean_bits_x": mean_bits["x"], "mean_bits_v": mean_bits["v"],
