@@ -681,7 +681,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
             // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
             void *coop_ws = nullptr;
             const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
-            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32) {   // 32^3 units are single CTAs: no exclusivity to worry about
+            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
                 CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
                 coop_ws = ctx->flat_ws.p;
             }
@@ -695,7 +695,15 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
                                  (int)subcells, nfiles, ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out,
                                  out_axis_stride);
         }
-        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
+        if (e == cudaErrorNotSupported) {   // no fused kernel for this shape on this device after all: the generic kernels
+            ctx->last_path = 0;
+            launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                                  ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
+                                  out_axis_stride, out_axis_stride);
+            CU(cudaGetLastError());
+            return MNW_OK;
+        }
         // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
         launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,
                          out, out_axis_stride, out_axis_stride, d_flags + 1);

@@ -1140,12 +1140,13 @@ size_t fused_work_bytes(int64_t nblocks) { return (size_t)(16 * nblocks + 256); 
 bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile, int subcells, const void *aos) {
     if (subcells <= 0 || nfile % subcells) return false;
     const int nsub = nfile / subcells;
-    if (nsub != 16 && nsub != 32 && nsub != 64) return false;
+    if (nsub != 16 && nsub != 32 && nsub != 64 && nsub != 128) return false;
     if (((uintptr_t)aos & 15) != 0 || nfile > 1024) return false;   // 32-bit float4 offsets inside a file
     for (int64_t i = 0; i < nparams; i++) {
         const FloatParamsHost &p = fp[i];
         if (!(p.flags & F_PERIODIC) || (p.flags & (F_LOG10 | F_CLAMP))) return false;
         if (p.pixels < 1 || p.pixels >= (1LL << 30)) return false;
+        if (nsub == 128 && p.pixels > (1LL << 22)) return false;   // 128^3 sub-cells: k_pipe_vec3 only
     }
     return true;
 }
@@ -1245,6 +1246,14 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
             }
             return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
         }
+        case 128: {   // 64 CTAs per unit: the cooperative pipeline or nothing (the caller then takes the generic kernels)
+            if (pipe_ok && coop_ws) {
+                const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 128);
+                if (e == cudaSuccess) return e;
+                (void)cudaGetLastError();
+            }
+            return cudaErrorNotSupported;
+        }
         case 16: {
             // a 16^3 unit stages 24 KB only: several CTAs per SM hide each other's read -> barrier -> pack phases
             static const int minb = getenv("MNW_FUSED16_MINB") ? atoi(getenv("MNW_FUSED16_MINB")) : 1;   // tuning knob
@@ -1338,7 +1347,7 @@ cudaError_t launch_flat_vec3(Launcher &L, const FusedWork &W, void *work, void *
 bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out) {
     if (subcells <= 0 || nfile % subcells || nfile > 1024) return false;
     const int nsub = nfile / subcells;
-    if (nsub != 16 && nsub != 32 && nsub != 64) return false;
+    if (nsub != 16 && nsub != 32 && nsub != 64 && nsub != 128) return false;
     return ((uintptr_t)aos_out & 15) == 0;
 }
 
@@ -1397,6 +1406,7 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
     const bool hash = h.jmode == 1;
     const int wrap = h.wrap_L > 0.0f ? (h.low_nonneg ? 2 : 1) : 0;
     switch (nsub) {
+        case 128: return launch_decode_vec3_n<128>(L, A, hash, wrap);
         case 64: return launch_decode_vec3_n<64>(L, A, hash, wrap);
         case 32: return launch_decode_vec3_n<32>(L, A, hash, wrap);
         case 16: return launch_decode_vec3_n<16>(L, A, hash, wrap);

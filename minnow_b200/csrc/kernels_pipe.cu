@@ -61,7 +61,7 @@ size_t pipe_coop_ws_bytes(int64_t nunits) { return (size_t)nunits * 64; }
 
 template <int NSUB>
 static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
-    constexpr int PARTS = NSUB == 64 ? 8 : 1;
+    constexpr int PARTS = NSUB * NSUB * NSUB / PIPE_CHUNK;   // CTAs per unit: 1, 8 or 64
     auto kern = k_pipe_vec3<true, NSUB>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
     static int grid_max = -1;
@@ -93,6 +93,7 @@ static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
 }
 
 cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws, int nsub) {
+    if (nsub == 128) return launch_pipe_vec3_coop_t<128>(L, A, ws);
     return nsub == 32 ? launch_pipe_vec3_coop_t<32>(L, A, ws) : launch_pipe_vec3_coop_t<64>(L, A, ws);
 }
 

@@ -285,11 +285,12 @@ __device__ __forceinline__ void emit_group(const unsigned (&f)[16], unsigned *bu
 // one z-plane per step; the staging layout, the packers and the look-back are the same.
 template <bool COOP, int NSUB>
 __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
-    static_assert(NSUB == 64 || (NSUB == 32 && COOP), "32^3 sub-cells run one CTA per unit");
+    static_assert(NSUB == 64 || ((NSUB == 32 || NSUB == 128) && COOP), "32^3 and 128^3 sub-cells: cooperative schedule only");
     constexpr int N = NSUB * NSUB * NSUB, CHUNK = PIPE_CHUNK, CS = PIPE_CS;
-    constexpr int PARTS = NSUB == 64 ? 8 : 1;                 // CTAs per unit
+    constexpr int PARTS = NSUB * NSUB * NSUB / PIPE_CHUNK;     // CTAs per unit: 1, 8 or 64
+    constexpr int PPP = PIPE_CHUNK / (NSUB * NSUB);           // z-planes per part: 32 (the whole unit), 8 or 2
     constexpr int LPR = NSUB / 4;                             // lanes per row (4 particles each): 16 or 8
-    constexpr int SPP = NSUB / (8 * 32 / LPR);                // steps per z-plane: 4 or 1
+    constexpr int SPP = NSUB / (8 * 32 / LPR);                // steps per z-plane: 1, 4 or 16
     constexpr int LT = 32 * PIPE_LW, PT = 32 * (PIPE_PW + 1);   // loader threads; packer + scanner threads
     constexpr int NGROUPS = 3 * (CHUNK / 1024);   // pack groups per CTA and unit
     constexpr int UM = PIPE_USLOTS - 1;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
         // lane geometry: step t covers rows 16 t .. 16 t + 15 of the CTA's 512; warp w rows 2 w, 2 w + 1
         // of those, lane l particles 4 (l & 15) .. + 3 of row (l >> 4)
         const unsigned toff0 = (unsigned)((32 / LPR) * warp + lane / LPR) * G.row4 + 3u * (unsigned)(lane % LPR);
-        auto toff = [&](unsigned rk) { return rk * 8u * G.plane4 + toff0; };   // rk: which eighth of the unit (64^3)
+        auto toff = [&](unsigned rk) { return rk * (unsigned)PPP * G.plane4 + toff0; };   // rk: which part of the unit
         const int e_thread = 128 * warp + 4 * lane;   // element of the thread's first particle at step 0
         // byte offset of that element's 8-byte piece in an axis' staging array (chunk swizzle c ^ ((c >> 3) & 7))
         const unsigned sbyte = (unsigned)((((e_thread >> 3) ^ ((e_thread >> 6) & 7)) << 4) + ((lane & 1) << 3));
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             quant12(0, bc);
             buf[0][0] = ld_stream_pinned(pr); buf[0][1] = ld_stream_pinned(pr + 1); buf[0][2] = ld_stream_pinned(pr + 2);
             pr += inc_rows;
-            pq = pr + (size_t)(PIPE_PFD / SPP) * G.plane4;
+            pq = pr + (size_t)(PIPE_PFD / SPP) * G.plane4 + (size_t)(PIPE_PFD % SPP) * step_lo;   // (no plane boundary in between)
         }
         for (int it = 0; unit < A.nunits; it++) {
             if (warp == 0) PIPE_DBG(it, 0);
@@ -496,11 +497,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         if (u == 3 && t0 == PIPE_STEPS - 8 - PIPE_PFD) pq = nxt;   // and so does the L2 prefetch, PIPE_PFD steps earlier
                         if (A.prefetch && (lane % LPR) == 0 && (t0 + u + 5 + PIPE_PFD < PIPE_STEPS || nxt != nullptr))
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pq), "r"(NSUB * 12) : "memory");
-                        pq += u == 2 ? inc_plane : inc_rows;
+                        pq += (SPP > 4 ? ((t0 + u + 5 + PIPE_PFD) % SPP) == SPP - 1 : u == 2) ? inc_plane : inc_rows;
                         if (t0 + u + 5 < PIPE_STEPS || nxt != nullptr) {
                             buf[un][0] = ld_stream_pinned(pr); buf[un][1] = ld_stream_pinned(pr + 1); buf[un][2] = ld_stream_pinned(pr + 2);
                         }
-                        pr += u == 2 ? inc_plane : inc_rows;
+                        pr += (SPP > 4 ? ((t0 + u + 5) % SPP) == SPP - 1 : u == 2) ? inc_plane : inc_rows;
                         // ---- integer half of step t ----
 #pragma unroll
                         for (int k = 0; k < 3; k++) {

@@ -378,3 +378,30 @@ def test_pipe_cooperative_large_batch_roundtrip(ctx):
     assert torch.equal(o, torch.cumsum(nbs, 1) - nbs)
     assert torch.equal(out_len, o[:, -1] + nbs[:, -1])
     assert int(bits.max()) <= 16 and int(bits.min()) >= 1
+
+
+@pytest.mark.parametrize("nfile,subcells", [(128, 1), (256, 2)])
+def test_pipe_128_subcells(ctx, orc, nfile, subcells):
+    """128^3 sub-cells: 64 CTAs per unit in the cooperative k_pipe_vec3 schedule, k_decode_vec3<128>"""
+    rng = np.random.default_rng(128 + subcells)
+    L, dx = 500.0, 0.01
+    vec = lagrangian(rng, nfile, L, 1.5)
+    px = mb.float_group_pixels(0.0, L, dx)
+    mins, bits = check(ctx, orc, vec, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, L)
+    if subcells == 2:
+        assert bits.max() <= 16   # packed by k_pipe_vec3 itself, not by the > 16 bit list
+
+
+def test_pipe_128_velocities(ctx, orc):
+    rng = np.random.default_rng(1280)
+    nfile, subcells = 128, 1
+    vec = (250.0 * rng.standard_normal((nfile ** 3, 3))).astype(np.float32)
+    lo, hi = orc.minp_limits(vec, False, 0.0)
+    px = [mb.float_group_pixels(float(lo[k]), float(hi[k]), 1.0) for k in range(3)]
+    vec[12345, 1] = np.nan                      # one bad value: the generic redo has to take over
+    descs = [mb.FloatDesc.make(lo[k], hi[k], px[k]) for k in range(3)]
+    mins, bits, offs, streams = ctx.encode_vec3_subcells(descs, vec, nfile, subcells)
+    omins, obits, onbytes, packed, stride, total = orc.bench_minp_encode(vec, nfile, subcells, lo.tolist(), hi.tolist(), px)
+    assert np.array_equal(mins, omins) and np.array_equal(bits, obits)
+    for k in range(3):
+        assert streams[k].tobytes() == packed[k * stride:k * stride + onbytes[k]].tobytes()

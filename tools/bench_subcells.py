@@ -6,9 +6,9 @@ dev = torch.device("cuda", 0)
 ctx = mb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 g = torch.Generator(device=dev); g.manual_seed(1)
-for nfile, subcells, nfiles in ((256, 8, 16), (256, 16, 16), (256, 4, 16)):
+for nfile, subcells, nfiles in ((256, 8, 16), (256, 16, 16), (256, 4, 16), (256, 2, 16)):
     n3 = nfile ** 3
-    L, dx = 1000.0, 0.005
+    L, dx = (1000.0 if nfile // subcells < 128 else 250.0), 0.005   # 128^3 sub-cells: a box in which they stay below 17 bits
     j = torch.arange(nfile, device=dev, dtype=torch.float32) * (L / nfile)
     grid = torch.stack(torch.meshgrid(j, j, j, indexing="ij")[::-1], dim=-1).reshape(n3, 3)
     aos = torch.remainder(torch.randn((nfiles, n3, 3), generator=g, device=dev) * 2.0 + grid[None], L).contiguous()
