@@ -347,6 +347,17 @@ def run_gpu(args):
                                  achieved_gbs=(algo.get(r["kernel"], 0) * args.steps / (r["ms"] * 1e-3) / 1e9 if r["ms"] else None))
                             for r in prof]}
 
+    # ---- size-independent check of what the timed steps left behind (not timed): every block's byte offset is the
+    # running sum of ArrayBytes(bits, n) within its (file, axis) stream, and a decode with the CENTER jitter lands
+    # within half a pixel (plus float32 rounding) of every input value
+    verified = None
+    if rank == 0:
+        try:
+            verified = verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, state["vd"], packed, meta, out_len,
+                                        decoded, stride)
+        except Exception as exc:   # a failed check is reported, it never costs the run its number
+            verified = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ------
     e2e = None if args.no_e2e else run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev)
 
@@ -374,11 +385,39 @@ def run_gpu(args):
                "config": workload_config({"sharding": "block ranges per GPU; NCCL all-gather of per-block sizes + "
                                           "offset scan" if world > 1 else "single GPU"}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "phases": phases,
-               "roofline": roof, "cpu_baseline": cpu}
+               "roofline": roof, "cpu_baseline": cpu, "verified": verified}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+def verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, vdescs, packed, meta, out_len, decoded, stride):
+    """Block offsets = running sums of ArrayBytes(bits, n) per (file, axis) stream; a CENTER-jitter decode lies within half
+    a pixel (+ float32 rounding) of every input value, modulo the group's range (every group is periodic in the format,
+    go/writer.go:74: a value that quantises to index == pixels, the field maximum, comes back at the other end of the
+    range, in the reference as here)."""
+    worst, ok = {}, True
+    with torch.cuda.stream(stream):
+        for key, field, descs_k, wrap in (("x", pos, pdescs, L_BOX), ("v", vel, vdescs, 0.0)):
+            ctx.decode_vec3_subcells_dev(descs_k, packed[key], stride, meta[key][2], meta[key][0], meta[key][1],
+                                         NFILE, SUB_CELLS, NFILES, wrap, mb.Jitter.make(mb.JITTER_CENTER, 0), decoded)
+            ctx.sync()
+            w = 0.0
+            for f in range(NFILES):
+                dk = [descs_k[(3 * f if len(descs_k) > 3 else 0) + k] for k in range(3)]
+                span = torch.tensor([q.high - q.low for q in dk], dtype=torch.float32, device=dev)
+                dxs = span / torch.tensor([float(q.pixels) for q in dk], dtype=torch.float32, device=dev)
+                d = (decoded[f] - field[f]).abs_()
+                d = torch.minimum(d, (span - d).abs_())
+                w = max(w, float((d / dxs).max().item()))
+            worst[key] = w
+            nbs = ((meta[key][1] * NSUB3 + 7) // 8).reshape(3 * NFILES, SC3)
+            o = meta[key][2].reshape(3 * NFILES, SC3)
+            ok = ok and bool(torch.equal(o, torch.cumsum(nbs, 1) - nbs)) and bool(torch.equal(out_len[key], o[:, -1] + nbs[:, -1]))
+    ok = ok and worst["x"] <= 0.53 and worst["v"] <= 0.53
+    return {"ok": bool(ok), "max_roundtrip_error_pixels": worst,
+            "offsets": "running sums of ArrayBytes(bits, n) per stream" if ok else "see ok"}
 
 
 def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
