@@ -1110,6 +1110,18 @@ __global__ void k_selftest_fastdiv(FloatParams fp, unsigned long long first, uns
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned)(first + i));
         const int qi = quantize_fast(x, fp.low, fp.rcp, -fp.dx);
+        // the pair / float4 form of k_pipe_vec3 and the group kernels: floor by RM(y + 2^23), accepted when the raw
+        // bits lie in [2^23, 2^23 + pixels) -- no test on the offset at all
+        if (Pm1 && P <= (1 << 22)) {
+            const float t = __fsub_rn(x, fp.low);
+            float y = __fmul_rn(t, fp.rcp);
+            float e = __fmaf_rn(-fp.dx, y, t);
+            y = __fmaf_rn(e, fp.rcp, y);
+            e = __fmaf_rn(-fp.dx, y, t);
+            y = __fmaf_rn(e, fp.rcp, y);
+            const unsigned q2 = __float_as_uint(__fadd_rd(y, 8388608.0f)) - 0x4B000000u;
+            if (q2 < (unsigned)P && (long long)q2 != quantize_exact(x, fp.low, fp.dx)) bad++;
+        }
         // the widest acceptance rule in use (k_flat_vec3): offset in [+0, high - low] and pixel index < pixels
         if (Pm1 && __float_as_uint(__fsub_rn(x, fp.low)) <= __float_as_uint(__fsub_rn(fp.high, fp.low)) &&
             (unsigned)qi < (unsigned)P) {

@@ -201,6 +201,10 @@ def test_fast_quantiser_matches_ieee_divide(ctx):
     px = mb.float_group_pixels(0.0, 1000.0, 0.005)
     bad, acc = ctx.selftest_fastdiv(mb.FloatDesc.make(0.0, 1000.0, px))
     assert bad == 0 and acc > 10 ** 8
+    # a velocity-like grid (negative low, dx = 1), exhaustive too: both the F2I form and the RM(y + 2^23) form
+    pv = mb.float_group_pixels(-1543.21, 1622.5, 1.0)
+    bad, acc = ctx.selftest_fastdiv(mb.FloatDesc.make(-1543.21, 1622.5, pv))
+    assert bad == 0 and acc > 10 ** 7
     rng = np.random.default_rng(3)
     for _ in range(24):
         lo = float(np.float32(rng.uniform(-2000, 2000)))
