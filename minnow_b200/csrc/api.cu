@@ -50,7 +50,7 @@ struct mnw_ctx {
     std::string err;
     int last_path = 0;
     int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, flat_ws, flat_scratch;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
 };
 
@@ -446,7 +446,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->flat_ws, &ctx->flat_scratch})
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     cudaStreamDestroy(ctx->L.stream);
@@ -674,27 +674,17 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
         W.repack_list = (int64_t *)(W.pub + nb);
         W.err = d_flags + 1; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
         CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
-        static const bool use_cluster = !(getenv("MNW_ENCODE") && !strcmp(getenv("MNW_ENCODE"), "flat"));   // tuning knob
-        cudaError_t e;
-        if (use_cluster) {
-            // The cooperative schedule owns the whole GPU while it runs: right for large batches, but calls on a
-            // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
-            void *coop_ws = nullptr;
-            const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
-            if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
-                CU(ctx->flat_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
-                coop_ws = ctx->flat_ws.p;
-            }
-            e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
-                                  ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
-                                  pipe_vec3_supported(fp.data(), ndesc), coop_ws);
-        } else {
-            CU(ctx->flat_ws.reserve(flat_work_bytes(nfiles * sc3)));
-            CU(ctx->flat_scratch.reserve(flat_scratch_bytes()));
-            e = launch_flat_vec3(ctx->L, W, ctx->flat_ws.p, ctx->flat_scratch.p, tab, desc_per_file, aos, (int)nfile,
-                                 (int)subcells, nfiles, ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out,
-                                 out_axis_stride);
+        // The cooperative schedule owns the whole GPU while it runs: right for large batches, but calls on a
+        // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
+        void *coop_ws = nullptr;
+        const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
+        if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
+            CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
+            coop_ws = ctx->coop_ws.p;
         }
+        const cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
+                                                ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
+                                                pipe_vec3_supported(fp.data(), ndesc), coop_ws);
         if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
         if (e == cudaErrorNotSupported) {   // no fused kernel for this shape on this device after all: the generic kernels
             ctx->last_path = 0;

@@ -37,16 +37,6 @@ size_t pipe_coop_ws_bytes(int64_t nunits);   // workspace of the cooperative k_p
 // k_pipe_vec3 (the warp-specialised 64^3 encode) applies when every group has pixels <= 2^22.
 bool pipe_vec3_supported(const FloatParamsHost *fp, int64_t nparams);
 
-// The same encode without clusters (k_flat_vec3): stats tiles park 16-bit indices in a scratch
-// ring that stays in L2, pack tiles follow a few units behind.  `work` holds flat_work_bytes,
-// `scratch` flat_scratch_bytes; same support conditions as launch_fused_vec3.
-size_t flat_work_bytes(int64_t nunits);
-size_t flat_scratch_bytes();
-cudaError_t launch_flat_vec3(Launcher &L, const FusedWork &W, void *work, void *scratch, const FloatParams *tab,
-                             int tab_per_file, const float *aos, int nfile, int subcells, int64_t nfiles,
-                             BlockStat *stats, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
-                             uint8_t *out, int64_t out_axis_stride);
-
 // 3-axis decode + periodic wrap + sub-cell scatter.
 bool fused_decode_vec3_supported(int nfile, int subcells, const void *aos_out);
 cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t nfiles);

@@ -1,5 +1,5 @@
 // fused_detail.cuh -- device helpers shared by the fused minp encode kernels
-// (kernels_fused.cu: k_fused_vec3 / k_flat_vec3, kernels_pipe.cu: k_pipe_vec3).
+// (kernels_fused.cu: k_fused_vec3, kernels_pipe.cu: k_pipe_vec3).
 // Everything sits in an anonymous namespace: each translation unit gets its own copy.
 #pragma once
 #include <cooperative_groups.h>

@@ -440,410 +440,6 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
 }
 
 // ---------------------------------------------------------------------------
-// encode, flat variant: no clusters.  A unit (sub-cell) is cut into tiles of 4096
-// particles; every tile is visited twice by independent CTAs, in ticket order:
-//   A-tile  read the AoS rows once, quantise, accumulate the block statistics with
-//           atomics, and park the 16-bit rotated pixel indices, planar per axis, in a
-//           scratch RING in global memory (24 MB: it lives in L2, the input stream is
-//           read with evict-first loads);
-//   B-tile  D units later: fetch the parked indices (L2), subtract the block origin, pack
-//           with compile-time bit width and write the bytes to their final offset.
-// The CTA that completes the last A-tile of a unit finalises it: (min, bits, nbytes), the
-// decoupled look-back over the earlier sub-cells of the file, and a `ready` flag.
-// Tickets are handed out in an order in which everything a CTA can wait for (ready flag,
-// ring slot, look-back words) belongs to LOWER tickets, i.e. to CTAs that are running or
-// done: no co-residency assumption, no deadlock.
-// ---------------------------------------------------------------------------
-struct UFin {   // finalised block, as the B-tiles need it
-    long long off;
-    int bits, mode;
-    unsigned base, padj;
-    unsigned pad0, pad1;
-};
-
-struct FlatArgs {
-    const float *aos;
-    const FloatParams *tab;
-    int tab_per_file;
-    int nfile, subcells;
-    int nunits, sc3;
-    int D, R;                 // B-runs follow D units behind the A-runs; the scratch ring holds R units
-    const long long *q0tab;   // [nunits][3] exact pixel index of x[0] of every block (k_unit_q0)
-    BlockStat *stats;
-    int64_t *mins, *bits, *offsets, *out_len;
-    uint8_t *out;
-    long long axis_stride;
-    unsigned *ustat;          // [nunits][3][4]: ~wmin, wmax, ~qmin, qmax (atomicMax, zero-initialised)
-    unsigned *uoob;           // [nunits]
-    int *adone, *bdone, *ready;   // [nunits] each
-    UFin *ufin;               // [nunits][3]
-    unsigned short *scratch;  // [R][3][N]
-    FusedWork W;
-};
-
-__device__ __forceinline__ int ld_volatile_i32(const int *p) {
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <int B>
-__device__ __forceinline__ void pack_group_flat(const unsigned (&v)[32], unsigned *region, int lane, uint8_t *dst) {
-    unsigned o[B];
-    pack32<B>(v, o);
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < B; j++) {
-        const int W = lane * B + j;
-        region[W ^ (W >> 5)] = o[j];
-    }
-    __syncwarp();
-    write_group<B>(dst, region, lane);
-}
-
-// x[0] of every block, quantised exactly: fixes the rotation of the arc statistics of its unit.
-__global__ void k_unit_q0(const FlatArgs A, long long *q0tab, int nsub) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * A.nunits) return;
-    const unsigned unit = i / 3, k = i % 3;
-    const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
-    const unsigned f = unit / sc3, sc = unit % sc3;
-    const unsigned ix0 = nsub * (sc % S), iy0 = nsub * ((sc / S) % S), iz0 = nsub * (sc / (S * S));
-    const float *cube = A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile);
-    const FloatParams fp = A.tab[(A.tab_per_file ? 3 * f : 0) + k];
-    const unsigned long long idx0 = ix0 + (unsigned long long)iy0 * nfile + (unsigned long long)iz0 * nfile * nfile;
-    q0tab[i] = quantize_exact(__ldg(cube + 3 * idx0 + k), fp.low, fp.dx);
-}
-
-// Exact redo of ONE thread's share of an A-tile (rare): some element left the range in which
-// the fast quantiser is trusted (negative or NaN offset, pixel index >= pixels).  Recomputes the
-// thread's staged indices with the IEEE divide and publishes its statistics straight to the unit
-// (the caller then contributes nothing for this thread).  Kept out of line so that the fast
-// path's register allocation does not pay for it.
-template <int NSUB, int NT>
-__device__ __noinline__ void flat_redo_thread(const float4 *b, unsigned tile, unsigned nfile, const FloatParams *tab,
-                                              const long long *q0u, unsigned short *stage, unsigned *ustat,
-                                              unsigned *uoob) {
-    constexpr int N3 = NSUB * NSUB * NSUB, TILE = N3 < 4096 ? N3 : 4096, R4 = 3 * NSUB / 4, RPP = NT / R4;
-    constexpr int ROWS = TILE / NSUB, passes = ROWS / RPP;
-    const int tid = threadIdx.x, col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
-    const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
-    unsigned oob = 0;
-    for (int c = 0; c < 4; c++) {
-        const int ax = (a0 + c) % 3;
-        const FloatParams fp = tab[ax];
-        const long long P = fp.pixels, q0 = q0u[ax];
-        const bool q0ok = (unsigned long long)q0 < (unsigned long long)P;
-        const unsigned C = q0ok ? (unsigned)arc_rotation(q0, P) : 0u;
-        if (!q0ok) oob = 1;
-        unsigned wmin = ~0u, wmax = 0u;
-        int qmin = INT_MAX, qmax = INT_MIN;
-        const int so = ax * TILE + rsub * NSUB + (4 * col4 + c) / 3;
-        for (int p = 0; p < passes; p++) {
-            const unsigned rowg = tile * ROWS + rsub + RPP * p;
-            const float x = ((const float *)(b + (size_t)((rowg / NSUB) * plane4 + (rowg % NSUB) * row4)))[c];
-            int q = quantize_rare(x, fp.low, fp.dx, (int)P, oob);
-            unsigned w = (unsigned)q + C;
-            w = min(w, w - (unsigned)P);
-            wmin = min(wmin, w); wmax = max(wmax, w); qmin = min(qmin, q); qmax = max(qmax, q);
-            stage[so + p * (RPP * NSUB)] = (unsigned short)w;
-        }
-        atomicMax(ustat + ax * 4 + 0, ~wmin); atomicMax(ustat + ax * 4 + 1, wmax);
-        atomicMax(ustat + ax * 4 + 2, ~(unsigned)qmin); atomicMax(ustat + ax * 4 + 3, (unsigned)qmax);
-    }
-    if (oob) atomicOr(uoob, 1u);
-}
-
-template <int NSUB, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_flat_vec3(const FlatArgs A) {
-    constexpr int N = NSUB * NSUB * NSUB;
-    constexpr int TILE = N < 4096 ? N : 4096;   // particles per tile
-    constexpr int TPU = N / TILE;               // tiles per unit
-    constexpr int ROWS = TILE / NSUB;
-    constexpr int R4 = 3 * NSUB / 4;
-    constexpr int RPP = NT / R4;
-    constexpr int PASSES = ROWS / RPP;
-    constexpr int GPA = TILE / 1024;            // pack groups per tile and axis
-    constexpr int NW = NT / 32;
-    static_assert(NT % R4 == 0 && ROWS % RPP == 0 && PASSES % 2 == 0, "threads tile the rows exactly");
-    static_assert(NSUB % (RPP * 2) == 0 || RPP % NSUB == 0, "the two rows of a step lie in one plane or one per plane");
-    static_assert(3 * TILE * 2 >= NW * 2048, "transposition regions fit the staging buffer");
-
-    __shared__ __align__(16) unsigned short stage[3 * TILE];
-    __shared__ unsigned s_red[NW][3][4];
-    __shared__ unsigned s_ticket;
-    __shared__ __align__(16) UFin s_fin[3];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
-    const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
-    const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
-    const unsigned total = (unsigned)(A.nunits + A.D) * (2u * TPU);
-
-    for (;;) {
-        if (tid == 0) s_ticket = atomicAdd(A.W.ticket, 1u);
-        __syncthreads();
-        const unsigned t = s_ticket;
-        if (t >= total) break;
-        // Tickets: per unit-step first the TPU A-tiles of unit `step`, then the TPU B-tiles of unit
-        // `step - D`; everything a tile can wait for (ring slot, ready flag, look-back words) belongs
-        // to lower tickets, i.e. to CTAs that are running or done.
-        const unsigned step = t / (2u * TPU), r = t % (2u * TPU);
-        const bool isA = r < (unsigned)TPU;
-        const int unit = isA ? (int)step : (int)step - A.D;
-        const unsigned tile = isA ? r : r - TPU;
-        if (unit < 0 || unit >= A.nunits) { __syncthreads(); continue; }
-        const unsigned f = (unsigned)unit / sc3, sc = (unsigned)unit % sc3;
-        const int slot = unit % A.R;
-
-        if (isA) {
-            // ================= A-tile =================
-            const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
-            const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
-            // row of pass p: tile * ROWS + rsub + RPP * p; the two rows of a step are `stp` apart, steps
-            // may cross z-planes of the sub-cell (NSUB < 64)
-            const float4 *b = (const float4 *)(A.aos + 3ull * f * ((unsigned long long)nfile * nfile * nfile)) +
-                              (3u * ix0 / 4u + iy0 * row4 + iz0 * plane4) + col4;
-            constexpr bool PLANE_STEP = RPP % NSUB == 0;
-            const unsigned stp = PLANE_STEP ? (RPP / NSUB) * plane4 : RPP * row4;   // float4 units per pass
-            auto row_off = [&](int p) {
-                const unsigned rowg = tile * ROWS + rsub + RPP * p;
-                return (size_t)((rowg / NSUB) * plane4 + (rowg % NSUB) * row4);
-            };
-            // parameters in this thread's axis order: relative axis j = actual axis (a0 + j) % 3
-            float low[3], rcp[3], ndx[3];
-            unsigned P[3], C[3], tmax[3];
-            bool bad = false;
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int ax = (a0 + j) % 3;
-                const FloatParams fp = tab[ax];
-                low[j] = fp.low; rcp[j] = fp.rcp; ndx[j] = -fp.dx;
-                P[j] = (unsigned)fp.pixels;
-                // offsets x - low are trusted in [+0, high - low]: as unsigned bit patterns that is one
-                // comparison, and it also rejects negative, NaN, infinite and overflowing values
-                tmax[j] = __float_as_uint(__fsub_rn(fp.high, fp.low));
-                const long long q0 = A.q0tab[(size_t)unit * 3 + ax];
-                const bool ok = (unsigned long long)q0 < (unsigned long long)fp.pixels;
-                C[j] = ok ? (unsigned)arc_rotation(q0, fp.pixels) : 0u;
-                if (!ok || !(fp.flags & F_FASTDIV)) bad = true;   // exact path: x[0] out of range / dx not vouched for
-            }
-            unsigned wmin[3] = {~0u, ~0u, ~0u}, wmax[3] = {0u, 0u, 0u};
-            unsigned qmin[3] = {~0u, ~0u, ~0u}, qmax[3] = {0u, 0u, 0u};   // valid pixel indices are >= 0
-            int so[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) so[c] = ((a0 + c) % 3) * TILE + rsub * NSUB + (4 * col4 + c) / 3;
-
-#pragma unroll 1
-            for (int p0 = 0; p0 < PASSES; p0 += 2) {
-                float4 v[2];
-                const float4 *bp = b + row_off(p0);
-#pragma unroll
-                for (int u = 0; u < 2; u++) v[u] = __ldcs(bp + (size_t)u * stp);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                    unsigned q[4], w[4];
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int j = c % 3;
-                        // go/group.go:319 without the divide (device_math.cuh quantize_fast); trusted for
-                        // offsets in [0, high - low] and pixel indices < pixels, checked once per tile below
-                        const float tt = __fsub_rn(x[c], low[j]);
-                        float y = __fmul_rn(tt, rcp[j]);
-                        float e = __fmaf_rn(ndx[j], y, tt);
-                        y = __fmaf_rn(e, rcp[j], y);
-                        e = __fmaf_rn(ndx[j], y, tt);
-                        y = __fmaf_rn(e, rcp[j], y);
-                        q[c] = (unsigned)__float2int_rd(y);
-                        bad |= __float_as_uint(tt) > tmax[j];
-                        const unsigned wr = q[c] + C[j];
-                        w[c] = min(wr, wr - P[j]);
-                        stage[so[c] + (p0 + u) * (RPP * NSUB)] = (unsigned short)w[c];
-                    }
-                    qmin[0] = __vimin3_u32(qmin[0], q[0], q[3]); qmax[0] = __vimax3_u32(qmax[0], q[0], q[3]);
-                    wmin[0] = __vimin3_u32(wmin[0], w[0], w[3]); wmax[0] = __vimax3_u32(wmax[0], w[0], w[3]);
-#pragma unroll
-                    for (int j = 1; j < 3; j++) {
-                        qmin[j] = min(qmin[j], q[j]); qmax[j] = max(qmax[j], q[j]);
-                        wmin[j] = min(wmin[j], w[j]); wmax[j] = max(wmax[j], w[j]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 3; j++) bad |= qmax[j] >= P[j];
-            if (bad) {   // rare: this thread's elements again, exactly; it publishes its own statistics
-                flat_redo_thread<NSUB, NT>(b, tile, nfile, tab, A.q0tab + (size_t)unit * 3, stage,
-                                           A.ustat + (size_t)unit * 12, A.uoob + unit);
-#pragma unroll
-                for (int j = 0; j < 3; j++) { wmin[j] = ~0u; wmax[j] = 0u; qmin[j] = ~0u; qmax[j] = 0u; }
-            }
-            // ---- tile statistics -> unit statistics (atomicMax on complemented minima) ----
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int j = (k - a0 + 3) % 3;
-                unsigned a = j == 0 ? wmin[0] : (j == 1 ? wmin[1] : wmin[2]);
-                unsigned bb = j == 0 ? wmax[0] : (j == 1 ? wmax[1] : wmax[2]);
-                unsigned cq = j == 0 ? qmin[0] : (j == 1 ? qmin[1] : qmin[2]);
-                unsigned dq = j == 0 ? qmax[0] : (j == 1 ? qmax[1] : qmax[2]);
-                a = __reduce_min_sync(0xffffffffu, a);
-                bb = __reduce_max_sync(0xffffffffu, bb);
-                cq = __reduce_min_sync(0xffffffffu, cq);
-                dq = __reduce_max_sync(0xffffffffu, dq);
-                if (lane == 0) { s_red[warp][k][0] = ~a; s_red[warp][k][1] = bb; s_red[warp][k][2] = ~cq; s_red[warp][k][3] = dq; }
-            }
-            if (tid == 32 && unit >= A.R) {   // the ring slot is free once the unit that used it is packed
-                while (ld_volatile_i32(A.bdone + (unit - A.R)) < TPU) { __nanosleep(64); }
-            }
-            __syncthreads();
-            if (tid < 12) {
-                const int k = tid >> 2, st = tid & 3;
-                unsigned m = 0;
-                for (int wi = 0; wi < NW; wi++) m = max(m, s_red[wi][k][st]);
-                atomicMax(A.ustat + ((size_t)unit * 3 + k) * 4 + st, m);
-            }
-            {   // park the 16-bit indices, planar per axis, in the scratch ring
-                unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile * TILE;
-                for (int i = tid; i < 3 * TILE / 8; i += NT) {
-                    const int k = i / (TILE / 8), wdx = i - k * (TILE / 8);
-                    __stcg((uint4 *)(scr + (size_t)k * N) + wdx, ((const uint4 *)(stage + k * TILE))[wdx]);
-                }
-            }
-            __threadfence();
-            __syncthreads();
-            if (warp == 0) {
-                int last = 0;
-                if (lane == 0) last = atomicAdd(A.adone + unit, 1) == TPU - 1;
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    // ================= finalise the unit =================
-                    __threadfence();
-#pragma unroll 1
-                    for (int k = 0; k < 3; k++) {
-                        const long long blk = ((long long)f * 3 + k) * sc3 + sc;
-                        const unsigned *us = A.ustat + ((size_t)unit * 3 + k) * 4;
-                        const unsigned uwmin = ~__ldcg(us), uwmax = __ldcg(us + 1);
-                        const int uqmin = (int)~__ldcg(us + 2), uqmax = (int)__ldcg(us + 3);
-                        const bool slow = __ldcg(A.uoob + unit) != 0;
-                        const FloatParams fp = tab[k];
-                        const long long Pk = fp.pixels, half = Pk / 2, K = Pk - half - 1;
-                        const long long q0k = A.q0tab[(size_t)unit * 3 + k];
-                        long long mn, pmin;
-                        unsigned long long maxoff;
-                        unsigned base, padj;
-                        bool wide;
-                        const unsigned long long spread = (unsigned long long)uwmax - uwmin + 1ULL;
-                        if (spread > (unsigned long long)half) {   // arc too wide: periodicMin returns 0
-                            wide = true;
-                            pmin = 0; mn = uqmin; maxoff = (unsigned long long)((long long)uqmax - uqmin);
-                            base = (unsigned)arc_rotation(q0k, Pk) + (unsigned)uqmin; padj = (unsigned)Pk;
-                        } else {
-                            wide = false;
-                            long long m = q0k + ((long long)uwmin - K);
-                            if (m < 0) m += Pk;
-                            pmin = m; mn = m; maxoff = spread - 1ULL;
-                            base = uwmin; padj = 0;
-                        }
-                        // bit.PrecisionNeeded: below 2^48 Go's float64 log2 agrees with the integer bit length
-                        int bits = maxoff < (1ULL << 48) ? 64 - __clzll((long long)maxoff) : precision_needed(maxoff);
-                        long long nbytes = array_bytes(bits, N);
-                        if (slow) { bits = 0; nbytes = 0; }
-                        if (lane == 0) st_relaxed(A.W.pub + blk, PUB_AGG | (unsigned long long)nbytes);
-                        const long long off = lookback(A.W.pub, blk - sc, blk);
-                        // parked values are the low 16 bits of w: enough when the packed value has <= 16 bits
-                        // and (wide arcs) w itself fits, i.e. pixels <= 65536
-                        int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
-                        if (lane == 0) {
-                            st_relaxed(A.W.pub + blk, PUB_PREFIX | (unsigned long long)(off + nbytes));
-                            if (off + nbytes > A.axis_stride) {   // never write past the caller's buffer
-                                atomicExch(A.W.err, 2);
-                                mode = 0;
-                            } else if (!slow && bits > 0 && mode == 0) {
-                                A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = blk;
-                            }
-                            if (slow) atomicExch(A.W.abort_flag, 1);
-                            BlockStat st = {};
-                            st.pmin = pmin; st.min = mn; st.nbytes = nbytes; st.out_off = off; st.do_bound = 1; st.bits = bits;
-                            st.q0 = q0k; st.oob = slow;
-                            A.stats[blk] = st;
-                            if (A.mins) A.mins[blk] = mn;
-                            if (A.bits) A.bits[blk] = bits;
-                            if (A.offsets) A.offsets[blk] = off;
-                            if (A.out_len && sc == sc3 - 1) A.out_len[f * 3 + k] = off + nbytes;
-                            UFin fin;
-                            fin.off = off; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj; fin.pad0 = fin.pad1 = 0;
-                            A.ufin[(size_t)unit * 3 + k] = fin;
-                        }
-                    }
-                    __threadfence();
-                    if (lane == 0) atomicExch(A.ready + unit, 1);
-                }
-            }
-        } else {
-            // ================= B-tile: pack 3 x GPA groups of 1024 parked indices =================
-            if (tid < 3) {
-                if (tid == 0) {
-                    while (ld_volatile_i32(A.ready + unit) == 0) { __nanosleep(64); }
-                    __threadfence();   // acquire: the unit's parked indices and UFin records are visible
-                }
-                __syncwarp(0x7);
-                const uint4 *fp4 = (const uint4 *)(A.ufin + (size_t)unit * 3 + tid);
-                uint4 *d4 = (uint4 *)&s_fin[tid];
-                d4[0] = __ldcg(fp4); d4[1] = __ldcg(fp4 + 1);
-            }
-            __syncthreads();
-            const unsigned short *scr = A.scratch + (size_t)slot * 3 * N + (size_t)tile * TILE;
-#pragma unroll 1
-            for (int g = warp; g < 3 * GPA; g += NW) {
-                const int k = g / GPA, gi = g - k * GPA;
-                const UFin fin = s_fin[k];
-                if (fin.mode == 0) continue;
-                const uint4 *src = (const uint4 *)(scr + (size_t)k * N + gi * 1024 + 32 * lane);
-                uint4 r4[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; s4++) r4[s4] = __ldcg(src + s4);
-                unsigned v[32];
-                if (fin.padj == 0) {   // narrow arc: v = w - wmin, exact modulo 2^16
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const unsigned rr[4] = {r4[s4].x, r4[s4].y, r4[s4].z, r4[s4].w};
-#pragma unroll
-                        for (int tt = 0; tt < 4; tt++) {
-                            v[8 * s4 + 2 * tt] = (rr[tt] - fin.base) & 0xffffu;
-                            v[8 * s4 + 2 * tt + 1] = ((rr[tt] >> 16) - fin.base) & 0xffffu;
-                        }
-                    }
-                } else {               // wide arc (pixels <= 65536): v = (w - C - qmin) mod pixels
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const unsigned rr[4] = {r4[s4].x, r4[s4].y, r4[s4].z, r4[s4].w};
-#pragma unroll
-                        for (int tt = 0; tt < 4; tt++) {
-                            const unsigned lo = (rr[tt] & 0xffffu) - fin.base, hi = (rr[tt] >> 16) - fin.base;
-                            v[8 * s4 + 2 * tt] = min(lo, lo + fin.padj);
-                            v[8 * s4 + 2 * tt + 1] = min(hi, hi + fin.padj);
-                        }
-                    }
-                }
-                unsigned *region = (unsigned *)stage + warp * 512;
-                const long long e0 = (long long)tile * TILE + (long long)gi * 1024;
-                uint8_t *dst = A.out + ((long long)f * 3 + k) * A.axis_stride + fin.off + ((e0 * fin.bits) >> 3);
-                switch (fin.bits) {
-#define MNW_CASE(B) case B: pack_group_flat<B>(v, region, lane, dst); break;
-                    MNW_CASE(1) MNW_CASE(2) MNW_CASE(3) MNW_CASE(4) MNW_CASE(5) MNW_CASE(6) MNW_CASE(7) MNW_CASE(8)
-                    MNW_CASE(9) MNW_CASE(10) MNW_CASE(11) MNW_CASE(12) MNW_CASE(13) MNW_CASE(14) MNW_CASE(15) MNW_CASE(16)
-#undef MNW_CASE
-                    default: break;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) atomicAdd(A.bdone + unit, 1);
-        }
-        __syncthreads();   // s_ticket and the staging buffer are reused by the next tile
-    }
-}
-
-// ---------------------------------------------------------------------------
 // decode
 // ---------------------------------------------------------------------------
 struct DecVec3Args {
@@ -1122,7 +718,7 @@ __global__ void k_selftest_fastdiv(FloatParams fp, unsigned long long first, uns
             const unsigned q2 = __float_as_uint(__fadd_rd(y, 8388608.0f)) - 0x4B000000u;
             if (q2 < (unsigned)P && (long long)q2 != quantize_exact(x, fp.low, fp.dx)) bad++;
         }
-        // the widest acceptance rule in use (k_flat_vec3): offset in [+0, high - low] and pixel index < pixels
+        // quantize_fast (F2I form): offset in [+0, high - low] and pixel index < pixels
         if (Pm1 && __float_as_uint(__fsub_rn(x, fp.low)) <= __float_as_uint(__fsub_rn(fp.high, fp.low)) &&
             (unsigned)qi < (unsigned)P) {
             acc++;
@@ -1274,84 +870,6 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
             if (minb == 4) return launch_fused_vec3_t<16, 1, 384, 2, 4, false>(L, A);
             return launch_fused_vec3_t<16, 1, 384, 4, 1, true>(L, A);
         }
-    }
-    return cudaErrorNotSupported;
-}
-
-// ---- flat encode ----
-size_t flat_control_bytes(int64_t nunits) { return (size_t)(64 * nunits + 256); }            // zeroed per launch
-size_t flat_work_bytes(int64_t nunits) { return flat_control_bytes(nunits) + (size_t)((96 + 24) * nunits + 256); }
-size_t flat_scratch_bytes() {
-    static const size_t mb = getenv("MNW_FLAT_SCRATCH_MB") ? (size_t)atoi(getenv("MNW_FLAT_SCRATCH_MB")) : 26;   // tuning knob
-    return mb << 20;
-}
-
-template <int NSUB, int NT, int MINB>
-static cudaError_t launch_flat_vec3_t(Launcher &L, FlatArgs &A) {
-    constexpr int N = NSUB * NSUB * NSUB, TILE = N < 4096 ? N : 4096, TPU = N / TILE;
-    auto kern = k_flat_vec3<NSUB, NT, MINB>;
-    static int grid_max = 0;
-    if (!grid_max) {
-        int per_sm = 0, dev = 0, sms = 148;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        grid_max = per_sm * sms;
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_flat_vec3<%d,%d,%d>: %d CTAs per SM\n", NSUB, NT, MINB, per_sm);
-    }
-    // B-tiles follow D units behind the A-tiles, far enough (about two grids' worth of tickets) that a
-    // unit is complete and finalised before its first B-tile is handed out; the ring holds 2*D units
-    A.D = (2 * grid_max + 2 * TPU - 1) / (2 * TPU);
-    const long long dmax = (long long)(flat_scratch_bytes() / (2 * 3 * (size_t)N * 2));
-    if (A.D > dmax) A.D = (int)dmax;
-    if (A.D < 1) return cudaErrorInvalidValue;
-    A.R = 2 * A.D;
-    const long long tickets = ((long long)A.nunits + A.D) * 2 * TPU;
-    const unsigned grid = (unsigned)(tickets < grid_max ? tickets : grid_max);
-    k_unit_q0<<<(3 * A.nunits + 255) / 256, 256, 0, L.stream>>>(A, (long long *)A.q0tab, NSUB);
-    L.count++;
-    L.begin("k_flat_vec3");
-    kern<<<grid, NT, 0, L.stream>>>(A);
-    L.end();
-    L.count++;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_flat_vec3(Launcher &L, const FusedWork &W, void *work, void *scratch, const FloatParams *tab,
-                             int tab_per_file, const float *aos, int nfile, int subcells, int64_t nfiles,
-                             BlockStat *stats, int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len,
-                             uint8_t *out, int64_t out_axis_stride) {
-    FlatArgs A = {};
-    A.aos = aos; A.tab = tab; A.tab_per_file = tab_per_file; A.nfile = nfile; A.subcells = subcells;
-    A.sc3 = subcells * subcells * subcells;
-    const int64_t nunits = nfiles * A.sc3;
-    if (nunits == 0) return cudaSuccess;
-    if (nunits >= (1LL << 28)) return cudaErrorInvalidValue;
-    A.nunits = (int)nunits;
-    A.stats = stats; A.mins = mins; A.bits = bits; A.offsets = offsets; A.out_len = out_len; A.out = out;
-    A.axis_stride = out_axis_stride; A.W = W;
-    unsigned char *w = (unsigned char *)work;
-    A.ustat = (unsigned *)w;                     w += 48 * nunits;
-    A.uoob = (unsigned *)w;                      w += 4 * nunits;
-    A.adone = (int *)w;                          w += 4 * nunits;
-    A.bdone = (int *)w;                          w += 4 * nunits;
-    A.ready = (int *)w;
-    A.ufin = (UFin *)((unsigned char *)work + ((flat_control_bytes(nunits) + 31) & ~(size_t)31));
-    A.q0tab = (const long long *)(A.ufin + 3 * nunits);
-    A.scratch = (unsigned short *)scratch;
-    cudaError_t e = cudaMemsetAsync(work, 0, flat_control_bytes(nunits), L.stream);
-    if (e != cudaSuccess) return e;
-    switch (nfile / subcells) {
-        case 64: {
-            static const int minb = getenv("MNW_FLAT_MINB") ? atoi(getenv("MNW_FLAT_MINB")) : 5;   // tuning knob
-            if (minb == 5) return launch_flat_vec3_t<64, 192, 5>(L, A);
-            if (minb == 3) return launch_flat_vec3_t<64, 192, 3>(L, A);
-            return launch_flat_vec3_t<64, 192, 4>(L, A);
-        }
-        case 32: return launch_flat_vec3_t<32, 192, 4>(L, A);
-        case 16: return launch_flat_vec3_t<16, 192, 4>(L, A);
     }
     return cudaErrorNotSupported;
 }

@@ -76,6 +76,7 @@ static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_NT, smem);
         if (e != cudaSuccess) return e;
         grid_max = (coop && per_sm >= 1) ? (sms / PARTS) * PARTS : 0;
+        if (grid_max && getenv("MNW_PIPE_GRID")) grid_max = atoi(getenv("MNW_PIPE_GRID"));   // tuning knob (any value >= PARTS is safe)
         if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop, %d>: grid %d, %zu B dynamic smem\n", NSUB, grid_max, smem);
     }
     if (grid_max < PARTS) return cudaErrorNotSupported;
