@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
 
     if (tid == 0) {
         for (int i = 0; i < PIPE_USLOTS; i++) mbar_init(&bar_unit[i], 1);
-        mbar_init(&bar_stats[0], CS); mbar_init(&bar_stats[1], CS);
+        mbar_init(&bar_stats[0], PARTS == 1 ? 1 : CS); mbar_init(&bar_stats[1], PARTS == 1 ? 1 : CS);
         for (int i = 0; i < PIPE_STEPS / 2; i++) mbar_init(&bar_empty[i], 6);
         for (int i = 0; i < 9; i++) mbar_init(&bar_off[0][0] + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -563,7 +563,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 s_cta[tid] = m;
             }
             __syncwarp();
-            if constexpr (COOP) {
+            if constexpr (PARTS == 1) {
+                // this CTA holds the whole unit: its statistics are the unit's, the scanner reads them from s_cta
+                if (tid == 0) mbar_arrive(&bar_stats[it & 1]);
+            } else if constexpr (COOP) {
                 // the unit's record in global memory: [4 k + {0, 1, 2, 3}] = ~wmin, wmax, ~qmin, qmax of axis k (atomicMax
                 // from zero), [12] oob, [13] parts arrived
                 unsigned *us = A.ustat + 16 * unit;
@@ -611,7 +614,9 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             const long long f = unit / A.sc3, sc = unit - f * A.sc3;
             const int par_i = it & 1;
             if (scanner) {
-                if constexpr (COOP) {   // all eight parts of the unit have posted their statistics
+                if constexpr (PARTS == 1) {
+                    mbar_wait(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
+                } else if constexpr (COOP) {   // all parts of the unit have posted their statistics
                     const unsigned *cnt = A.ustat + 16 * unit + 13;
                     unsigned c;
                     do {
@@ -629,7 +634,11 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 if (lane < 3) {
                     XStat x;
                     x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
-                    if constexpr (COOP) {
+                    if constexpr (PARTS == 1) {
+                        x.wmin = s_cta[4 * k]; x.wmax = s_cta[4 * k + 1];
+                        x.qmin = (int)(s_cta[4 * k + 2] - FMAGIC); x.qmax = (int)(s_cta[4 * k + 3] - FMAGIC);
+                        x.oob = s_cta[12];
+                    } else if constexpr (COOP) {
                         const unsigned *us = A.ustat + 16 * unit;
                         x.wmin = ~__ldcg(us + 4 * k); x.wmax = __ldcg(us + 4 * k + 1);
                         x.qmin = (int)~__ldcg(us + 4 * k + 2); x.qmax = (int)__ldcg(us + 4 * k + 3);
