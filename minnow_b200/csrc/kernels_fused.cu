@@ -864,7 +864,7 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams
         }
         case 16: {
             // a 16^3 unit stages 24 KB only: several CTAs per SM hide each other's read -> barrier -> pack phases
-            static const int minb = getenv("MNW_FUSED16_MINB") ? atoi(getenv("MNW_FUSED16_MINB")) : 1;   // tuning knob
+            static const int minb = getenv("MNW_FUSED16_MINB") ? atoi(getenv("MNW_FUSED16_MINB")) : 2;   // tuning knob (measured best with round-robin tickets)
             if (minb == 2) return launch_fused_vec3_t<16, 1, 384, 4, 2, true>(L, A);
             if (minb == 3) return launch_fused_vec3_t<16, 1, 384, 4, 3, false>(L, A);
             if (minb == 4) return launch_fused_vec3_t<16, 1, 384, 2, 4, false>(L, A);
