@@ -292,7 +292,7 @@ class Context:
             if d is not None:
                 cols[i].desc = d
             ptrs[i] = a.ctypes.data if n else None
-        stride = (8 if any(d is None for _, d in columns) else 4) * n + 16   # ArrayBytes(bits, n) of the widest kind
+        stride = 8 * n + 16   # ArrayBytes(64, n): a NaN in a float column makes a block of more than 32 bits
         mins, bits, nbytes = (np.zeros(nc, np.int64) for _ in range(3))
         out = np.empty(max(nc * stride, 1), np.uint8)
         self._check(self.lib.mnw_encode_columns(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), stride))

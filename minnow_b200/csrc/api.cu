@@ -50,8 +50,9 @@ struct mnw_ctx {
     std::string err;
     int last_path = 0;
     int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws, group_ws;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
+    bool flags_init = false; // the device flag words have been zeroed once (the error word is sticky afterwards)
 };
 
 namespace {
@@ -117,13 +118,35 @@ int reserve_batch(mnw_ctx *ctx, int64_t nb, int64_t nchains) {
     return MNW_OK;
 }
 
-// After the stream has drained: surface device-side error flags.
+// Per-call reset of the device flag words.  Word 1 is the ERROR word: it is sticky -- set by the kernels
+// (1: value range 2^64-1, 2: packed output does not fit), read AND cleared only by check_flags(), so that an
+// error raised by a `_dev` call is still there when the caller reaches mnw_sync().
+int reset_flags(mnw_ctx *ctx) {
+    CU(ctx->flags.reserve(64));
+    int *d_flags = ctx->flags.as<int>();
+    if (!ctx->flags_init) {
+        CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+        ctx->flags_init = true;
+    } else {
+        CU(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->L.stream));
+        CU(cudaMemsetAsync(d_flags + 2, 0, 64 - 2 * sizeof(int), ctx->L.stream));
+    }
+    return MNW_OK;
+}
+
+// Synchronises the stream and surfaces (then clears) the device-side error word.
 int check_flags(mnw_ctx *ctx) {
+    if (!ctx->flags_init) {
+        CU(cudaStreamSynchronize(ctx->L.stream));
+        return MNW_OK;
+    }
     CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(cudaStreamSynchronize(ctx->L.stream));
-    if (ctx->h_flags[1] == 1)
+    const int err = ctx->h_flags[1];
+    if (err) CU(cudaMemsetAsync(ctx->flags.as<int>() + 1, 0, sizeof(int), ctx->L.stream));
+    if (err == 1)
         return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
-    if (ctx->h_flags[1] == 2)
+    if (err == 2)
         return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
     return MNW_OK;
 }
@@ -144,7 +167,7 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
     int rc = reserve_batch(ctx, nblocks, 1);
     if (rc) return rc;
     int *d_flags = ctx->flags.as<int>();
-    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
     if (nblocks == 0) {
         if (out_len) CU(cudaMemsetAsync(out_len, 0, 8, ctx->L.stream));
         return MNW_OK;
@@ -168,6 +191,16 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
                       fp.pixels < (1LL << 31);
     // contiguous int64 blocks: the vectorised two-pass kernels (blocks wider than 32 bits fall to k_pack)
     const bool i64c = !ctx->force_generic && !d_idx && kind == KIND_I64;
+    // uniform contiguous blocks: the fused single-read kernel (MNW_GROUP=twopass keeps the two-pass kernels, for A/B runs)
+    static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
+    if ((f32c || i64c) && !d_starts && n > 0 && !twopass) {
+        CU(ctx->group_ws.reserve(group_fused_ws_bytes(nblocks)));
+        ctx->last_path = 2;
+        const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, mins, bits,
+                                                  offsets, out_len, out, 0, out_cap, ctx->group_ws.p);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused group encode: %s", cudaGetErrorString(e));
+        return MNW_OK;
+    }
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
                           ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
                           0, out_cap, nullptr, f32c, i64c);
@@ -252,7 +285,7 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
     if (ncols * tpb >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
     std::vector<size_t> off((size_t)ncols);
     size_t tot = 0;
-    bool any_f = false, any_i = false;
+    bool any_f = false, any_i = false, degenerate = false;
     for (int64_t c = 0; c < ncols; c++) {
         off[(size_t)c] = tot;
         tot += ((size_t)(cols[c].is_float ? 4 : 8) * (size_t)n + 15) & ~(size_t)15;
@@ -262,6 +295,9 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
             if (rc) return rc;
             if (!cols[c].desc.periodic || cols[c].desc.pixels >= (1LL << 31))
                 return fail(ctx, MNW_ERR_ARG, "column %lld: mnw_encode_columns takes periodic FloatGroups with pixels < 2^31", (long long)c);
+            // Low == High, or a NaN / zero / negative Dx: pixels <= 0 (or INT64_MIN).  The reference carries such a
+            // group through its int64 arithmetic; so do the exact kernels (as encode_group_dev does)
+            if (cols[c].desc.pixels < 1) degenerate = true;
             any_f = true;
         } else {
             any_i = true;
@@ -273,7 +309,7 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
     int rc = reserve_batch(ctx, ncols, ncols);
     if (rc) return rc;
     int *d_flags = ctx->flags.as<int>();
-    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
     std::vector<BlockDesc> hd((size_t)ncols);
     for (int64_t c = 0; c < ncols; c++) {
         BlockDesc d = {};
@@ -298,10 +334,20 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
     ctx->last_path = 0;
     int64_t *d_meta = ctx->meta.as<int64_t>();
     int64_t *d_mins = d_meta, *d_bits = d_meta + ncols, *d_offs = d_meta + 2 * ncols, *d_len = d_meta + 3 * ncols;
-    const bool fast = !ctx->force_generic;
-    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
-                          d_flags, d_flags + 1, d_mins, d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride,
-                          (int64_t)dstride, nullptr, fast && any_f, fast && any_i);
+    const bool fast = !ctx->force_generic && !degenerate;
+    static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
+    if (fast && n > 0 && !twopass) {   // every column is one uniform contiguous block of its own chain: the fused single-read kernel
+        CU(ctx->group_ws.reserve(group_fused_ws_bytes(ncols)));
+        ctx->last_path = 2;
+        const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, d_mins,
+                                                  d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride, (int64_t)dstride,
+                                                  ctx->group_ws.p);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused column encode: %s", cudaGetErrorString(e));
+    } else {
+        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
+                              d_flags, d_flags + 1, d_mins, d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride,
+                              (int64_t)dstride, nullptr, fast && any_f, fast && any_i);
+    }
     CU(cudaGetLastError());
     std::vector<int64_t> h_meta(4 * (size_t)ncols);
     CU(cudaMemcpyAsync(h_meta.data(), d_meta, h_meta.size() * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
@@ -446,7 +492,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws})
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     cudaStreamDestroy(ctx->L.stream);
@@ -456,9 +502,9 @@ void mnw_destroy(mnw_ctx *ctx) {
 const char *mnw_last_error(const mnw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int mnw_sync(mnw_ctx *ctx) {
-    if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
-    CU(cudaStreamSynchronize(ctx->L.stream));
-    return MNW_OK;
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
+    return check_flags(ctx);            /* waits for the stream; reports what the `_dev` calls could not */
 }
 
 void *mnw_stream(mnw_ctx *ctx) { return (void *)ctx->L.stream; }
@@ -549,6 +595,8 @@ int mnw_encode_columns(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, cons
 int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, const int64_t *idx, int64_t nblocks,
                                 const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
                                 int64_t out_cap, int64_t *out_len) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
     return encode_group_host(ctx, KIND_I64, nullptr, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
 }
@@ -556,6 +604,8 @@ int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, 
 int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, const float *col, int64_t ncol,
                                   const int64_t *idx, int64_t nblocks, const int64_t *starts, int64_t *mins,
                                   int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     int rc = check_desc(ctx, desc);
     if (rc) return rc;
     if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
@@ -656,7 +706,7 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
     int rc = reserve_batch(ctx, nb, 3 * nfiles);
     if (rc) return rc;
     int *d_flags = ctx->flags.as<int>();
-    CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
     if (nb == 0) return MNW_OK;
 
     BatchShape sh = {};
@@ -724,12 +774,15 @@ int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
     h.tab_per_file = desc_per_file;
     int rc = fill_decode_float(ctx, h, desc, desc_per_file ? 3 * nfiles : 3, jitter);
     if (rc) return rc;
-    if (h.jmode == 2) return fail(ctx, MNW_ERR_ARG, "vec3 decode supports jitter modes CENTER and HASH");
+    if (h.jmode == 2) {   // caller's doubles, u_stream[block * n + i] (DEVICE pointer here): the generic kernel reads them
+        if (!jitter->u_stream) return fail(ctx, MNW_ERR_ARG, "jitter mode STREAM without u_stream");
+        h.u = jitter->u_stream;
+    }
     const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells;
     h.data = data; h.stream_len = data_axis_stride; h.offsets = offsets; h.mins = mins; h.bits = bits;
     h.n = nsub * nsub * nsub; h.nsel = nfiles * 3 * sc3; h.wrap_L = wrap_L;
     h.nfile = (int32_t)nfile; h.subcells = (int32_t)subcells; h.out = aos_out;
-    if (!ctx->force_generic && fused_decode_vec3_supported((int)nfile, (int)subcells, aos_out)) {
+    if (!ctx->force_generic && h.jmode != 2 && fused_decode_vec3_supported((int)nfile, (int)subcells, aos_out)) {
         cudaError_t e = launch_fused_decode_vec3(ctx->L, h, nfiles);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 decode: %s", cudaGetErrorString(e));
         return MNW_OK;
@@ -837,6 +890,15 @@ int mnw_decode_vec3_subcells(mnw_ctx *ctx, const mnw_float_desc desc[3], const u
     CU(cudaMemcpyAsync(d_meta, offsets, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
     CU(cudaMemcpyAsync(d_meta + nb, mins, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
     CU(cudaMemcpyAsync(d_meta + 2 * nb, bits, 8 * (size_t)nb, cudaMemcpyHostToDevice, ctx->L.stream));
+    mnw_jitter jdev;
+    if (jitter && jitter->mode == MNW_JITTER_STREAM) {   // the caller's doubles, one per decoded value: [3 * sc3][n]
+        if (!jitter->u_stream) return fail(ctx, MNW_ERR_ARG, "jitter mode STREAM without u_stream");
+        CU(ctx->ustream.reserve(8 * 3 * (size_t)np));
+        CU(cudaMemcpyAsync(ctx->ustream.p, jitter->u_stream, 8 * 3 * (size_t)np, cudaMemcpyHostToDevice, ctx->L.stream));
+        jdev = *jitter;
+        jdev.u_stream = ctx->ustream.as<double>();
+        jitter = &jdev;
+    }
     int rc = mnw_decode_vec3_subcells_dev(ctx, desc, 0, ctx->in.as<uint8_t>(), stride, d_meta, d_meta + nb, d_meta + 2 * nb,
                                           nfile, subcells, 1, wrap_L, jitter, ctx->dec_out.as<float>());
     if (rc) return rc;

@@ -70,6 +70,69 @@ MNW_HD double go_log10(double x) {
     return go_log2(x) * 0.3010299956639812 /* Ln2/Ln10 = 0x3fd34413509f79ff */;
 }
 
+// ---- Go math.Exp / math.Pow (portable pure-Go algorithms: exp.go `exp` + `expmulti`, pow.go `pow`), used by
+// minh's Log columns on the read side: float32(math.Pow(10, float64(x))), go/minh/minh.go:315-319.
+// The reference's own test of this step is a tolerance test (go/minh/minh_test.go:110-113); on amd64 Go's
+// math.Exp is an assembly routine whose result depends on the CPU's FMA support, so a bit-exact target does not
+// exist: this is the portable algorithm, evaluated without contraction.
+MNW_HD double go_exp(double x) {
+    const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10;
+    const double Log2e = 1.44269504088896338700e+00;
+    const double Overflow = 7.09782712893383973096e+02, Underflow = -7.45133219101941108420e+02;
+    const double NearZero = 1.0 / (1 << 28);
+    if (x != x || x > 1.7976931348623157e308) return x;
+    if (x < -1.7976931348623157e308) return 0;
+    if (x > Overflow) return INFINITY;
+    if (x < Underflow) return 0;
+    if (-NearZero < x && x < NearZero) return 1 + x;
+    int k = 0;
+    if (x < 0) k = (int)(Log2e * x - 0.5);
+    else if (x > 0) k = (int)(Log2e * x + 0.5);
+    const double hi = x - (double)k * Ln2Hi, lo = (double)k * Ln2Lo;
+    const double P1 = 1.66666666666666657415e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05;
+    const double P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    const double r = hi - lo, t = r * r;
+    const double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    const double y = 1 - ((lo - (r * c) / (2 - c)) - hi);
+    return ldexp(y, k);
+}
+
+// math.Pow(10, y): pow.go with x = 10 (none of its x-dependent special cases applies).
+MNW_HD double go_pow10(double y) {
+    if (y == 0) return 1;
+    if (y == 1) return 10;
+    if (y != y) return y;
+    if (y > 1.7976931348623157e308) return INFINITY;   // |x| > 1, y = +Inf
+    if (y < -1.7976931348623157e308) return 0;
+    if (y == 0.5) return sqrt(10.0);
+    if (y == -0.5) return 1 / sqrt(10.0);
+    double yi, yf = modf(fabs(y), &yi);
+    if (yi >= 9.223372036854775808e18) return y > 0 ? INFINITY : 0;
+    double a1 = 1.0;
+    long long ae = 0;
+    if (yf != 0) {
+        if (yf > 0.5) { yf--; yi++; }
+        a1 = go_exp(yf * go_log(10.0));
+    }
+    int xe0;
+    double x1 = frexp(10.0, &xe0);
+    long long xe = xe0;
+    for (long long i = (long long)yi; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) {   // overflow / underflow is certain: Ldexp decides
+            ae += xe;
+            break;
+        }
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < .5) { x1 += x1; xe--; }
+    }
+    if (y < 0) { a1 = 1 / a1; ae = -ae; }
+    if (ae > 100000) ae = 100000;
+    if (ae < -100000) ae = -100000;
+    return ldexp(a1, (int)ae);
+}
+
 // bit.PrecisionNeeded, go/bit/bit.go:19-21: int(ceil(log2(float64(max+1)))).
 // Returns -1 for max = 2^64-1 (Go: log2(0) = -Inf, conversion undefined).
 MNW_HD int precision_needed(unsigned long long max) {

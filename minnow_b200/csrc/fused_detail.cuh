@@ -8,6 +8,7 @@
 
 #include "device_math.cuh"
 #include "engine.cuh"
+#include "f32x2.cuh"
 #include "fused.cuh"
 #include "launch.cuh"
 #include "pack.cuh"

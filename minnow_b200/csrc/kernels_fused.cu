@@ -763,8 +763,8 @@ template <int NSUB, int CS, int NT, int UNROLL, int MINB, bool PIPE>
 static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
     auto kern = k_fused_vec3<NSUB, CS, NT, UNROLL, MINB, PIPE>;
     const size_t smem = (size_t)6 * (NSUB * NSUB * NSUB / CS);
-    static bool configured = false;
-    static int max_clusters = 0;
+    static DevCfg cfgs[MNW_MAX_DEVICES];
+    DevCfg &dc = dev_cfg(cfgs);
     cudaError_t e;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -772,20 +772,20 @@ static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (!configured) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    std::call_once(dc.once, [&] {
+        dc.err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (dc.err != cudaSuccess) return;
         if (CS > 8) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (e != cudaSuccess) return e;
+            dc.err = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (dc.err != cudaSuccess) return;
         }
         cfg.gridDim = dim3(CS);
-        e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-        if (e != cudaSuccess) return e;
-        if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_fused_vec3<%d,%d,%d>: %d co-resident clusters, %zu B dynamic smem\n", NSUB, CS, NT, max_clusters, smem);
-        configured = true;
-    }
+        dc.err = cudaOccupancyMaxActiveClusters(&dc.a, kern, &cfg);
+        if (dc.err == cudaSuccess && dc.a < 1) dc.err = cudaErrorLaunchOutOfResources;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_fused_vec3<%d,%d,%d>: %d co-resident clusters, %zu B dynamic smem\n", NSUB, CS, NT, dc.a, smem);
+    });
+    if (dc.err != cudaSuccess) return dc.err;
+    const int max_clusters = dc.a;
     long long clusters = A.nunits < max_clusters ? A.nunits : max_clusters;
     cfg.gridDim = dim3((unsigned)(clusters * CS));
     L.begin("k_fused_vec3");
@@ -887,21 +887,23 @@ static cudaError_t launch_decode_vec3_t(Launcher &L, const DecVec3Args &A) {
     constexpr int N = NSUB * NSUB * NSUB, SLAB = N < 4096 ? N : 4096;
     constexpr size_t smem = (size_t)2 * 3 * (SLAB * 3 + 32);
     auto kern = k_decode_vec3<NSUB, NT, MINB, HASH, WRAP>;
-    static bool configured = false;
-    static int per_sm = 1;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    static DevCfg cfgs[MNW_MAX_DEVICES];
+    DevCfg &dc = dev_cfg(cfgs);
+    std::call_once(dc.once, [&] {
+        dc.err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (dc.err != cudaSuccess) return;
+        int per = 0;
+        dc.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NT, smem);
+        if (dc.err != cudaSuccess) return;
+        if (per < 1) { dc.err = cudaErrorLaunchOutOfResources; return; }
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        per_sm *= sms;
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_decode_vec3<%d>: %d co-resident CTAs, %zu B dynamic smem\n", NSUB, per_sm, smem);
-        configured = true;
-    }
+        dc.a = per * sms;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_decode_vec3<%d>: %d co-resident CTAs, %zu B dynamic smem\n", NSUB, dc.a, smem);
+    });
+    if (dc.err != cudaSuccess) return dc.err;
+    const int per_sm = dc.a;
     const long long grid = A.nslabs < per_sm ? A.nslabs : per_sm;
     L.begin("k_decode_vec3");
     kern<<<(unsigned)grid, NT, smem, L.stream>>>(A);

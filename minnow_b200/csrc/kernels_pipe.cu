@@ -11,8 +11,8 @@ namespace mnw {
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
     auto kern = k_pipe_vec3<false, 64>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
-    static bool configured = false;
-    static int max_clusters = 0;
+    static DevCfg cfgs[MNW_MAX_DEVICES];
+    DevCfg &dc = dev_cfg(cfgs);
     cudaError_t e;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -20,16 +20,16 @@ cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
     attr[0].val.clusterDim.x = PIPE_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(PIPE_NT); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (!configured) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    std::call_once(dc.once, [&] {
+        dc.err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (dc.err != cudaSuccess) return;
         cfg.gridDim = dim3(PIPE_CS);
-        e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-        if (e != cudaSuccess) return e;
-        if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3: %d co-resident clusters, %zu B dynamic smem\n", max_clusters, smem);
-        configured = true;
-    }
+        dc.err = cudaOccupancyMaxActiveClusters(&dc.a, kern, &cfg);
+        if (dc.err == cudaSuccess && dc.a < 1) dc.err = cudaErrorLaunchOutOfResources;
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3: %d co-resident clusters, %zu B dynamic smem\n", dc.a, smem);
+    });
+    if (dc.err != cudaSuccess) return dc.err;
+    const int max_clusters = dc.a;
     const long long clusters = A.nunits < max_clusters ? A.nunits : max_clusters;
     cfg.gridDim = dim3((unsigned)(clusters * PIPE_CS));
     L.begin("k_pipe_vec3");
@@ -64,21 +64,24 @@ static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
     constexpr int PARTS = NSUB * NSUB * NSUB / PIPE_CHUNK;   // CTAs per unit: 1, 8 or 64
     auto kern = k_pipe_vec3<true, NSUB>;
     const size_t smem = (size_t)6 * PIPE_CHUNK + (size_t)PIPE_PW * PIPE_TBUF * 4;
-    static int grid_max = -1;
+    static DevCfg cfgs[MNW_MAX_DEVICES];
+    DevCfg &dc = dev_cfg(cfgs);
     cudaError_t e;
-    if (grid_max < 0) {
+    std::call_once(dc.once, [&] {
         int dev = 0, sms = 0, coop = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_NT, smem);
-        if (e != cudaSuccess) return e;
-        grid_max = (coop && per_sm >= 1) ? (sms / PARTS) * PARTS : 0;
-        if (grid_max && getenv("MNW_PIPE_GRID")) grid_max = atoi(getenv("MNW_PIPE_GRID"));   // tuning knob (any value >= PARTS is safe)
-        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop, %d>: grid %d, %zu B dynamic smem\n", NSUB, grid_max, smem);
-    }
+        dc.err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (dc.err != cudaSuccess) return;
+        dc.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_NT, smem);
+        if (dc.err != cudaSuccess) return;
+        dc.a = (coop && per_sm >= 1) ? (sms / PARTS) * PARTS : 0;
+        if (dc.a && getenv("MNW_PIPE_GRID")) dc.a = atoi(getenv("MNW_PIPE_GRID"));   // tuning knob (any value >= PARTS is safe)
+        if (getenv("MNW_DEBUG")) fprintf(stderr, "k_pipe_vec3<coop, %d>: grid %d, %zu B dynamic smem\n", NSUB, dc.a, smem);
+    });
+    if (dc.err != cudaSuccess) return dc.err;
+    const int grid_max = dc.a;
     if (grid_max < PARTS) return cudaErrorNotSupported;
     const long long items = PARTS * A.nunits;
     const unsigned grid = (unsigned)(items < grid_max ? items : grid_max);   // >= PARTS: no CTA ever holds two parts of a unit

@@ -2,11 +2,29 @@
 // translation units.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <vector>
 #include <cuda_runtime.h>
 #include "engine.cuh"
 
 namespace mnw {
+
+// Launch configuration that is a property of (kernel, DEVICE): the dynamic shared memory opt-in
+// (cudaFuncSetAttribute) and the occupancy / SM-count queries.  One table per kernel instantiation,
+// indexed by the calling thread's current device (every entry point sets it to its context's device first);
+// initialised once per device under std::call_once, so that contexts on several GPUs, used from several
+// host threads of one process, each get their own opt-in and grid size.
+constexpr int MNW_MAX_DEVICES = 64;
+struct DevCfg {
+    std::once_flag once;
+    cudaError_t err = cudaSuccess;
+    int a = 0, b = 0;   // kernel-specific (co-resident clusters / CTAs, grid size)
+};
+inline DevCfg &dev_cfg(DevCfg (&table)[MNW_MAX_DEVICES]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return table[(unsigned)dev % MNW_MAX_DEVICES];
+}
 
 // Optional per-kernel timing with CUDA events on the launching stream
 // (mnw_profile): the roofline figure of bench.py is read from here.
@@ -67,6 +85,13 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
                            int64_t chain_cap, const int *run_if = nullptr, bool f32c = false, bool i64c = false);
+// kernels_group.cu: the fused single-read encoder of uniform contiguous blocks (k_init + k_group_fused + the wide
+// blocks through k_pack).  flags: the context's device flag words.  ws: group_fused_ws_bytes(nblocks) of scratch.
+size_t group_fused_ws_bytes(int64_t nblocks);
+cudaError_t launch_group_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh, int *flags,
+                                int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
+                                int64_t chain_stride, int64_t chain_cap, void *ws);
+void launch_init_stats(Launcher &L, const BlockDesc *descs, BlockStat *stats, int64_t nb);
 void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
                       const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,
                       int64_t chain_cap, int *err);

@@ -134,12 +134,11 @@ class Reader:
         out = {}
         for name in names:
             c, idx = self._index(name, b)
-            x = self.f.Data(idx)
-            if x.dtype != np.float32:
+            t = self.f.DataType(idx)
+            if t not in (minnow.FloatGroup, minnow.Float32Group):
                 raise TypeError("Column '%s' does not hold float32" % name)
-            if self.Columns[c]["Log"] != 0:                   # float32(math.Pow(10, float64(x))), :315-319
-                x = np.power(10.0, x.astype(np.float64)).astype(np.float32)
-            out[name] = x
+            # float32(math.Pow(10, float64(x))) of a Log column (:315-319) runs in the decode kernel
+            out[name] = self.f.Data(idx, log10=(t == minnow.FloatGroup and self.Columns[c]["Log"] != 0))
         return out
 
     def Ints(self, names):                                                                   # :228-240

@@ -52,8 +52,11 @@ class _Group:
         self.low = self.high = np.float32(0)
         self.pixels, self.periodic = 0, 1
 
-    def block_offset(self, b):     # go/block_index.go:25-35
-        return int(sum(self.sizes[:b - self.start_block]))
+    def block_offset(self, b):     # go/block_index.go:25-35: offsets[b - start - 1], kept as a running-sum array
+        if len(getattr(self, "_ends", ())) != len(self.sizes):
+            self._ends = np.cumsum(np.asarray(self.sizes, np.int64)) if self.sizes else np.zeros(0, np.int64)
+        k = b - self.start_block
+        return int(self._ends[k - 1]) if k > 0 else 0
 
 
 class Writer:
@@ -254,7 +257,9 @@ class Reader:
     def DataLen(self, b):                                      # :135-137
         return int(self.groups[self.block_index[b]].N)
 
-    def Data(self, b):                                         # :114-127
+    def Data(self, b, log10=False):                            # :114-127
+        """log10: the block is a minh Log column -- float32(math.Pow(10, float64(x))) of go/minh/minh.go:315-319
+        is applied on the device by the decode kernel (mnw_float_desc.log10)."""
         i = int(self.block_index[b])
         g = self.groups[i]
         self.f.seek(int(self.group_offsets[i]) + g.block_offset(b))
@@ -266,7 +271,7 @@ class Reader:
         meta = (np.zeros(1, np.int64), np.array([g.mins[k]], np.int64), np.array([g.bits[k]], np.int64))
         if g.gt == IntGroup:                                   # intGroup.readData, go/group.go:257-263
             return np.asarray(self.ctx.decode_int_blocks(data, *meta, g.N)).reshape(-1)
-        d = FloatDesc.make(g.low, g.high, g.pixels, g.periodic)                        # floatGroup.readData, :299-310
+        d = FloatDesc.make(g.low, g.high, g.pixels, g.periodic, 1 if log10 else 0)     # floatGroup.readData, :299-310
         jit = Jitter.make(self.jitter.mode, self.jitter.seed, self.jitter.block_id0 + b)
         return np.asarray(self.ctx.decode_float_blocks(d, data, *meta, g.N, jitter=jit)).reshape(-1)
 

@@ -106,7 +106,8 @@ class Reader:
             self.f.f.seek(int(self.f.group_offsets[k]))
             data3.append(np.frombuffer(self.f.f.read(int(sum(g.sizes))), np.uint8))
             mins += g.mins; bits += g.bits
-            offs += [g.block_offset(g.start_block + i) for i in range(sc3)]
+            ends = np.cumsum(np.asarray(g.sizes, np.int64))                                  # blockOffset, go/block_index.go:25-35
+            offs += [0] + [int(e) for e in ends[:-1]]
         return self.ctx.decode_vec3_subcells(descs, data3, np.array(offs, np.int64), np.array(mins, np.int64),
                                              np.array(bits, np.int64), nfile, sub,
                                              wrap_L=float(np.float32(self.Header["L"])) if self.Periodic else 0.0,
