@@ -375,8 +375,23 @@ def run_gpu(args):
             nby += cpu_step(orc, p0, v0, threads)
             reps += 1
         dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        nby1 = cpu_step(orc, p0, v0, 1)          # the reference is single-threaded: its own figure is the 1-core one
+        dt1 = time.perf_counter() - t1
+        import bench_configs
         cpu = {"value": nby / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": "file 0 of 64 (256^3 particles, x and v), encode+decode, %d repetitions, OpenMP over blocks" % reps}
+               "one_core_value": nby1 / dt1 / 1e9, "cpu": bench_configs.cpu_model(),
+               "sample": "file 0 of 64 (256^3 particles, x and v), encode+decode, %d repetitions, OpenMP over blocks "
+                         "(+ one repetition on 1 core)" % reps}
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        import bench_configs
+        from oracle import oracle as orc
+        orc.lib()
+        del decoded
+        torch.cuda.empty_cache()
+        configs = bench_configs.run_all(torch, mb, orc, ctx, stream, dev, peaks["hbm_gbs"], host_threads())
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -385,7 +400,7 @@ def run_gpu(args):
                "config": workload_config({"sharding": "block ranges per GPU; NCCL all-gather of per-block sizes + "
                                           "offset scan" if world > 1 else "single GPU"}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "phases": phases,
-               "roofline": roof, "cpu_baseline": cpu, "verified": verified}
+               "roofline": roof, "cpu_baseline": cpu, "verified": verified, "configs": configs}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -416,7 +431,37 @@ def verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, vdescs, pack
             o = meta[key][2].reshape(3 * NFILES, SC3)
             ok = ok and bool(torch.equal(o, torch.cumsum(nbs, 1) - nbs)) and bool(torch.equal(out_len[key], o[:, -1] + nbs[:, -1]))
     ok = ok and worst["x"] <= 0.53 and worst["v"] <= 0.53
-    return {"ok": bool(ok), "max_roundtrip_error_pixels": worst,
+    # ---- what the TIMED steps (the cooperative full-batch k_pipe_vec3 run) left behind for file 0 of x and of v, against
+    # the oracle on the same particles: (min, bits) of all 3 x 64 blocks, every packed byte, and the HASH-jitter decode
+    from oracle import oracle as orc
+    orc.lib()
+    threads = host_threads()
+    bytes_equal, detail = True, {}
+    with torch.cuda.stream(stream):
+        for key, field, descs_k, wrap in (("x", pos, pdescs, L_BOX), ("v", vel, vdescs, 0.0)):
+            dk = [descs_k[k] for k in range(3)]   # file 0: the first three descriptors (shared ones or its own)
+            lo, hi, px = [d.low for d in dk], [d.high for d in dk], [d.pixels for d in dk]
+            host = field[0].cpu().numpy()
+            om, ob, onb, opk, ostride, _ = orc.bench_minp_encode(host, NFILE, SUB_CELLS, lo, hi, px, threads)
+            gm, gb, go = (meta[key][i][:3 * SC3].cpu().numpy() for i in range(3))
+            e = bool(np.array_equal(gm, om) and np.array_equal(gb, ob))
+            for k in range(3):
+                want = b"".join(opk[t * ostride:t * ostride + onb[t]].tobytes() for t in range(k * SC3, (k + 1) * SC3))
+                ln = int(out_len[key][k].item())
+                got = packed[key][k * stride:k * stride + ln].cpu().numpy().tobytes()
+                e = e and ln == len(want) and got == want
+                e = e and bool(np.array_equal(go[k * SC3:(k + 1) * SC3], np.concatenate([[0], np.cumsum(onb[k * SC3:(k + 1) * SC3])[:-1]])))
+            ctx.decode_vec3_subcells_dev(descs_k, packed[key], stride, meta[key][2], meta[key][0], meta[key][1],
+                                         NFILE, SUB_CELLS, NFILES, wrap, mb.Jitter.make(mb.JITTER_HASH, 7), decoded)
+            ctx.sync()
+            want = orc.bench_minp_decode(opk, ostride, NFILE, SUB_CELLS, lo, hi, px, om, ob, wrap > 0, L_BOX, 1, 7, threads)
+            e = e and decoded[0].cpu().numpy().tobytes() == want.tobytes()
+            detail[key] = bool(e)
+            bytes_equal = bytes_equal and e
+    return {"ok": bool(ok and bytes_equal), "bytes_equal_oracle": bool(bytes_equal), "bytes_equal_detail": detail,
+            "bytes_equal_scope": "file 0 of x and of v from the timed cooperative full-batch run: (min, bits, offsets) of 3 x 64 blocks, all "
+                                 "packed bytes, HASH-jitter decoded floats, against the oracle",
+            "max_roundtrip_error_pixels": worst,
             "offsets": "running sums of ArrayBytes(bits, n) per stream" if ok else "see ok"}
 
 
@@ -512,6 +557,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 configurations (profiling runs)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -144,6 +144,12 @@ MNW_API int mnw_encode_columns(mnw_ctx *ctx, int64_t ncols, const mnw_column *co
                                int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
                                int64_t out_col_stride);
 
+/* The same on device-resident columns: data_dev is a HOST array of ncols DEVICE pointers; mins, bits, nbytes, out are
+ * DEVICE pointers; enqueued on the context's stream without synchronising (errors: mnw_sync). */
+MNW_API int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const void *const *data_dev,
+                                   int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
+                                   int64_t out_col_stride);
+
 /* Decode nsel blocks of one group.  data/offsets/mins/bits describe the whole
  * group (nblocks entries; offsets as produced above); sel lists the block ids
  * to decode (NULL = blocks 0..nsel-1); block sel[j] lands at out + j*n.
@@ -245,6 +251,21 @@ MNW_API int mnw_decode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *des
                                          int64_t subcells, int64_t nfiles, float wrap_L,
                                          const mnw_jitter *jitter, float *aos_out);
 
+/* The whole of minp.Writer.Vectors / Reader.Vectors for nfiles device-resident cubes with NO host round trip inside:
+ * for a non-periodic field bounds() (go/minp/minp.go:291-300), Nextafter32, the pixel counts (go/writer.go:73) and the
+ * derived group constants are computed by kernels on the stream, so the call only enqueues.  desc_dev is a DEVICE array of
+ * 3 * nfiles mnw_float_desc: written by the encode (what the files' group tails need; copy it back after mnw_sync),
+ * read by the decode.  Other arguments as in mnw_encode_vec3_subcells_dev / mnw_decode_vec3_subcells_dev.  If a derived
+ * group lies outside what the fused kernels cover (pixels < 1 or > 2^22), the generic kernels encode the batch. */
+MNW_API int mnw_minp_encode_vectors_dev(mnw_ctx *ctx, const float *aos, int64_t nfile, int64_t subcells, int64_t nfiles,
+                                        int periodic, float L, float dx, mnw_float_desc *desc_dev, int64_t *mins,
+                                        int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_axis_stride,
+                                        int64_t *out_len);
+MNW_API int mnw_minp_decode_vectors_dev(mnw_ctx *ctx, const mnw_float_desc *desc_dev, const uint8_t *data,
+                                        int64_t data_axis_stride, const int64_t *offsets, const int64_t *mins,
+                                        const int64_t *bits, int64_t nfile, int64_t subcells, int64_t nfiles, int periodic,
+                                        float L, const mnw_jitter *jitter, float *aos_out);
+
 /* minp.Writer.Vectors limits for NON-periodic fields (go/minp/minp.go:92-95):
  * lo = min over particles, hi = Nextafter32(max, 2*max), per axis.  aos holds
  * nfiles cubes of np particles each; lo/hi are HOST arrays [nfiles][3].  The
@@ -273,8 +294,19 @@ MNW_API int mnw_profile_summary(mnw_ctx *ctx, char *buf, int64_t cap);
 MNW_API int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t first_bits, uint64_t count,
                                  uint64_t *mismatches, uint64_t *accepted);
 
-/* Which device path the last encode on ctx took: 0 = generic two-pass,
- * 1 = fused single-read cluster kernel.  For tests and the benchmark. */
+/* Diagnostic: minh Log columns take float32(log10(float64 x)) (go/minh/minh.go:143) through a table + series form with
+ * an exact fallback (device_math.cuh go_log10_f32).  This compares it with the restated Go algorithm on every float32
+ * bit pattern in [first_bits, first_bits + count) and reports how many results differ (must be 0). */
+MNW_API int mnw_selftest_log10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64_t *mismatches);
+
+/* out[i] = float32(math.Pow(10, float64(x[i]))): the read side of a minh Log column that is stored raw (Float32Group),
+ * go/minh/minh.go:315-319.  FloatGroup Log columns get it inside mnw_decode_float_blocks (desc.log10).  HOST pointers.
+ * Go's math.Pow / math.Exp are restated from the portable pure-Go sources (parity unpinned: the reference's own test of
+ * this step is a tolerance test, go/minh/minh_test.go:110-113). */
+MNW_API int mnw_pow10_f32(mnw_ctx *ctx, const float *x, int64_t n, float *out);
+
+/* Which device path the last encode on ctx took: 0 = generic two-pass, 1 = fused single-read minp kernels
+ * (k_pipe_vec3 / k_fused_vec3), 2 = fused group kernel (k_group_fused).  For tests and the benchmark. */
 MNW_API int mnw_last_path(const mnw_ctx *ctx);
 /* Force the generic path (testing both paths against the oracle). */
 MNW_API void mnw_force_generic(mnw_ctx *ctx, int on);

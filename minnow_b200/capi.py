@@ -65,6 +65,7 @@ SIGNATURES = {
     "mnw_minp_encode_vectors": (_int, [_p, _p, _i64, _i64, _int, _f32, _f32, _FD, _p, _p, _p, _p, _i64, _p]),
     "mnw_encode_int_group_gather": (_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_encode_columns": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64]),
+    "mnw_encode_columns_dev": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64]),
     "mnw_encode_float_group_gather": (_int, [_p, _FD, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
@@ -86,11 +87,15 @@ SIGNATURES = {
     "mnw_decode_float_blocks_dev": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _i64, _i64, _p, _JT, _p]),
     "mnw_encode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p]),
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
+    "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
+    "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
     "mnw_vec3_limits": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mnw_vec3_limits_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mnw_scan_offsets_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mnw_profile": (_int, [_p, _int]),
     "mnw_profile_summary": (_int, [_p, C.c_char_p, _i64]),
+    "mnw_selftest_log10": (_int, [_p, C.c_uint32, _u64, C.POINTER(_u64)]),
+    "mnw_pow10_f32": (_int, [_p, _p, _i64, _p]),
     "mnw_last_path": (_int, [_p]),
     "mnw_force_generic": (None, [_p, _int]),
 }
@@ -206,6 +211,19 @@ class Context:
         self._check(self.lib.mnw_selftest_fastdiv(self.h, C.byref(desc), first_bits, count, C.byref(bad), C.byref(acc)))
         return bad.value, acc.value
 
+    def selftest_log10(self, first_bits=0, count=1 << 32):
+        """-> mismatches of go_log10_f32 against the restated Go math.Log10 over float32 bit patterns"""
+        bad = _u64(0)
+        self._check(self.lib.mnw_selftest_log10(self.h, first_bits, count, C.byref(bad)))
+        return bad.value
+
+    def pow10_f32(self, x):
+        """float32(math.Pow(10, float64(x))), go/minh/minh.go:315-319"""
+        x = _np(x, np.float32).reshape(-1)
+        out = np.empty_like(x)
+        self._check(self.lib.mnw_pow10_f32(self.h, _ptr(x), len(x), _ptr(out)))
+        return out
+
     def force_generic(self, on=True):
         self.lib.mnw_force_generic(self.h, int(on))
 
@@ -297,6 +315,18 @@ class Context:
         out = np.empty(max(nc * stride, 1), np.uint8)
         self._check(self.lib.mnw_encode_columns(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), stride))
         return mins, bits, [out[i * stride:i * stride + int(nbytes[i])].copy() for i in range(nc)]
+
+    def encode_columns_dev(self, columns, n, mins, bits, nbytes, out, out_col_stride):
+        """mnw_encode_columns_dev: columns = [(device tensor, FloatDesc or None)], outputs device tensors"""
+        nc = len(columns)
+        cols = (Column * max(nc, 1))()
+        ptrs = (C.c_void_p * max(nc, 1))()
+        for i, (x, d) in enumerate(columns):
+            cols[i].is_float = 0 if d is None else 1
+            if d is not None:
+                cols[i].desc = d
+            ptrs[i] = x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+        self._check(self.lib.mnw_encode_columns_dev(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), out_col_stride))
 
     def decode_int_blocks(self, data, offsets, mins, bits, n, sel=None):
         """intGroup.readData per selected block (go/group.go:257-263)"""
@@ -395,6 +425,19 @@ class Context:
     def decode_int_blocks_dev(self, data, data_len, offsets, mins, bits, n, nsel, sel, out):
         self._check(self.lib.mnw_decode_int_blocks_dev(self.h, _ptr(data), data_len, _ptr(offsets), _ptr(mins),
                                                        _ptr(bits), n, nsel, _ptr(sel), _ptr(out)))
+
+    def minp_encode_vectors_dev(self, aos, nfile, subcells, nfiles, periodic, L, dx, desc_dev, mins, bits, offsets, out,
+                                out_axis_stride, out_len):
+        """minp.Writer.Vectors for nfiles resident cubes, no host round trip; desc_dev: device buffer of 24 * 3 * nfiles bytes"""
+        self._check(self.lib.mnw_minp_encode_vectors_dev(self.h, _ptr(aos), nfile, subcells, nfiles, int(bool(periodic)), float(L),
+                                                         float(dx), _ptr(desc_dev), _ptr(mins), _ptr(bits), _ptr(offsets), _ptr(out),
+                                                         out_axis_stride, _ptr(out_len)))
+
+    def minp_decode_vectors_dev(self, desc_dev, data, data_axis_stride, offsets, mins, bits, nfile, subcells, nfiles, periodic,
+                                L, jitter, aos_out):
+        self._check(self.lib.mnw_minp_decode_vectors_dev(self.h, _ptr(desc_dev), _ptr(data), data_axis_stride, _ptr(offsets),
+                                                         _ptr(mins), _ptr(bits), nfile, subcells, nfiles, int(bool(periodic)), float(L),
+                                                         C.byref(jitter), _ptr(aos_out)))
 
     def vec3_limits(self, aos, nfiles=1, dev=False):
         """minp.Writer.Vectors limits of non-periodic fields (go/minp/minp.go:92-95) -> lo, hi [nfiles, 3]"""

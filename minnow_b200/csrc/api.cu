@@ -52,6 +52,8 @@ struct mnw_ctx {
     int force_generic = 0;
     DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws, group_ws;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
+    void *h_stage = nullptr; // pinned staging for gathered uploads (grow-only)
+    size_t h_stage_cap = 0;
     bool flags_init = false; // the device flag words have been zeroed once (the error word is sticky afterwards)
 };
 
@@ -128,8 +130,7 @@ int reset_flags(mnw_ctx *ctx) {
         CU(cudaMemsetAsync(d_flags, 0, 64, ctx->L.stream));
         ctx->flags_init = true;
     } else {
-        CU(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->L.stream));
-        CU(cudaMemsetAsync(d_flags + 2, 0, 64 - 2 * sizeof(int), ctx->L.stream));
+        CU(cudaMemsetAsync(d_flags, 0, FLAG_ERR * sizeof(int), ctx->L.stream));   // everything but the error word
     }
     return MNW_OK;
 }
@@ -140,10 +141,10 @@ int check_flags(mnw_ctx *ctx) {
         CU(cudaStreamSynchronize(ctx->L.stream));
         return MNW_OK;
     }
-    CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaMemcpyAsync(ctx->h_flags, ctx->flags.as<int>() + FLAG_ERR, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
     CU(cudaStreamSynchronize(ctx->L.stream));
-    const int err = ctx->h_flags[1];
-    if (err) CU(cudaMemsetAsync(ctx->flags.as<int>() + 1, 0, sizeof(int), ctx->L.stream));
+    const int err = ctx->h_flags[0];
+    if (err) CU(cudaMemsetAsync(ctx->flags.as<int>() + FLAG_ERR, 0, sizeof(int), ctx->L.stream));
     if (err == 1)
         return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
     if (err == 2)
@@ -185,24 +186,28 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
         return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
 
     ctx->last_path = 0;
-    launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks, d_idx);
-    // contiguous float32 blocks of a periodic group with pixels < 2^31: the vectorised two-pass kernels
+    // contiguous float32 blocks of a periodic group with pixels < 2^31: the vectorised kernels
     const bool f32c = !ctx->force_generic && !d_idx && kind == KIND_F32 && (fp.flags & F_PERIODIC) && fp.pixels >= 1 &&
                       fp.pixels < (1LL << 31);
-    // contiguous int64 blocks: the vectorised two-pass kernels (blocks wider than 32 bits fall to k_pack)
+    // contiguous int64 blocks: the vectorised kernels (blocks wider than 32 bits fall to k_pack)
     const bool i64c = !ctx->force_generic && !d_idx && kind == KIND_I64;
     // uniform contiguous blocks: the fused single-read kernel (MNW_GROUP=twopass keeps the two-pass kernels, for A/B runs)
     static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
-    if ((f32c || i64c) && !d_starts && n > 0 && !twopass) {
-        CU(ctx->group_ws.reserve(group_fused_ws_bytes(nblocks)));
+    // (TMA tile fetches: every block must start on a 16-byte boundary)
+    const bool aligned = ((uintptr_t)x & 15) == 0 && (nblocks == 1 || (n * (kind == KIND_I64 ? 8 : 4)) % 16 == 0);
+    const bool fused = (f32c || i64c) && !d_starts && n > 0 && aligned && !twopass;
+    if (fused) CU(ctx->group_ws.reserve(group_fused_ws_bytes(nblocks)));
+    launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks, d_idx,
+                        fused ? ctx->stats.as<BlockStat>() : nullptr, fused ? ctx->group_ws.p : nullptr);
+    if (fused) {
         ctx->last_path = 2;
         const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, mins, bits,
-                                                  offsets, out_len, out, 0, out_cap, ctx->group_ws.p);
+                                                  offsets, out_len, out, 0, out_cap, ctx->group_ws.p, kind == KIND_I64, true);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused group encode: %s", cudaGetErrorString(e));
         return MNW_OK;
     }
     launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
-                          ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
+                          ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
                           0, out_cap, nullptr, f32c, i64c);
     CU(cudaGetLastError());
     return MNW_OK;
@@ -341,11 +346,11 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
         ctx->last_path = 2;
         const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, d_mins,
                                                   d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride, (int64_t)dstride,
-                                                  ctx->group_ws.p);
+                                                  ctx->group_ws.p, any_i);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused column encode: %s", cudaGetErrorString(e));
     } else {
         launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
-                              d_flags, d_flags + 1, d_mins, d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride,
+                              d_flags, d_flags + FLAG_ERR, d_mins, d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride,
                               (int64_t)dstride, nullptr, fast && any_f, fast && any_i);
     }
     CU(cudaGetLastError());
@@ -407,22 +412,45 @@ int decode_blocks_host(mnw_ctx *ctx, int mode, const mnw_float_desc *desc, const
         c_off[j] = total; c_min[j] = mins[b]; c_bits[j] = bits[b];
         total += nb;
     }
-    CU(ctx->in.reserve((size_t)total + 16));
     bool contiguous = true;
     for (int64_t j = 0; j + 1 < nsel && contiguous; j++) {
         int64_t b = sel ? sel[j] : j, b2 = sel ? sel[j + 1] : j + 1;
         contiguous = offsets[b] + (c_off[j + 1] - c_off[j]) == offsets[b2];
     }
+    // The selected blocks' bytes go up in ONE copy: as they lie when they are contiguous; the whole span they cover
+    // when they make up a quarter of it or more (random access to a large fraction of a group); otherwise gathered
+    // back to back into pinned staging by the host first.  (One copy per block would cost microseconds per block.)
+    int64_t span_lo = 0, span_hi = 0;
+    if (!contiguous) {
+        span_lo = INT64_MAX;
+        for (int64_t j = 0; j < nsel; j++) {
+            const int64_t b = sel ? sel[j] : j, nbj = (j + 1 < nsel ? c_off[j + 1] : total) - c_off[j];
+            span_lo = offsets[b] < span_lo ? offsets[b] : span_lo;
+            span_hi = offsets[b] + nbj > span_hi ? offsets[b] + nbj : span_hi;
+        }
+    }
+    const bool whole_span = !contiguous && 4 * total >= span_hi - span_lo;
+    CU(ctx->in.reserve((size_t)(whole_span ? span_hi - span_lo : total) + 16));
     if (contiguous) {
         int64_t b = sel ? sel[0] : 0;
         if (total > 0) CU(cudaMemcpyAsync(ctx->in.p, data + offsets[b], (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
+    } else if (whole_span) {
+        CU(cudaMemcpyAsync(ctx->in.p, data + span_lo, (size_t)(span_hi - span_lo), cudaMemcpyHostToDevice, ctx->L.stream));
+        for (int64_t j = 0; j < nsel; j++) c_off[j] = offsets[sel ? sel[j] : j] - span_lo;   // blocks stay where they are
+        total = span_hi - span_lo;
     } else {
-        for (int64_t j = 0; j < nsel; j++) {
-            int64_t nb = (j + 1 < nsel ? c_off[j + 1] : total) - c_off[j];
-            int64_t b = sel ? sel[j] : j;
-            if (nb > 0) CU(cudaMemcpyAsync(ctx->in.as<uint8_t>() + c_off[j], data + offsets[b], (size_t)nb,
-                                           cudaMemcpyHostToDevice, ctx->L.stream));
+        if ((size_t)total > ctx->h_stage_cap) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+            CU(cudaMallocHost(&ctx->h_stage, (size_t)total + (size_t)total / 4 + 4096));
+            ctx->h_stage_cap = (size_t)total + (size_t)total / 4 + 4096;
         }
+        CU(cudaStreamSynchronize(ctx->L.stream));   // an earlier call's copy out of the staging has finished
+        for (int64_t j = 0; j < nsel; j++) {
+            const int64_t nbj = (j + 1 < nsel ? c_off[j + 1] : total) - c_off[j], b = sel ? sel[j] : j;
+            if (nbj > 0) memcpy((uint8_t *)ctx->h_stage + c_off[j], data + offsets[b], (size_t)nbj);
+        }
+        if (total > 0) CU(cudaMemcpyAsync(ctx->in.p, ctx->h_stage, (size_t)total, cudaMemcpyHostToDevice, ctx->L.stream));
     }
     CU(ctx->meta.reserve(m.size() * 8));
     CU(cudaMemcpyAsync(ctx->meta.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice, ctx->L.stream));
@@ -495,6 +523,7 @@ void mnw_destroy(mnw_ctx *ctx) {
                       &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->L.stream);
     delete ctx;
 }
@@ -590,6 +619,66 @@ int mnw_encode_columns(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, cons
     if (!ctx) return MNW_ERR_ARG;
     (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     return encode_columns_host(ctx, ncols, cols, data, n, mins, bits, nbytes, out, out_col_stride);
+}
+
+int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const void *const *data_dev, int64_t n,
+                           int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out, int64_t out_col_stride) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (ncols < 0 || n < 0 || out_col_stride < 0) return fail(ctx, MNW_ERR_ARG, "negative column count, length or stride");
+    if (ncols == 0) return MNW_OK;
+    if (!cols || !data_dev) return fail(ctx, MNW_ERR_ARG, "null column table");
+    const int64_t tpb = (n + PACK_TILE - 1) / PACK_TILE, cpb = (n + STATS_CHUNK - 1) / STATS_CHUNK;
+    if (ncols * tpb >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
+    bool any_f = false, any_i = false, degenerate = false, aligned = true;
+    std::vector<BlockDesc> hd((size_t)ncols);
+    for (int64_t c = 0; c < ncols; c++) {
+        if (!data_dev[c] && n > 0) return fail(ctx, MNW_ERR_ARG, "column %lld has no data", (long long)c);
+        BlockDesc d = {};
+        d.src = data_dev[c];
+        d.n = n; d.access = ACC_CONTIG; d.chain = (int32_t)c;
+        d.tile0 = c * tpb; d.chunk0 = c * cpb;
+        aligned = aligned && ((uintptr_t)data_dev[c] & 15) == 0;
+        if (cols[c].is_float) {
+            if (!cols[c].desc.periodic || cols[c].desc.pixels >= (1LL << 31))
+                return fail(ctx, MNW_ERR_ARG, "column %lld: mnw_encode_columns takes periodic FloatGroups with pixels < 2^31", (long long)c);
+            if (cols[c].desc.pixels < 1) degenerate = true;
+            const FloatParamsHost fp = to_params(cols[c].desc);
+            d.kind = KIND_F32; d.flags = fp.flags;
+            d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
+            any_f = true;
+        } else {
+            d.kind = KIND_I64;
+            any_i = true;
+        }
+        hd[(size_t)c] = d;
+    }
+    int rc = reserve_batch(ctx, ncols, ncols);
+    if (rc) return rc;
+    int *d_flags = ctx->flags.as<int>();
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
+    CU(cudaMemcpyAsync(ctx->descs.p, hd.data(), sizeof(BlockDesc) * (size_t)ncols, cudaMemcpyHostToDevice, ctx->L.stream));   // pageable: staged before return
+    BatchShape sh = {};
+    sh.nblocks = ncols; sh.nchains = ncols; sh.blocks_per_chain = 1; sh.uniform_n = n;
+    sh.total_tiles = ncols * tpb; sh.total_chunks = ncols * cpb;
+    CU(ctx->meta.reserve(8 * (size_t)ncols + 64));
+    int64_t *d_offs = ctx->meta.as<int64_t>();   // (every column is block 0 of its own group: offsets are all 0)
+    const bool fast = !ctx->force_generic && !degenerate;
+    static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
+    if (fast && n > 0 && aligned && !twopass) {
+        CU(ctx->group_ws.reserve(group_fused_ws_bytes(ncols)));
+        ctx->last_path = 2;
+        const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, mins, bits,
+                                                  d_offs, nbytes, out, out_col_stride, out_col_stride, ctx->group_ws.p, any_i);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused column encode: %s", cudaGetErrorString(e));
+    } else {
+        ctx->last_path = 0;
+        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
+                              d_flags, d_flags + FLAG_ERR, mins, bits, d_offs, nbytes, out, out_col_stride, out_col_stride, nullptr,
+                              fast && any_f, fast && any_i);
+    }
+    CU(cudaGetLastError());
+    return MNW_OK;
 }
 
 int mnw_encode_int_group_gather(mnw_ctx *ctx, const int64_t *col, int64_t ncol, const int64_t *idx, int64_t nblocks,
@@ -688,6 +777,81 @@ int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const 
     return MNW_OK;
 }
 
+// The minp encode of a batch of files whose group parameters are in the device table `tab`.  fp (host copy of the
+// table) is null when the parameters were derived on the device (k_vec3_params): the fused kernels are then launched on
+// the strength of the shape alone and return at once if the device raised the skip flag; the generic kernels, gated on
+// the abort flag, take over.  The flag words have been reset by the caller.
+static int encode_vec3_core(mnw_ctx *ctx, const FloatParams *tab, const std::vector<FloatParams> *fp, int desc_per_file,
+                            const float *aos, int64_t nfile, int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
+                            int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
+    const int64_t ndesc = desc_per_file ? 3 * nfiles : 3;
+    const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells, n = nsub * nsub * nsub;
+    const int64_t nb = nfiles * 3 * sc3;
+    int *d_flags = ctx->flags.as<int>();
+    if (nb == 0) return MNW_OK;
+
+    BatchShape sh = {};
+    sh.nblocks = nb; sh.nchains = 3 * nfiles; sh.blocks_per_chain = sc3; sh.uniform_n = n;
+    sh.total_tiles = nb * ((n + PACK_TILE - 1) / PACK_TILE);
+    sh.total_chunks = nb * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
+    if (sh.total_tiles >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
+    launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, tab, desc_per_file);
+
+    bool fused_ok, pipe_ok;
+    if (fp) {
+        fused_ok = fused_vec3_supported(fp->data(), ndesc, (int)nfile, (int)subcells, aos);
+        pipe_ok = pipe_vec3_supported(fp->data(), ndesc);
+    } else {   // shape and alignment only; k_vec3_params vouches for the parameters (or raises the skip flag)
+        fused_ok = (nsub == 16 || nsub == 32 || nsub == 64 || nsub == 128) && ((uintptr_t)aos & 15) == 0 && nfile <= 1024;
+        pipe_ok = true;
+    }
+    if (!ctx->force_generic && fused_ok) {
+        ctx->last_path = 1;
+        CU(ctx->fused_ws.reserve(fused_work_bytes(nb)));
+        FusedWork W = {};
+        W.pub = ctx->fused_ws.as<unsigned long long>();
+        W.repack_list = (int64_t *)(W.pub + nb);
+        W.err = d_flags + FLAG_ERR; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
+        W.skip = fp ? nullptr : d_flags + 5;
+        CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
+        // The cooperative schedule owns the whole GPU while it runs: right for large batches, but calls on a
+        // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
+        void *coop_ws = nullptr;
+        const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
+        if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
+            CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
+            coop_ws = ctx->coop_ws.p;
+        }
+        const cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
+                                                ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
+                                                pipe_ok, coop_ws);
+        if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
+        if (e == cudaErrorNotSupported) {   // no fused kernel for this shape on this device after all: the generic kernels
+            ctx->last_path = 0;
+            launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                                  ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
+                                  out_axis_stride, out_axis_stride);
+            CU(cudaGetLastError());
+            return MNW_OK;
+        }
+        // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
+        launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,
+                         out, out_axis_stride, out_axis_stride, d_flags + FLAG_ERR);
+        // blocks that need the exact sequential periodicMin: the whole call again, generically
+        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                              ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
+                              out_axis_stride, out_axis_stride, W.abort_flag);
+        CU(cudaGetLastError());
+        return MNW_OK;
+    }
+    ctx->last_path = 0;
+    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                          ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
+                          out_axis_stride, out_axis_stride);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
 int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int desc_per_file, const float *aos,
                                  int64_t nfile, int64_t subcells, int64_t nfiles, int64_t *mins, int64_t *bits,
                                  int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
@@ -701,63 +865,87 @@ int mnw_encode_vec3_subcells_dev(mnw_ctx *ctx, const mnw_float_desc *desc, int d
     const FloatParams *tab = nullptr;
     rc0 = upload_params(ctx, desc, ndesc, fp, &tab);
     if (rc0) return rc0;
-    const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells, n = nsub * nsub * nsub;
-    const int64_t nb = nfiles * 3 * sc3;
-    int rc = reserve_batch(ctx, nb, 3 * nfiles);
+    const int64_t sc3 = subcells * subcells * subcells;
+    int rc = reserve_batch(ctx, nfiles * 3 * sc3, 3 * nfiles);
     if (rc) return rc;
-    int *d_flags = ctx->flags.as<int>();
     { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
-    if (nb == 0) return MNW_OK;
+    return encode_vec3_core(ctx, tab, &fp, desc_per_file, aos, nfile, subcells, nfiles, mins, bits, offsets, out, out_axis_stride, out_len);
+}
 
-    BatchShape sh = {};
-    sh.nblocks = nb; sh.nchains = 3 * nfiles; sh.blocks_per_chain = sc3; sh.uniform_n = n;
-    sh.total_tiles = nb * ((n + PACK_TILE - 1) / PACK_TILE);
-    sh.total_chunks = nb * ((n + STATS_CHUNK - 1) / STATS_CHUNK);
-    if (sh.total_tiles >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
-    launch_build_vec3(ctx->L, ctx->descs.as<BlockDesc>(), nfiles, aos, (int32_t)nfile, (int32_t)subcells, tab, desc_per_file);
+int mnw_minp_encode_vectors_dev(mnw_ctx *ctx, const float *aos, int64_t nfile, int64_t subcells, int64_t nfiles, int periodic,
+                                float L, float dx, mnw_float_desc *desc_dev, int64_t *mins, int64_t *bits, int64_t *offsets,
+                                uint8_t *out, int64_t out_axis_stride, int64_t *out_len) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0 || nfile > 2048)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    const int64_t sc3 = subcells * subcells * subcells, np = nfile * nfile * nfile, nsub = nfile / subcells;
+    int rc = reserve_batch(ctx, nfiles * 3 * sc3, 3 * nfiles);
+    if (rc) return rc;
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
+    if (nfiles == 0) return MNW_OK;
+    if (periodic) {   // [0, L) on every axis (go/minp/minp.go:88-90): the parameters are known on the host
+        mnw_float_desc d[3];
+        for (int k = 0; k < 3; k++) {
+            memset(&d[k], 0, sizeof d[k]);
+            d[k].low = 0.0f; d[k].high = L; d[k].pixels = mnw_float_group_pixels(0.0f, L, dx); d[k].periodic = 1;
+        }
+        std::vector<FloatParams> fp;
+        const FloatParams *tab = nullptr;
+        rc = upload_params(ctx, d, 3, fp, &tab);
+        if (rc) return rc;
+        if (desc_dev) {
+            std::vector<mnw_float_desc> all((size_t)(3 * nfiles));
+            for (size_t i = 0; i < all.size(); i++) all[i] = d[i % 3];
+            CU(cudaMemcpyAsync(desc_dev, all.data(), all.size() * sizeof(mnw_float_desc), cudaMemcpyHostToDevice, ctx->L.stream));   // pageable: staged before return
+        }
+        return encode_vec3_core(ctx, tab, &fp, 0, aos, nfile, subcells, nfiles, mins, bits, offsets, out, out_axis_stride, out_len);
+    }
+    // non-periodic (go/minp/minp.go:92-95): bounds() per file, then the three FloatGroups' parameters, all on the device
+    if ((np + 32767) / 32768 >= 65536LL * 32768 || nfiles > 65535) return fail(ctx, MNW_ERR_ARG, "too many files in one call");
+    CU(ctx->aux.reserve(24 * (size_t)nfiles + 64));
+    CU(ctx->params.reserve(sizeof(FloatParams) * 3 * (size_t)nfiles));
+    launch_vec3_limits(ctx->L, aos, np, nfiles, ctx->aux.as<uint32_t>());
+    int *d_flags = ctx->flags.as<int>();
+    launch_vec3_params(ctx->L, ctx->aux.as<uint32_t>(), nfiles, dx, ctx->params.as<FloatParams>(), desc_dev, d_flags + 5, d_flags + 2,
+                       nsub == 16 ? 0 : 1);
+    CU(cudaGetLastError());
+    return encode_vec3_core(ctx, ctx->params.as<FloatParams>(), nullptr, 1, aos, nfile, subcells, nfiles, mins, bits, offsets, out,
+                            out_axis_stride, out_len);
+}
 
-    if (!ctx->force_generic && fused_vec3_supported(fp.data(), ndesc, (int)nfile, (int)subcells, aos)) {
-        ctx->last_path = 1;
-        CU(ctx->fused_ws.reserve(fused_work_bytes(nb)));
-        FusedWork W = {};
-        W.pub = ctx->fused_ws.as<unsigned long long>();
-        W.repack_list = (int64_t *)(W.pub + nb);
-        W.err = d_flags + 1; W.abort_flag = d_flags + 2; W.repack_count = d_flags + 3; W.ticket = (unsigned int *)(d_flags + 4);
-        CU(cudaMemsetAsync(W.pub, 0, 8 * (size_t)nb, ctx->L.stream));
-        // The cooperative schedule owns the whole GPU while it runs: right for large batches, but calls on a
-        // file or two (the host-pointer entry points, several contexts at a time) overlap better as clusters.
-        void *coop_ws = nullptr;
-        const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
-        if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
-            CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
-            coop_ws = ctx->coop_ws.p;
+int mnw_minp_decode_vectors_dev(mnw_ctx *ctx, const mnw_float_desc *desc_dev, const uint8_t *data, int64_t data_axis_stride,
+                                const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t nfile, int64_t subcells,
+                                int64_t nfiles, int periodic, float L, const mnw_jitter *jitter, float *aos_out) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (nfile <= 0 || subcells <= 0 || nfile % subcells != 0 || nfiles < 0 || !desc_dev)
+        return fail(ctx, MNW_ERR_ARG, "vec3: nfile = %lld, subcells = %lld", (long long)nfile, (long long)subcells);
+    DecodeHost h;
+    h.mode = 2;
+    h.tab_per_file = 1;
+    CU(ctx->params.reserve(sizeof(FloatParams) * 3 * (size_t)nfiles));
+    launch_params_from_desc(ctx->L, desc_dev, 3 * nfiles, ctx->params.as<FloatParams>());
+    h.tab = ctx->params.as<FloatParams>();
+    h.low_nonneg = periodic != 0 && L > 0.0f;   // a periodic field's groups are [0, L): every decoded value is >= +0
+    if (jitter) {
+        if (jitter->mode < 0 || jitter->mode > 2) return fail(ctx, MNW_ERR_ARG, "unknown jitter mode %d", jitter->mode);
+        h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0;
+        if (h.jmode == 2) {
+            if (!jitter->u_stream) return fail(ctx, MNW_ERR_ARG, "jitter mode STREAM without u_stream");
+            h.u = jitter->u_stream;
         }
-        const cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
-                                                ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
-                                                pipe_vec3_supported(fp.data(), ndesc), coop_ws);
-        if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
-        if (e == cudaErrorNotSupported) {   // no fused kernel for this shape on this device after all: the generic kernels
-            ctx->last_path = 0;
-            launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
-                                  ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
-                                  out_axis_stride, out_axis_stride);
-            CU(cudaGetLastError());
-            return MNW_OK;
-        }
-        // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
-        launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,
-                         out, out_axis_stride, out_axis_stride, d_flags + 1);
-        // blocks that need the exact sequential periodicMin: the whole call again, generically
-        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
-                              ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
-                              out_axis_stride, out_axis_stride, W.abort_flag);
-        CU(cudaGetLastError());
+    }
+    const int64_t sc3 = subcells * subcells * subcells, nsub = nfile / subcells;
+    h.data = data; h.stream_len = data_axis_stride; h.offsets = offsets; h.mins = mins; h.bits = bits;
+    h.n = nsub * nsub * nsub; h.nsel = nfiles * 3 * sc3; h.wrap_L = periodic ? L : 0.0f;
+    h.nfile = (int32_t)nfile; h.subcells = (int32_t)subcells; h.out = aos_out;
+    if (!ctx->force_generic && h.jmode != 2 && fused_decode_vec3_supported((int)nfile, (int)subcells, aos_out)) {
+        cudaError_t e = launch_fused_decode_vec3(ctx->L, h, nfiles);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused vec3 decode: %s", cudaGetErrorString(e));
         return MNW_OK;
     }
-    ctx->last_path = 0;
-    launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
-                          ctx->slow.as<int64_t>(), d_flags, d_flags + 1, mins, bits, offsets, out_len, out,
-                          out_axis_stride, out_axis_stride);
+    launch_decode(ctx->L, h);
     CU(cudaGetLastError());
     return MNW_OK;
 }
@@ -930,6 +1118,35 @@ int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint32_t firs
     CU(cudaStreamSynchronize(ctx->L.stream));
     if (mismatches) *mismatches = h[0];
     if (accepted) *accepted = h[1];
+    return MNW_OK;
+}
+
+int mnw_selftest_log10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64_t *mismatches) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if ((uint64_t)first_bits + count > (1ULL << 32)) return fail(ctx, MNW_ERR_ARG, "bit pattern range exceeds 2^32");
+    CU(ctx->meta.reserve(64));
+    launch_selftest_log10(ctx->L, first_bits, count, ctx->meta.as<unsigned long long>());
+    CU(cudaGetLastError());
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, ctx->meta.p, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    if (mismatches) *mismatches = h;
+    return MNW_OK;
+}
+
+int mnw_pow10_f32(mnw_ctx *ctx, const float *x, int64_t n, float *out) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (n < 0) return fail(ctx, MNW_ERR_ARG, "negative length");
+    if (n == 0) return MNW_OK;
+    CU(ctx->in.reserve(4 * (size_t)n));
+    CU(ctx->dec_out.reserve(4 * (size_t)n));
+    CU(cudaMemcpyAsync(ctx->in.p, x, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    launch_pow10_f32(ctx->L, ctx->in.as<float>(), n, ctx->dec_out.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->dec_out.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
     return MNW_OK;
 }
 

@@ -185,9 +185,37 @@ MNW_D int quantize_fast(float v, float low, float rcp, float ndx /* = -dx */) {
     return __float2int_rd(y);
 }
 
+// float32(math.Log10(float64(x))), go/minh/minh.go:143, at a fraction of the FP64 work of go_log10.  A float32 has
+// 24 mantissa bits: m = c_k (1 + r) with c_k the centre of its 1/128 interval and |r| <= 2^-8, so
+// log10(x) = e log10(2) + log10(c_k) + ln(1 + r) / ln(10) with a 5-term series (absolute error < 2^-46).  go_log10's own
+// absolute error is below 2^-45.  The float32 rounding of BOTH is therefore the same number unless a rounding boundary
+// lies within 2^-40 of the value: then (and for zero, negative, subnormal, infinite and NaN inputs) go_log10 decides.
+__device__ const double2 MNW_LOG10_TAB[128] = {
+#include "log10_table.inc"
+};
+MNW_D float go_log10_f32(float x) {
+    const unsigned u = __float_as_uint(x);
+    if (u - 0x00800000u < 0x7f000000u) {   // positive and normal
+        const int e = (int)(u >> 23) - 127;
+        const unsigned mant = u & 0x7fffffu;
+        const double m = __hiloint2double((int)(0x3ff00000u | (mant >> 3)), (int)(mant << 29));   // 1.mant
+        const double2 t = __ldg(&MNW_LOG10_TAB[mant >> 16]);
+        const double r = fma(m, t.x, -1.0);
+        double p = fma(r, 0.2, -0.25);
+        p = fma(r, p, 0.33333333333333331);
+        p = fma(r, p, -0.5);
+        p = fma(r, p, 1.0);
+        p = p * r;   // ln(1 + r)
+        const double y = fma(p, 0x1.bcb7b1526e50ep-2 /* 1 / ln 10 */, fma((double)e, 0x1.34413509f79ffp-2 /* log10 2 */, t.y));
+        const float lo = __double2float_rn(y - 0x1p-40), hi = __double2float_rn(y + 0x1p-40);
+        if (lo == hi) return lo;
+    }
+    return __double2float_rn(go_log10((double)x));
+}
+
 // minh processFloatGroup, go/minh/minh.go:141-149 (hi_clamp = Nextafter32(High, -Inf)).
 MNW_D float minh_pre(float v, bool is_log, bool clamp, float low, float high, float hi_clamp) {
-    if (is_log) v = __double2float_rn(go_log10((double)v));
+    if (is_log) v = go_log10_f32(v);
     if (clamp) {
         if (v < low) v = low;
         if (v >= high) v = hi_clamp;

@@ -54,6 +54,18 @@ struct FloatParams {
     float rcp;       // RN(1 / dx)
 };
 
+// The context's 16 device flag words: [0] slow-block count, [2] abort flag (fused minp encode), [3] repack / wide block
+// count, [4] ticket, [FLAG_ERR] the sticky ERROR word (1: value range 2^64-1, 2: packed output does not fit), which
+// only mnw_sync / the host-pointer entry points read and clear; every call zeroes the words before it.
+constexpr int FLAG_ERR = 15;
+
+// mnw_float_desc (include/minnow_cuda.h) as the kernels see it: same 24 bytes.
+struct FloatDescPod {
+    float low, high;
+    int64_t pixels;
+    uint8_t periodic, log10, clamp, reserved[5];
+};
+
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_CHUNK = 16384;   // elements per k_stats CTA
 constexpr int PACK_THREADS = 128;

@@ -23,6 +23,8 @@ struct FusedWork {
     int *repack_count;
     int *abort_flag;           // some block needs the exact sequential periodicMin: rerun generically
     int *err;
+    const int *skip;           // (may be null) set before the launch by k_vec3_params: the group parameters derived on
+                               // the device are outside what the fused kernels cover -- every CTA returns at once
 };
 
 // minp sub-cell gather + 3-axis encode.  Supported when nfile/subcells is 16, 32
@@ -45,5 +47,8 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
 // d_out2[0] = mismatches among accepted fast results, d_out2[1] = accepted results.
 void launch_selftest_fastdiv(Launcher &L, const FloatParamsHost &fp, unsigned long long first,
                              unsigned long long count, unsigned long long *d_out2);
+
+void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out);
+void launch_pow10_f32(Launcher &L, const float *x, long long n, float *out);
 
 }  // namespace mnw

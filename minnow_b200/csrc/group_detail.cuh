@@ -269,6 +269,57 @@ __device__ __forceinline__ void slow_block(const BlockDesc &d, BlockStat *sb, in
     __syncthreads();
 }
 
+// slow_block for ONE warp (all 32 lanes of the calling warp, no CTA-level barrier): the exact sequential periodicMin and
+// the min / max of bound() of a block with out-of-range pixel indices.
+__device__ __forceinline__ void slow_block_warp(const BlockDesc &d, BlockStat *sb, int *err) {
+    const long long P = d.pixels;
+    const int lane = threadIdx.x & 31;
+    long long x0 = block_value(d, 0), width = 1;
+    bool returned_zero = false;
+    for (int64_t base = 0; base < d.n && !returned_zero; base += 32) {
+        int64_t i = base + lane;
+        bool valid = i < d.n;
+        long long q = valid ? block_value(d, i) : 0;
+        unsigned pending = __ballot_sync(0xffffffffu, valid);
+        while (pending) {
+            long long x1 = (long long)((unsigned long long)x0 + (unsigned long long)width - 1ULL);
+            if (x1 >= P) x1 = (long long)((unsigned long long)x1 - (unsigned long long)P);
+            long long d0 = periodic_distance(q, x0, P);
+            long long d1 = periodic_distance(q, x1, P);
+            bool inside = d0 > 0 && d1 < 0;
+            unsigned act = __ballot_sync(0xffffffffu, !inside) & pending;
+            if (!act) break;
+            int j = __ffs(act) - 1;
+            long long e0 = __shfl_sync(0xffffffffu, d0, j);
+            long long e1 = __shfl_sync(0xffffffffu, d1, j);
+            if (e1 > (long long)(0ULL - (unsigned long long)e0)) {
+                width = (long long)((unsigned long long)width + (unsigned long long)e1);
+            } else {
+                x0 = (long long)((unsigned long long)x0 + (unsigned long long)e0);
+                if (x0 < 0) x0 = (long long)((unsigned long long)x0 + (unsigned long long)P);
+                width = (long long)((unsigned long long)width - (unsigned long long)e0);
+            }
+            if (width > P / 2) { returned_zero = true; break; }
+            pending &= ~((2u << j) - 1u);  // elements up to j are done
+        }
+    }
+    const long long pmin = returned_zero ? 0 : x0;   // uniform across the warp
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    for (int64_t i = lane; i < d.n; i += 32) {
+        long long q = bound1(block_value(d, i), pmin, P);
+        mn = q < mn ? q : mn;
+        mx = q > mx ? q : mx;
+    }
+    mn = warp_min_ll(mn); mx = warp_max_ll(mx);
+    if (lane == 0) {
+        BlockStat s = *sb;
+        s.pmin = pmin; s.do_bound = 1; s.min = mn;
+        finish_stat(s, d.n, (unsigned long long)mx - (unsigned long long)mn, err);
+        *sb = s;
+    }
+    __syncwarp();
+}
+
 // One 4096-element tile of one block through the 64-bit capable packer (any width, any access pattern), by a CTA of
 // PACK_THREADS threads: bound, subtract min, LSB-first packing (go/bit/bit.go:84-134) to the byte-aligned
 // destination.  s_out: PACK_THREADS * 64 + 4 words of shared scratch.  Ends with a __syncthreads().

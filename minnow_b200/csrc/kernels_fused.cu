@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_vec3(const FusedArgs A) {
     // rows of one batch: either all in one z-plane (RPP*UNROLL divides NSUB) or one row per
     // plane step (RPP is a multiple of NSUB); both make the row offset linear in u
     static_assert(NSUB % (RPP * UNROLL) == 0 || RPP % NSUB == 0, "batch rows are equally spaced");
+    if (A.W.skip && *A.W.skip) return;   // uniform over the grid: written before the launch
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *stage = (unsigned short *)smem_raw;   // [3][CHUNK], swizzled
@@ -737,6 +738,37 @@ void launch_selftest_fastdiv(Launcher &L, const FloatParamsHost &fp, unsigned lo
     cudaMemsetAsync(d_out2, 0, 16, L.stream);
     if (count == 0) return;
     k_selftest_fastdiv<<<148 * 8, 256, 0, L.stream>>>(fp, first, count, d_out2, d_out2 + 1);
+    L.count++;
+}
+
+// go_log10_f32 (table + series, exact fallback) against float32(go_log10(float64 x)) over float bit patterns
+__global__ void k_selftest_log10(unsigned long long first, unsigned long long count, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)(first + i));
+        const unsigned a = __float_as_uint(go_log10_f32(x)), b = __float_as_uint(__double2float_rn(go_log10((double)x)));
+        if (a != b && !((a & 0x7fffffffu) > 0x7f800000u && (b & 0x7fffffffu) > 0x7f800000u)) bad++;   // (any NaN equals any NaN)
+    }
+    for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out) {
+    cudaMemsetAsync(d_out, 0, 8, L.stream);
+    if (count == 0) return;
+    k_selftest_log10<<<148 * 8, 256, 0, L.stream>>>(first, count, d_out);
+    L.count++;
+}
+
+// float32(math.Pow(10, float64(x))) of a raw float32 column (minh Log columns stored as Float32Group, go/minh/minh.go:315-319)
+__global__ void k_pow10_f32(const float *x, long long n, float *out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __double2float_rn(go_pow10((double)x[i]));
+}
+void launch_pow10_f32(Launcher &L, const float *x, long long n, float *out) {
+    if (n == 0) return;
+    long long g = (n + 255) / 256;
+    k_pow10_f32<<<(unsigned)(g < 148 * 16 ? g : 148 * 16), 256, 0, L.stream>>>(x, n, out);
     L.count++;
 }
 

@@ -27,7 +27,8 @@ namespace mnw {
 // (BoundaryWriter.Column, go/minh/boundary.go:184-225).
 __global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                                const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                               FloatParams fp, int64_t blocks_per_chain, const int64_t *idx) {
+                               FloatParams fp, int64_t blocks_per_chain, const int64_t *idx, BlockStat *stats_init,
+                               unsigned long long *ws_zero) {
     int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= nb) return;
     BlockDesc d = {};
@@ -51,6 +52,17 @@ __global__ void k_build_contig(BlockDesc *descs, int64_t nb, int32_t kind, const
     d.tile0 = tile0 ? tile0[b] : b * tpb;
     d.chunk0 = chunk0 ? chunk0[b] : b * cpb;
     descs[b] = d;
+    if (stats_init) {   // what k_init would do in a launch of its own (the fused group encode)
+        BlockStat s = {};
+        s.wmin = ~0ULL; s.wmax = 0ULL;
+        s.qmin = LLONG_MAX; s.qmax = LLONG_MIN;
+        s.q0 = d.n > 0 ? block_value(d, 0) : 0;
+        stats_init[b] = s;
+    }
+    if (ws_zero) {      // k_group_fused's per-block words: look-back word, wide list entry, counter
+        ws_zero[b] = 0ULL; ws_zero[nb + b] = 0ULL;
+        ((unsigned *)(ws_zero + 2 * nb))[b] = 0u;
+    }
 }
 
 // minp.Writer.Vectors block order: per file f, axis k, sub-cell sc (go/minp/minp.go:112-118)
@@ -285,6 +297,66 @@ __global__ void __launch_bounds__(LIMITS4_THREADS) k_vec3_limits4(const float *_
     __syncthreads();
     if (threadIdx.x < 3) atomicMin(&keys[f * 6 + threadIdx.x], s_k[threadIdx.x]);
     else if (threadIdx.x < 6) atomicMax(&keys[f * 6 + threadIdx.x], s_k[threadIdx.x]);
+}
+
+// The three FloatGroups of every file of a NON-periodic field, derived on the device from the limits keys -- what
+// minp.Writer.Vectors does on the host between bounds() and FloatGroup (go/minp/minp.go:92-95, go/writer.go:72-75):
+// lo = min, hi = Nextafter32(max, 2 * max), pixels = int64(ceil(float64((hi - lo) / dx))) in float32, and the derived
+// constants of FloatParams exactly as api.cu to_params computes them on the host.  flags[0] (skip) and flags[1] (abort)
+// are raised when some group is outside what the fused minp kernels cover (they then return at once and the generic
+// kernels, gated on the abort flag, encode the batch).
+__global__ void k_vec3_params(const uint32_t *keys, int64_t nfiles, float dx_user, FloatParams *tab, FloatDescPod *desc_out,
+                              int *skip, int *abort_flag, int need_pipe) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= 3 * nfiles) return;
+    const int64_t f = i / 3;
+    const int k = (int)(i % 3);
+    auto key_to_float = [](uint32_t kk) { return __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk); };
+    const float lo = key_to_float(keys[6 * f + k]), mx = key_to_float(keys[6 * f + 3 + k]);
+    const float hi = nextafterf(mx, __fmul_rn(2.0f, mx));                       // go/minp/minp.go:94
+    const float span = __fsub_rn(hi, lo);
+    const double c = ceil((double)__fdiv_rn(span, dx_user));                    // go/writer.go:73
+    const long long pixels = (c >= -9223372036854775808.0 && c < 9223372036854775808.0) ? (long long)c : LLONG_MIN;
+    FloatParams p = {};
+    p.low = lo; p.high = hi; p.pixels = pixels;
+    p.dx = __fdiv_rn(span, __ll2float_rn(pixels));                               // go/group.go:316
+    p.hi_clamp = nextafterf(hi, -INFINITY);
+    p.flags = F_PERIODIC;                                                        // go/writer.go:74
+    p.rcp = __fdiv_rn(1.0f, p.dx);
+    const bool normal_dx = fabsf(p.dx) >= 1.17549435e-38f && fabsf(p.dx) <= 3.40282347e38f;
+    const bool normal_rcp = fabsf(p.rcp) >= 1.17549435e-38f && fabsf(p.rcp) <= 3.40282347e38f;
+    if (normal_dx && normal_rcp && p.dx > 0x1p-60f && p.dx < 0x1p60f && pixels >= 2) p.flags |= F_FASTDIV;
+    tab[i] = p;
+    FloatDescPod d = {};
+    d.low = lo; d.high = hi; d.pixels = pixels; d.periodic = 1;
+    if (desc_out) desc_out[i] = d;
+    if (pixels < 1 || pixels >= (1LL << 30) || (need_pipe && pixels > (1LL << 22))) { atomicExch(skip, 1); atomicExch(abort_flag, 1); }
+}
+
+void launch_vec3_params(Launcher &L, const uint32_t *keys, int64_t nfiles, float dx, FloatParams *tab, void *desc_out, int *skip,
+                        int *abort_flag, int need_pipe) {
+    if (nfiles == 0) return;
+    k_vec3_params<<<(unsigned)((3 * nfiles + 127) / 128), 128, 0, L.stream>>>(keys, nfiles, dx, tab, (FloatDescPod *)desc_out, skip, abort_flag, need_pipe);
+    L.count++;
+}
+
+// FloatParams from group descriptors that live on the device (the decode side of the same fields).
+__global__ void k_params_from_desc(const FloatDescPod *desc, int64_t n, FloatParams *tab) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FloatDescPod d = desc[i];
+    FloatParams p = {};
+    p.low = d.low; p.high = d.high; p.pixels = d.pixels;
+    p.dx = __fdiv_rn(__fsub_rn(d.high, d.low), __ll2float_rn(d.pixels));
+    p.hi_clamp = nextafterf(d.high, -INFINITY);
+    p.flags = (d.periodic ? F_PERIODIC : 0) | (d.log10 ? F_LOG10 : 0) | (d.clamp ? F_CLAMP : 0);
+    p.rcp = __fdiv_rn(1.0f, p.dx);
+    tab[i] = p;
+}
+void launch_params_from_desc(Launcher &L, const void *desc, int64_t n, FloatParams *tab) {
+    if (n == 0) return;
+    k_params_from_desc<<<(unsigned)((n + 127) / 128), 128, 0, L.stream>>>((const FloatDescPod *)desc, n, tab);
+    L.count++;
 }
 
 // ---------------------------------------------------------------------------
@@ -817,9 +889,11 @@ static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n +
 
 void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx) {
+                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx, BlockStat *stats_init,
+                         void *ws_zero) {
     if (nb == 0) return;
-    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, fp, blocks_per_chain, idx);
+    k_build_contig<<<grid_for(nb, 256), 256, 0, L.stream>>>(descs, nb, kind, src, n, starts, tile0, chunk0, fp, blocks_per_chain, idx,
+                                                             stats_init, (unsigned long long *)ws_zero);
     L.count++;
 }
 

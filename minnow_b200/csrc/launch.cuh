@@ -75,12 +75,16 @@ struct DecodeHost {
 // kernels_generic.cu
 void launch_build_contig(Launcher &L, BlockDesc *descs, int64_t nb, int32_t kind, const void *src, int64_t n,
                          const int64_t *starts, const int64_t *tile0, const int64_t *chunk0,
-                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx = nullptr);
+                         const FloatParamsHost &fp, int64_t blocks_per_chain, const int64_t *idx = nullptr,
+                         BlockStat *stats_init = nullptr, void *ws_zero = nullptr);
 void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const float *aos, int32_t nfile,
                        int32_t subcells, const FloatParams *tab, int tab_per_file);
 // bounds() of minp.Writer.Vectors (go/minp/minp.go:291-300): keys[f*6 + k] = min, [f*6 + 3 + k] = max,
 // as order-preserving uint32 keys (decode with key_to_float on the host).
 void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int64_t nfiles, uint32_t *keys);
+void launch_vec3_params(Launcher &L, const uint32_t *keys, int64_t nfiles, float dx, FloatParams *tab, void *desc_out, int *skip,
+                        int *abort_flag, int need_pipe);
+void launch_params_from_desc(Launcher &L, const void *desc, int64_t n, FloatParams *tab);
 void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh,
                            int64_t *slow_list, int *slow_count, int *err, int64_t *mins, int64_t *bits,
                            int64_t *offsets, int64_t *out_len, uint8_t *out, int64_t chain_stride,
@@ -90,7 +94,7 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
 size_t group_fused_ws_bytes(int64_t nblocks);
 cudaError_t launch_group_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh, int *flags,
                                 int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
-                                int64_t chain_stride, int64_t chain_cap, void *ws);
+                                int64_t chain_stride, int64_t chain_cap, void *ws, bool has_i64, bool prepared = false);
 void launch_init_stats(Launcher &L, const BlockDesc *descs, BlockStat *stats, int64_t nb);
 void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
                       const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,

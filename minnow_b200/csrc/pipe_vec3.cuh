@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     constexpr int LT = 32 * PIPE_LW, PT = 32 * (PIPE_PW + 1);   // loader threads; packer + scanner threads
     constexpr int NGROUPS = 3 * (CHUNK / 1024);   // pack groups per CTA and unit
     constexpr int UM = PIPE_USLOTS - 1;
+    if (A.W.skip && *A.W.skip) return;   // uniform over the grid: written before the launch
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *stage = (unsigned short *)smem_raw;   // [3][CHUNK], swizzled like k_fused_vec3

@@ -138,7 +138,7 @@ class Reader:
             if t not in (minnow.FloatGroup, minnow.Float32Group):
                 raise TypeError("Column '%s' does not hold float32" % name)
             # float32(math.Pow(10, float64(x))) of a Log column (:315-319) runs in the decode kernel
-            out[name] = self.f.Data(idx, log10=(t == minnow.FloatGroup and self.Columns[c]["Log"] != 0))
+            out[name] = self.f.Data(idx, log10=bool(self.Columns[c]["Log"] != 0))
         return out
 
     def Ints(self, names):                                                                   # :228-240

@@ -266,7 +266,8 @@ class Reader:
         k = b - g.start_block
         raw = self.f.read(g.sizes[k])
         if g.gt in _FIXED:                                     # fixedSizeGroup.readData
-            return np.frombuffer(raw, _FIXED[g.gt]).copy()
+            x = np.frombuffer(raw, _FIXED[g.gt]).copy()
+            return self.ctx.pow10_f32(x) if (log10 and g.gt == Float32Group) else x
         data = np.frombuffer(raw, np.uint8)
         meta = (np.zeros(1, np.int64), np.array([g.mins[k]], np.int64), np.array([g.bits[k]], np.int64))
         if g.gt == IntGroup:                                   # intGroup.readData, go/group.go:257-263

@@ -99,6 +99,8 @@ def _declare(L):
         "orc_minh_close": (_i64, [_p, C.POINTER(_p)]),
         "orc_bench_minp_encode": (_i64, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _int]),
         "orc_bench_minp_decode": (None, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _int, _f32, _int, _u64, _p, _int]),
+        "orc_bench_group_encode": (_i64, [_int, _p, _i64, _i64, _f32, _f32, _i64, _int, _int, _p, _p, _p, _p, _i64, _int]),
+        "orc_bench_group_decode": (None, [_int, _p, _i64, _i64, _i64, _p, _p, _p, _f32, _f32, _i64, _int, _int, _u64, _p, _int]),
         "orc_max_threads": (_int, []),
     }
     for name, (res, args) in sig.items():
@@ -444,6 +446,31 @@ def bench_minp_decode(packed, stride, nfile, sub_cells, low, high, pixels, mins,
     lib().orc_bench_minp_decode(_ptr(packed), stride, nfile, sub_cells, _ptr(low), _ptr(high), _ptr(pixels),
                                 _ptr(mins), _ptr(bits), int(periodic), Lbox, jitter_mode, seed,
                                 _ptr(out), threads)
+    return out
+
+
+def bench_group_encode(x, n, nblocks, desc=None, threads=0):
+    """nblocks blocks of one group; desc = None for an IntGroup (x int64) or (low, high, pixels, is_log, clamp).
+    -> mins, bits, nbytes, packed (block b at b * stride), stride, total"""
+    kind = 0 if desc is None else 1
+    x = _c(x, np.int64 if kind == 0 else np.float32)
+    low, high, pixels, is_log, clamp = desc if desc is not None else (0.0, 0.0, 0, 0, 0)
+    stride = 8 * n + 8
+    mins, bits, nbytes = (np.zeros(nblocks, np.int64) for _ in range(3))
+    out = np.zeros(nblocks * stride, np.uint8)
+    total = lib().orc_bench_group_encode(kind, _ptr(x), n, nblocks, low, high, pixels, int(is_log), int(clamp),
+                                         _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), stride, threads)
+    return mins, bits, nbytes, out, stride, int(total)
+
+
+def bench_group_decode(packed, stride, n, mins, bits, desc=None, sel=None, jitter_mode=1, seed=0, threads=0):
+    kind = 0 if desc is None else 1
+    low, high, pixels, is_log, _ = desc if desc is not None else (0.0, 0.0, 0, 0, 0)
+    s = _c(sel, np.int64) if sel is not None else None
+    nsel = len(s) if s is not None else len(mins)
+    out = np.zeros((nsel, n), np.int64 if kind == 0 else np.float32)
+    lib().orc_bench_group_decode(kind, _ptr(packed), stride, n, nsel, _ptr(s) if s is not None else None, _ptr(mins), _ptr(bits),
+                                 low, high, pixels, int(is_log), jitter_mode, seed, _ptr(out), threads)
     return out
 
 

@@ -1,0 +1,362 @@
+"""GPU parity of what round 2 added, through the C ABI, against the CPU oracle:
+the fused single-read group kernel (k_group_fused) on the BASELINE shapes and its edge cases, the batched column calls,
+device-derived minp group parameters, the benchmarked cooperative full-batch k_pipe_vec3 run byte for byte, block
+selections, the sticky device error word, the STREAM jitter of the vec3 decoder, minh Log columns (fast float32 log10
+on the write side, 10^x on the read side).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import minnow_b200 as mb
+from helpers import oracle_float_group, oracle_int_group, uniform_starts
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = mb.Context(0)
+    yield c
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------- k_group_fused
+@pytest.mark.parametrize("n,nb", [(65536, 16),            # C1: 2^20 halos as 16 blocks
+                                  (4096, 100),            # look-back over more than 32 predecessors
+                                  (4096 * 3 + 20, 5),     # whole tiles + a partial last tile (aligned blocks)
+                                  (5000, 7), (100, 9), (4, 3),   # blocks smaller than two tiles / one tile / one vector
+                                  (1 << 18, 3)])
+def test_group_fused_float_shapes(ctx, orc, n, nb):
+    rng = np.random.default_rng(n + nb)
+    L, dx = 125.0, 0.001
+    px = mb.float_group_pixels(0.0, L, dx)
+    d = mb.FloatDesc.make(0.0, L, px)
+    x = (rng.random(n * nb) * L).astype(np.float32)
+    x[:n] = np.mod(120.0 + 8.0 * rng.random(n), L).astype(np.float32)        # block 0: an arc across the periodic boundary
+    if nb > 2:
+        x[2 * n:3 * n] = np.float32(17.25)                                  # block 2: 0 bits
+    mins, bits, offs, data = ctx.encode_float_group(d, x, n, nb)
+    if (n * 4) % 16 == 0:
+        assert ctx.last_path == 2
+    om, ob, oo, od = oracle_float_group(orc, x, uniform_starts(n, nb), 0.0, L, px)
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo)
+    assert data.tobytes() == od.tobytes()
+    got = ctx.decode_float_blocks(d, data, offs, mins, bits, n, jitter=mb.Jitter.make(mb.JITTER_HASH, 5))
+    for b in range(nb):
+        end = offs[b + 1] if b + 1 < nb else len(data)
+        want = orc.float_block_decode(data[offs[b]:end], n, int(mins[b]), int(bits[b]), 0.0, L, px, 1, 1, 5, b)
+        assert got[b].tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n,nb", [(65536, 16), (4096, 70), (4096 * 2 + 6, 4), (3000, 5), (2, 3)])
+def test_group_fused_int_shapes(ctx, orc, n, nb):
+    rng = np.random.default_rng(7 * n + nb)
+    x = rng.integers(10 ** 9, 10 ** 9 + (1 << 20), n * nb).astype(np.int64)
+    x[:n] = rng.integers(-(1 << 62), 1 << 62, n)          # block 0: wider than 32 bits (the k_pack list)
+    if nb > 1:
+        x[n:2 * n] = -5                                   # block 1: 0 bits
+    mins, bits, offs, data = ctx.encode_int_group(x, n, nb)
+    if (n * 8) % 16 == 0:
+        assert ctx.last_path == 2
+    om, ob, oo, od = oracle_int_group(orc, x, uniform_starts(n, nb))
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo)
+    assert data.tobytes() == od.tobytes()
+    assert np.array_equal(ctx.decode_int_blocks(data, offs, mins, bits, n).reshape(-1), x)
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -3.0, 130.0, 1e30])
+def test_group_fused_bad_values(ctx, orc, bad):
+    """NaN / infinite / out-of-range values: the block's exact sequential periodicMin and the 64-bit packer, inside the
+    fused kernel's flow; the other blocks of the group are unaffected"""
+    rng = np.random.default_rng(11)
+    n, nb, L = 4096 * 4, 6, 125.0
+    px = mb.float_group_pixels(0.0, L, 0.001)
+    d = mb.FloatDesc.make(0.0, L, px)
+    x = (60.0 + 3.0 * rng.random(n * nb)).astype(np.float32)
+    x[3 * n + 777] = bad
+    x[5 * n] = bad            # element 0 of a block
+    mins, bits, offs, data = ctx.encode_float_group(d, x, n, nb)
+    assert ctx.last_path == 2
+    om, ob, oo, od = oracle_float_group(orc, x, uniform_starts(n, nb), 0.0, L, px)
+    assert np.array_equal(mins, om) and np.array_equal(bits, ob) and np.array_equal(offs, oo)
+    assert data.tobytes() == od.tobytes()
+
+
+def test_encode_columns_dev_c3_shape(ctx, orc):
+    """one minh block of the text_to_minh type menu (IntGroup, linear and log10 FloatGroups) in ONE device call"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    n = 4096 * 5 + 12
+    px, lpx = mb.float_group_pixels(0.0, 125.0, 0.001), mb.float_group_pixels(10.0, 15.0, 0.01)
+    dpos, dlog = mb.FloatDesc.make(0.0, 125.0, px, 1, 0, 1), mb.FloatDesc.make(10.0, 15.0, lpx, 1, 1, 1)
+    host = [((np.arange(n, dtype=np.int64) * 3 + rng.integers(0, 3, n)) + 10 ** 9, None),
+            ((rng.random(n) * 130.0 - 2.0).astype(np.float32), dpos),           # some values outside [0, 125): clamped
+            (np.power(10.0, 9.5 + 6.0 * rng.random(n)).astype(np.float32), dlog),
+            (rng.integers(-50, 50, n).astype(np.int64), None),
+            (np.power(10.0, 12.0 + 0.001 * rng.random(n)).astype(np.float32), dlog)]
+    cols = [(torch.from_numpy(a).to(dev), d) for a, d in host]
+    nc = len(cols)
+    stride = 8 * n + 256
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, lens = (torch.zeros(nc, **i64) for _ in range(3))
+    out = torch.zeros(nc * stride, dtype=torch.uint8, device=dev)
+    ctx.encode_columns_dev(cols, n, mins, bits, lens, out, stride)
+    ctx.sync()
+    assert ctx.last_path == 2
+    for c, (a, d) in enumerate(host):
+        if d is None:
+            om, ob, od = orc.int_block_encode(a)
+        else:
+            om, ob, od = orc.float_block_encode(orc.minh_process_float(a, d.log10, d.low, d.high), d.low, d.high, d.pixels)
+        assert (int(mins[c]), int(bits[c]), int(lens[c])) == (om, ob, len(od)), c
+        assert out[c * stride:c * stride + len(od)].cpu().numpy().tobytes() == od.tobytes(), c
+    # the host-pointer form gives the same
+    hm, hb, hp = ctx.encode_columns(host)
+    assert np.array_equal(hm, mins.cpu().numpy()) and np.array_equal(hb, bits.cpu().numpy())
+    for c in range(nc):
+        assert hp[c].tobytes() == out[c * stride:c * stride + len(hp[c])].cpu().numpy().tobytes()
+
+
+def test_log10_float32_fast_form_is_exact(ctx):
+    """go_log10_f32 (table + series + exact fallback) == float32(restated Go math.Log10) on EVERY float32 bit pattern"""
+    assert ctx.selftest_log10(0, 1 << 32) == 0
+
+
+def test_log10_float32_against_numpy(ctx, orc):
+    """and the restated Go math.Log10 itself is a correct log10: within one float32 ulp of numpy's on random inputs
+    (a tolerance test, as the reference's own is: go/minh/minh_test.go:110-113)"""
+    rng = np.random.default_rng(4)
+    x = np.power(10.0, rng.uniform(-30, 30, 200000)).astype(np.float32)
+    got = orc.minh_process_float(x.copy(), 1, -np.inf, np.inf)
+    want = np.log10(x.astype(np.float64)).astype(np.float32)
+    assert np.all(np.abs(got.astype(np.float64) - want) <= np.spacing(np.abs(want)).astype(np.float64))
+
+
+# ---------------------------------------------------------------------------------------- minp, device-derived parameters
+def _files(rng, nfiles, nfile, scale):
+    return [(scale * (f + 1) * rng.standard_normal((nfile ** 3, 3))).astype(np.float32) for f in range(nfiles)]
+
+
+@pytest.mark.parametrize("nfile,subcells,scale", [(128, 2, 150.0), (64, 2, 150.0), (64, 4, 150.0), (128, 2, 4.0e6)])
+def test_minp_vectors_dev_nonperiodic(ctx, orc, nfile, subcells, scale):
+    """mnw_minp_encode_vectors_dev derives limits, pixels and group constants on the device; the result equals the
+    oracle's minp.Writer.Vectors per file.  scale = 4e6: pixel counts beyond 2^22, the generic kernels take over"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(nfile + subcells)
+    nfiles, sc3, n3 = 3, subcells ** 3, nfile ** 3
+    vecs = _files(rng, nfiles, nfile, scale)
+    aos = torch.from_numpy(np.concatenate(vecs)).to(dev)
+    nb = nfiles * 3 * sc3
+    stride = 8 * n3 + 256
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    desc_dev = torch.zeros(24 * 3 * nfiles, dtype=torch.uint8, device=dev)
+    ctx.minp_encode_vectors_dev(aos, nfile, subcells, nfiles, False, 0.0, 1.0, desc_dev, mins, bits, offs, out, stride, out_len)
+    ctx.sync()
+    dd = np.frombuffer(desc_dev.cpu().numpy().tobytes(), np.dtype([("low", "<f4"), ("high", "<f4"), ("pixels", "<i8"), ("flags", "u1", 8)]))
+    m, b, o, ln, outh = (t.cpu().numpy() for t in (mins, bits, offs, out_len, out))
+    for f in range(nfiles):
+        lo, hi = orc.minp_limits(vecs[f], False, 0.0)
+        px = [orc.float_group_pixels(float(lo[k]), float(hi[k]), np.float32(1.0)) for k in range(3)]
+        for k in range(3):
+            assert (dd["low"][3 * f + k], dd["high"][3 * f + k], dd["pixels"][3 * f + k]) == (lo[k], hi[k], px[k])
+            assert dd["flags"][3 * f + k][0] == 1
+        om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(vecs[f], nfile, subcells, lo.tolist(), hi.tolist(), px)
+        sl = slice(f * 3 * sc3, (f + 1) * 3 * sc3)
+        assert np.array_equal(m[sl], om) and np.array_equal(b[sl], ob)
+        for k in range(3):
+            want = b"".join(packed[t * ostride:t * ostride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
+            assert ln[3 * f + k] == len(want)
+            assert outh[(3 * f + k) * stride:(3 * f + k) * stride + len(want)].tobytes() == want
+    assert ctx.last_path == 1
+    # and back: the decode reads the parameters from the same device array
+    dec = torch.zeros((nfiles, n3, 3), dtype=torch.float32, device=dev)
+    ctx.minp_decode_vectors_dev(desc_dev, out, stride, offs, mins, bits, nfile, subcells, nfiles, False, 0.0,
+                                mb.Jitter.make(mb.JITTER_HASH, 9), dec)
+    ctx.sync()
+    f = 1
+    lo, hi = orc.minp_limits(vecs[f], False, 0.0)
+    px = [orc.float_group_pixels(float(lo[k]), float(hi[k]), np.float32(1.0)) for k in range(3)]
+    om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(vecs[f], nfile, subcells, lo.tolist(), hi.tolist(), px)
+    want = np.zeros((n3, 3), np.float32)
+    nsub3 = (nfile // subcells) ** 3
+    sb = [np.zeros(nsub3, np.float32) for _ in range(3)]
+    for sc in range(sc3):
+        for k in range(3):
+            t = k * sc3 + sc
+            sb[k] = orc.float_block_decode(packed[t * ostride:t * ostride + onb[t]], nsub3, int(om[t]), int(ob[t]), float(lo[k]), float(hi[k]),
+                                           px[k], 1, 1, 9, f * 3 * sc3 + t)
+        orc.lib().orc_set_sub_cell(want.ctypes.data, sb[0].ctypes.data, sb[1].ctypes.data, sb[2].ctypes.data, sc, subcells, nfile // subcells)
+    assert dec[f].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_minp_vectors_dev_periodic(ctx, orc):
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    nfile, subcells, nfiles, L, dx = 64, 2, 2, 100.0, 0.01
+    sc3, n3 = subcells ** 3, nfile ** 3
+    vecs = [np.mod(rng.random((n3, 3)) * L, L).astype(np.float32) for _ in range(nfiles)]
+    for v in vecs:
+        v[v >= L] = 0
+    aos = torch.from_numpy(np.concatenate(vecs)).to(dev)
+    nb, stride = nfiles * 3 * sc3, 8 * n3 + 256
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    desc_dev = torch.zeros(24 * 3 * nfiles, dtype=torch.uint8, device=dev)
+    ctx.minp_encode_vectors_dev(aos, nfile, subcells, nfiles, True, L, dx, desc_dev, mins, bits, offs, out, stride, out_len)
+    dec = torch.zeros((nfiles, n3, 3), dtype=torch.float32, device=dev)
+    ctx.minp_decode_vectors_dev(desc_dev, out, stride, offs, mins, bits, nfile, subcells, nfiles, True, L, mb.Jitter.make(mb.JITTER_HASH, 2), dec)
+    ctx.sync()
+    px = mb.float_group_pixels(0.0, L, dx)
+    m, b = mins.cpu().numpy(), bits.cpu().numpy()
+    for f in range(nfiles):
+        om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(vecs[f], nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3)
+        sl = slice(f * 3 * sc3, (f + 1) * 3 * sc3)
+        assert np.array_equal(m[sl], om) and np.array_equal(b[sl], ob)
+    want = orc.bench_minp_decode(packed, ostride, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, om, ob, True, L, 1, 2)
+    # file 1's jitter block ids start at 3 * sc3: decode the oracle's blocks with those ids through the GPU-independent formula
+    got = dec[0].cpu().numpy()
+    om0, ob0, onb0, packed0, ostride0, _ = orc.bench_minp_encode(vecs[0], nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3)
+    want0 = orc.bench_minp_decode(packed0, ostride0, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, om0, ob0, True, L, 1, 2)
+    assert got.tobytes() == want0.tobytes()
+
+
+def test_cooperative_full_batch_bytes_equal_oracle(ctx, orc):
+    """the schedule bench.py times -- cooperative k_pipe_vec3<1, 64> on a batch of >= 256 units, no environment knob --
+    byte for byte against the oracle: (min, bits, offsets), every packed byte, HASH-jitter decoded floats"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    nfile, subcells, nfiles, L, dx = 256, 4, 4, 1000.0, 0.005
+    sc3, n3, nsub3 = subcells ** 3, nfile ** 3, (nfile // subcells) ** 3
+    assert nfiles * sc3 >= 256
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    aos = torch.rand((nfiles, n3, 3), generator=g, device=dev, dtype=torch.float32) * 3.0
+    j = torch.arange(nfile, device=dev, dtype=torch.float32) * (L / nfile)
+    grid = torch.stack(torch.meshgrid(j, j, j, indexing="ij")[::-1], dim=-1).reshape(n3, 3)
+    aos = torch.remainder(aos + grid[None], L).contiguous()
+    aos[aos >= L] = 0.0
+    px = mb.float_group_pixels(0.0, L, dx)
+    descs = [mb.FloatDesc.make(0.0, L, px) for _ in range(3)]
+    nb, stride = nfiles * 3 * sc3, 4 * nsub3 * sc3
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    ctx.encode_vec3_subcells_dev(descs, aos, nfile, subcells, nfiles, mins, bits, offs, out, stride, out_len)
+    dec = torch.empty_like(aos)
+    ctx.decode_vec3_subcells_dev(descs, out, stride, offs, mins, bits, nfile, subcells, nfiles, L, mb.Jitter.make(mb.JITTER_HASH, 7), dec)
+    ctx.sync()
+    assert ctx.last_path == 1
+    m, b, o, ln = (t.cpu().numpy() for t in (mins, bits, offs, out_len))
+    for f in range(nfiles):
+        host = aos[f].cpu().numpy()
+        om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(host, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3)
+        sl = slice(f * 3 * sc3, (f + 1) * 3 * sc3)
+        assert np.array_equal(m[sl], om) and np.array_equal(b[sl], ob)
+        for k in range(3):
+            want = b"".join(packed[t * ostride:t * ostride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
+            assert ln[3 * f + k] == len(want)
+            assert out[(3 * f + k) * stride:(3 * f + k) * stride + len(want)].cpu().numpy().tobytes() == want
+            assert np.array_equal(o[sl][k * sc3:(k + 1) * sc3], np.concatenate([[0], np.cumsum(onb[k * sc3:(k + 1) * sc3])[:-1]]))
+        if f == 0:
+            want = orc.bench_minp_decode(packed, ostride, nfile, subcells, [0.0] * 3, [L] * 3, [px] * 3, om, ob, True, L, 1, 7)
+            assert dec[0].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_vec3_decode_stream_jitter(ctx, orc):
+    rng = np.random.default_rng(33)
+    nfile, subcells, L = 32, 2, 50.0
+    n3, sc3, nsub3 = nfile ** 3, subcells ** 3, (nfile // subcells) ** 3
+    vec = np.mod(rng.random((n3, 3)) * L, L).astype(np.float32)
+    px = mb.float_group_pixels(0.0, L, 0.01)
+    descs = [mb.FloatDesc.make(0.0, L, px) for _ in range(3)]
+    mins, bits, offs, streams = ctx.encode_vec3_subcells(descs, vec, nfile, subcells)
+    u = rng.random(3 * n3)                                             # u[block * n + i], block = k * sc3 + sc
+    got = ctx.decode_vec3_subcells(descs, streams, offs, mins, bits, nfile, subcells, wrap_L=L,
+                                   jitter=mb.Jitter.make(mb.JITTER_STREAM, u_stream=u.ctypes.data))
+    want = np.zeros((n3, 3), np.float32)
+    sb = [None] * 3
+    for sc in range(sc3):
+        for k in range(3):
+            t = k * sc3 + sc
+            end = offs[t + 1] if (t + 1) % sc3 else len(streams[k])
+            sb[k] = orc.float_block_decode(streams[k][offs[t]:end], nsub3, int(mins[t]), int(bits[t]), 0.0, L, px, 1, 2, 0, 0,
+                                           u[t * nsub3:(t + 1) * nsub3])
+            sb[k] = np.where(sb[k] < 0, sb[k] + np.float32(L), np.where(sb[k] >= L, sb[k] - np.float32(L), sb[k])).astype(np.float32)
+        orc.lib().orc_set_sub_cell(want.ctypes.data, sb[0].ctypes.data, sb[1].ctypes.data, sb[2].ctypes.data, sc, subcells, nfile // subcells)
+    assert got.tobytes() == want.tobytes()
+
+
+# ---------------------------------------------------------------------------------------- host-pointer decode of selections
+@pytest.mark.parametrize("pick", ["sparse", "dense", "contiguous", "reversed"])
+def test_decode_block_selection_upload_strategies(ctx, orc, pick):
+    rng = np.random.default_rng(len(pick))
+    n, nb, L = 4096, 300, 125.0
+    px = mb.float_group_pixels(0.0, L, 0.001)
+    d = mb.FloatDesc.make(0.0, L, px)
+    x = (rng.random(n * nb) * rng.random(nb).repeat(n) * L).astype(np.float32)     # different widths per block
+    mins, bits, offs, data = ctx.encode_float_group(d, x, n, nb)
+    sel = {"sparse": rng.permutation(nb)[:9], "dense": rng.permutation(nb)[:200], "contiguous": np.arange(40, 90),
+           "reversed": np.arange(nb)[::-1]}[pick].astype(np.int64)
+    got = ctx.decode_float_blocks(d, data, offs, mins, bits, n, sel=sel, jitter=mb.Jitter.make(mb.JITTER_HASH, 8))
+    for j, b in enumerate(sel):
+        end = offs[b + 1] if b + 1 < nb else len(data)
+        want = orc.float_block_decode(data[offs[b]:end], n, int(mins[b]), int(bits[b]), 0.0, L, px, 1, 1, 8, int(b))
+        assert got[j].tobytes() == want.tobytes()
+    xi = rng.integers(0, 1 << 30, n * nb).astype(np.int64)
+    mi, bi, oi, di = ctx.encode_int_group(xi, n, nb)
+    assert np.array_equal(ctx.decode_int_blocks(di, oi, mi, bi, n, sel=sel), xi.reshape(nb, n)[sel])
+
+
+# ---------------------------------------------------------------------------------------- error reporting of `_dev` calls
+def test_dev_call_errors_surface_at_sync(ctx):
+    """a `_dev` encode whose packed output does not fit reports MNW_ERR_CAPACITY at the next mnw_sync (the device error
+    word is sticky until read), and the context is usable afterwards"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    n, nb = 4096 * 8, 4
+    x = torch.rand(n * nb, device=dev, dtype=torch.float32) * 125.0
+    d = mb.FloatDesc.make(0.0, 125.0, mb.float_group_pixels(0.0, 125.0, 0.001))
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(1, **i64)
+    out = torch.zeros(1000, dtype=torch.uint8, device=dev)
+    ctx.encode_float_group_dev(d, x, n, nb, mins, bits, offs, out, out.numel(), out_len)
+    other = torch.zeros(8 * 64, dtype=torch.uint8, device=dev)       # a second, harmless call before the sync
+    ctx.encode_int_group_dev(torch.arange(64, **i64), 64, 1, mins, bits, offs, other, other.numel(), out_len)
+    with pytest.raises(mb.MinnowError) as e:
+        ctx.sync()
+    assert e.value.code == -3
+    ctx.sync()                                                       # reported once
+    big = torch.zeros(4 * n * nb + 64, dtype=torch.uint8, device=dev)
+    ctx.encode_float_group_dev(d, x, n, nb, mins, bits, offs, big, big.numel(), out_len)
+    ctx.sync()
+    assert int(bits.max()) == 17
+
+
+# ---------------------------------------------------------------------------------------- minh Log columns, read side
+def test_minh_log_column_reads_back_through_device_pow(ctx, tmp_path):
+    from minnow_b200 import minh, minnow
+    rng = np.random.default_rng(12)
+    n = 5000
+    mass = np.power(10.0, rng.uniform(10.0, 15.0, n)).astype(np.float32)
+    raw = np.power(10.0, rng.uniform(-3.0, 3.0, n)).astype(np.float32)
+    cols = minh.columns([(minnow.FloatGroup, 1, 10.0, 15.0, 0.001), (minnow.Float32Group, 1, 0, 0, 0)])
+    path = str(tmp_path / "log.minh")
+    w = minh.Create(path, ctx)
+    w.Header(["mass", "rawlog"], "text", cols)
+    w.Geometry(100.0, 0.0, 1)
+    w.Block([mass, np.log10(raw.astype(np.float64)).astype(np.float32)])
+    w.Close()
+    r = minh.Open(path, ctx)
+    out = r.Floats(["mass", "rawlog"])
+    r.Close()
+    assert np.all(np.abs(np.log10(out["mass"].astype(np.float64)) - np.log10(mass.astype(np.float64))) <= 0.001 * 0.51 + 1e-6)
+    assert np.allclose(out["rawlog"], raw, rtol=3e-6)
+    assert np.array_equal(ctx.pow10_f32(np.array([0.0, 1.0, -1.0, 2.0], np.float32)), np.array([1.0, 10.0, 0.1, 100.0], np.float32))
