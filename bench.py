@@ -465,13 +465,41 @@ def verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, vdescs, pack
             "offsets": "running sums of ArrayBytes(bits, n) per stream" if ok else "see ok"}
 
 
+def pcie_ceiling(torch, dev, mib=512, reps=6):
+    """The duplex pinned-copy bandwidth of this GPU in this process, measured now (tools/pcie_probe.cu does the same
+    standalone): both directions at once on two streams, CUDA events.  The e2e step moves (nearly) the same number of
+    bytes each way, so its ceiling is what the slower direction sustains while the other one is busy too."""
+    n = mib << 20
+    ha, hb = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    da, db = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s0):
+        da.copy_(ha, non_blocking=True)
+    with torch.cuda.stream(s1):
+        hb.copy_(db, non_blocking=True)
+    torch.cuda.synchronize()
+    a0, b0, a1, b1 = ev(), ev(), ev(), ev()
+    with torch.cuda.stream(s0):
+        a0.record(s0)
+        for _ in range(reps):
+            da.copy_(ha, non_blocking=True)
+        b0.record(s0)
+    with torch.cuda.stream(s1):
+        a1.record(s1)
+        for _ in range(reps):
+            hb.copy_(db, non_blocking=True)
+        b1.record(s1)
+    torch.cuda.synchronize()
+    return {"duplex_h2d_gbs": n * reps / a0.elapsed_time(b0) / 1e6, "duplex_d2h_gbs": n * reps / a1.elapsed_time(b1) / 1e6,
+            "how": "%d x %d MiB pinned copies in each direction at once, CUDA events" % (reps, mib)}
+
+
 def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
-    """The same step through the host-pointer C ABI: every file's particles come from pinned host
-    memory (mnw_minp_encode_vectors: upload, limits, encode), packed bytes and metadata go back to
-    the host, are sent down again and decoded to host memory (mnw_decode_vec3_subcells).  A context
-    is single-threaded like a minnow.Writer, so the files are spread over a few worker threads with
-    one context each: the copies of one file overlap the kernels and the opposite-direction copies
-    of the others (the calls release the GIL)."""
+    """The same step through the host-pointer C ABI with ONE host thread: every file's particles come from pinned host
+    memory (mnw_pipe_minp_encode_vectors: upload, limits, parameters, encode, packed bytes and metadata back to the host),
+    are sent down again and decoded to host memory (mnw_pipe_minp_decode_vectors).  The pipe keeps several files in flight
+    on separate streams, so uploads, kernels and downloads of different files overlap; the thread only submits and waits."""
     import ctypes as C
     import psutil
     budget = 0.35 * psutil.virtual_memory().available / max(world, 1)
@@ -483,53 +511,55 @@ def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
     hvel.copy_(vel[:nfiles])
     stride = 4 * NP_FILE + 256
     nbk = 3 * SC3
-    nworkers = max(1, min(args.e2e_threads, nfiles))
-    P = lambda a: C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, LAG = 4, 2                                  # host buffer sets; encode -> decode distance in jobs
+    pipe = mb.Pipe(local_rank, depth=2 * K)
+    P = lambda a: C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
 
-    class Worker:
+    class Buf:
         def __init__(self):
-            self.ctx = mb.Context(local_rank)
             self.hout = torch.empty(3 * stride, dtype=torch.uint8).pin_memory()
             self.hdec = torch.empty((NP_FILE, 3), dtype=torch.float32).pin_memory()
             self.mins, self.bits, self.offs = (np.zeros(nbk, np.int64) for _ in range(3))
             self.lens = np.zeros(3, np.int64)
             self.d3 = (mb.FloatDesc * 3)()
-            self.jit = mb.Jitter.make(mb.JITTER_HASH, 7)
-            self.h2d = self.d2h = 0
+            self.ptrs = (C.c_void_p * 3)(*[self.hout.data_ptr() + k * stride for k in range(3)])
+            self.enc = self.dec = -1
+    bufs = [Buf() for _ in range(K)]
+    jit = mb.Jitter.make(mb.JITTER_HASH, 7)
+    jobs = [(field, f) for f in range(nfiles) for field in ("x", "v")]
+    counts = {"h2d": 0, "d2h": 0}
 
-        def one(self, field, f, count):
-            c, lib = self.ctx, self.ctx.lib
-            src = hpos[f] if field == "x" else hvel[f]
-            periodic = field == "x"
-            c._check(lib.mnw_minp_encode_vectors(c.h, P(src), NFILE, SUB_CELLS, int(periodic), L_BOX if periodic else 0.0,
-                                                 DX_POS if periodic else DV, self.d3, P(self.mins), P(self.bits),
-                                                 P(self.offs), P(self.hout), stride, P(self.lens)))
-            ptrs = (C.c_void_p * 3)(*[self.hout.data_ptr() + k * stride for k in range(3)])
-            c._check(lib.mnw_decode_vec3_subcells(c.h, self.d3, ptrs, P(self.lens), P(self.offs), P(self.mins), P(self.bits),
-                                                  NFILE, SUB_CELLS, L_BOX if periodic else 0.0, C.byref(self.jit), P(self.hdec)))
-            if count:
-                pk = int(self.lens.sum())
-                self.h2d += 12 * NP_FILE + pk + 3 * 8 * nbk
-                self.d2h += pk + 3 * 8 * nbk + 12 * NP_FILE
-
-        def run(self, files, count):
-            for f in files:
-                self.one("x", f, count)
-                self.one("v", f, count)
-
-    workers = [Worker() for _ in range(nworkers)]
-    for w in workers:                              # warm-up (buffers grow once)
-        w.run([0], False)
+    def one_pass(count):
+        nj = len(jobs)
+        for i in range(nj + LAG):
+            if i < nj:
+                b = bufs[i % K]
+                if b.dec >= 0:
+                    pipe.wait(b.dec)               # the decode that last used this buffer set
+                field, f = jobs[i]
+                per = field == "x"
+                b.enc = pipe.encode(hpos[f] if per else hvel[f], NFILE, SUB_CELLS, per, L_BOX if per else 0.0, DX_POS if per else DV,
+                                    b.d3, b.mins, b.bits, b.offs, b.hout, stride, b.lens)
+            j = i - LAG
+            if j >= 0:
+                b = bufs[j % K]
+                pipe.wait(b.enc)
+                per = jobs[j][0] == "x"
+                b.dec = pipe.decode(b.d3, b.ptrs, b.lens, b.offs, b.mins, b.bits, NFILE, SUB_CELLS, L_BOX if per else 0.0, jit, b.hdec)
+                if count:
+                    pk = int(b.lens.sum())
+                    counts["h2d"] += 12 * NP_FILE + pk + 3 * 8 * nbk
+                    counts["d2h"] += pk + (3 * 8 * nbk + 24 + 72 + 8) + 12 * NP_FILE
+        pipe.drain()
+        for b in bufs:
+            b.dec = -1
+    one_pass(False)                                # warm-up (buffers grow once)
     torch.cuda.synchronize()
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
-        ths = [threading.Thread(target=w.run, args=(range(i, nfiles, nworkers), True)) for i, w in enumerate(workers)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
+        one_pass(True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -537,16 +567,28 @@ def run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    # what the last pass left in the last buffer set, against the device-resident arm's result for the same file
+    pipe.close()
     nbytes = steps * nfiles * 4 * 12 * NP_FILE
     scale = NFILES / nfiles                       # bytes per full step, as counted from the copies made
-    h2d, d2h = sum(w.h2d for w in workers), sum(w.d2h for w in workers)
-    for w in workers:
-        w.ctx.close()
-    return {"value": world * nbytes / dt / 1e9, "unit": "GB/s",
-            "h2d_bytes_per_step": int(h2d / steps * scale), "d2h_bytes_per_step": int(d2h / steps * scale),
-            "files_timed_per_step": nfiles, "steps": steps, "host_threads": nworkers,
-            "api": "mnw_minp_encode_vectors + mnw_decode_vec3_subcells, one file per call, pinned host buffers, "
-                   "%d host threads with one context each" % nworkers}
+    h2d, d2h = counts["h2d"] / steps * scale, counts["d2h"] / steps * scale
+    del hpos, hvel, bufs
+    ceil = pcie_ceiling(torch, dev)
+    if world > 1:                                 # every rank probes at the same time: the NODE's ceiling
+        import torch.distributed as dist
+        c = torch.tensor([ceil["duplex_h2d_gbs"], ceil["duplex_d2h_gbs"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.MIN)
+        ceil["duplex_h2d_gbs"], ceil["duplex_d2h_gbs"] = float(c[0]), float(c[1])
+        ceil["how"] += "; all ranks at once, minimum over ranks"
+    t_min = max(h2d / (ceil["duplex_h2d_gbs"] * 1e9), d2h / (ceil["duplex_d2h_gbs"] * 1e9))
+    value = world * nbytes / dt / 1e9
+    ceiling = world * 4 * 12 * NSIDE ** 3 / t_min / 1e9
+    return {"value": value, "unit": "GB/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "files_timed_per_step": nfiles, "steps": steps, "host_threads": 1,
+            "pcie": ceil, "ceiling_gbs": ceiling, "frac_of_ceiling": value / ceiling,
+            "api": "mnw_pipe_minp_encode_vectors + mnw_pipe_minp_decode_vectors, one file per call, pinned host buffers, ONE host "
+                   "thread; %d host buffer sets, pipe depth %d" % (K, 2 * K)}
 
 
 def main():
@@ -558,7 +600,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 configurations (profiling runs)")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -279,6 +279,30 @@ MNW_API int mnw_vec3_limits_dev(mnw_ctx *ctx, const float *aos, int64_t np, int6
 MNW_API int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64_t base,
                                  int64_t *offsets, int64_t *total);
 
+/* ---- pipelined host <-> device streaming (the staging either side of the kernels) ----------------------------------
+ * Replaces the one-block-at-a-time file cursor of go/writer.go:90-141 / go/reader.go:114-127 / go/bit/bit.go:161-181 on
+ * the host side of the boundary.  A pipe is a ring of `depth` slots (a private stream and device staging each).
+ * Submitting a file ENQUEUES its upload, kernels and download and returns a ticket at once; with one host thread the
+ * upload of file i+1, the kernels of file i and the download of file i-1 overlap.  The caller's buffers (pinned for
+ * full speed, any host memory for correctness) must stay valid until mnw_pipe_wait(ticket) returns; results and errors
+ * of a ticket are delivered by that wait.  Submitting blocks only when all `depth` slots are in flight.
+ * Arguments as in mnw_minp_encode_vectors / mnw_decode_vec3_subcells.  Not thread-safe, like a context. */
+typedef struct mnw_pipe mnw_pipe;
+MNW_API int mnw_pipe_create(int device, int depth, mnw_pipe **out);
+MNW_API void mnw_pipe_destroy(mnw_pipe *pipe);
+MNW_API const char *mnw_pipe_last_error(const mnw_pipe *pipe);
+MNW_API int mnw_pipe_minp_encode_vectors(mnw_pipe *pipe, const float *aos, int64_t nfile, int64_t subcells, int periodic,
+                                         float L, float dx, mnw_float_desc desc_out[3], int64_t *mins, int64_t *bits,
+                                         int64_t *offsets, uint8_t *out, int64_t out_axis_stride, int64_t out_len[3],
+                                         int64_t *ticket);
+MNW_API int mnw_pipe_minp_decode_vectors(mnw_pipe *pipe, const mnw_float_desc desc[3], const uint8_t *const data[3],
+                                         const int64_t data_len[3], const int64_t *offsets, const int64_t *mins,
+                                         const int64_t *bits, int64_t nfile, int64_t subcells, float wrap_L,
+                                         const mnw_jitter *jitter, float *aos_out, int64_t *ticket);
+MNW_API int mnw_pipe_poll(mnw_pipe *pipe);                  /* advance what can be advanced, never blocks */
+MNW_API int mnw_pipe_wait(mnw_pipe *pipe, int64_t ticket);  /* that ticket is complete; returns its status */
+MNW_API int mnw_pipe_drain(mnw_pipe *pipe);                 /* everything submitted is complete */
+
 /* Per-kernel timing with CUDA events on the context's stream.  mnw_profile(ctx, 1)
  * starts recording the library's bandwidth-carrying kernels, mnw_profile(ctx, 0)
  * stops; mnw_profile_summary synchronises and writes a JSON array

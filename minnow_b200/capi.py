@@ -89,6 +89,14 @@ SIGNATURES = {
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
     "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
+    "mnw_pipe_create": (_int, [_int, _int, C.POINTER(_p)]),
+    "mnw_pipe_destroy": (None, [_p]),
+    "mnw_pipe_last_error": (C.c_char_p, [_p]),
+    "mnw_pipe_minp_encode_vectors": (_int, [_p, _p, _i64, _i64, _int, _f32, _f32, _FD, _p, _p, _p, _p, _i64, _p, C.POINTER(_i64)]),
+    "mnw_pipe_minp_decode_vectors": (_int, [_p, _FD, _p, _p, _p, _p, _p, _i64, _i64, _f32, _JT, _p, C.POINTER(_i64)]),
+    "mnw_pipe_poll": (_int, [_p]),
+    "mnw_pipe_wait": (_int, [_p, _i64]),
+    "mnw_pipe_drain": (_int, [_p]),
     "mnw_vec3_limits": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mnw_vec3_limits_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mnw_scan_offsets_dev": (_int, [_p, _p, _i64, _i64, _p, _p]),
@@ -152,6 +160,54 @@ def _ptr(a):
     if hasattr(a, "data_ptr"):      # torch tensor (device or pinned host)
         return _p(a.data_ptr())
     return _p(int(a))
+
+
+class Pipe:
+    """mnw_pipe: a ring of `depth` slots through which one host thread streams minp files (upload, kernels and download
+    of different files overlap).  encode / decode return a ticket; the caller's arrays must stay alive and untouched
+    until wait(ticket)."""
+
+    def __init__(self, device=0, depth=4):
+        self.lib = load_library()
+        h = _p()
+        rc = self.lib.mnw_pipe_create(device, depth, C.byref(h))
+        if rc:
+            raise MinnowError(rc, self.lib.mnw_last_error(None).decode())
+        self.h, self.depth = h, depth
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mnw_pipe_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise MinnowError(rc, self.lib.mnw_pipe_last_error(self.h).decode())
+
+    def encode(self, aos, nfile, subcells, periodic, L, dx, desc_out, mins, bits, offsets, out, out_axis_stride, out_len):
+        t = _i64(-1)
+        self._check(self.lib.mnw_pipe_minp_encode_vectors(self.h, _ptr(aos), nfile, subcells, int(bool(periodic)), float(L), float(dx),
+                                                          desc_out, _ptr(mins), _ptr(bits), _ptr(offsets), _ptr(out), out_axis_stride,
+                                                          _ptr(out_len), C.byref(t)))
+        return t.value
+
+    def decode(self, desc3, data_ptrs3, data_len, offsets, mins, bits, nfile, subcells, wrap_L, jitter, aos_out):
+        t = _i64(-1)
+        self._check(self.lib.mnw_pipe_minp_decode_vectors(self.h, desc3, data_ptrs3, _ptr(data_len), _ptr(offsets), _ptr(mins),
+                                                          _ptr(bits), nfile, subcells, float(wrap_L), C.byref(jitter), _ptr(aos_out),
+                                                          C.byref(t)))
+        return t.value
+
+    def poll(self):
+        self._check(self.lib.mnw_pipe_poll(self.h))
+
+    def wait(self, ticket):
+        self._check(self.lib.mnw_pipe_wait(self.h, ticket))
+
+    def drain(self):
+        self._check(self.lib.mnw_pipe_drain(self.h))
 
 
 class Context:

@@ -9,57 +9,17 @@
 #include <string>
 #include <vector>
 
-#include "../../include/minnow_cuda.h"
+#include "ctx.cuh"
 #include "device_math.cuh"
-#include "engine.cuh"
-#include "launch.cuh"
 #include "fused.cuh"
 
 using namespace mnw;
 
 namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {  // retry with the exact size
-            (void)cudaGetLastError();
-            want = n;
-            e = cudaMalloc(&p, want);
-        }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return (T *)p; }
-};
-
 std::string g_create_error;
-
 }  // namespace
 
-struct mnw_ctx {
-    int device = 0;
-    Launcher L;
-    std::string err;
-    int last_path = 0;
-    int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws, group_ws;
-    int *h_flags = nullptr;  // pinned: [slow_count, err]
-    void *h_stage = nullptr; // pinned staging for gathered uploads (grow-only)
-    size_t h_stage_cap = 0;
-    bool flags_init = false; // the device flag words have been zeroed once (the error word is sticky afterwards)
-};
-
-namespace {
-
-int fail(mnw_ctx *c, int code, const char *fmt, ...) {
+int mnw_fail(mnw_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -68,13 +28,15 @@ int fail(mnw_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf; else g_create_error = buf;
     return code;
 }
+#define fail mnw_fail
 
-#define CU(call)                                                                       \
-    do {                                                                               \
-        cudaError_t e__ = (call);                                                      \
-        if (e__ != cudaSuccess)                                                        \
-            return fail(ctx, MNW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));   \
-    } while (0)
+int mnw_report_device_error(mnw_ctx *ctx, int err) {
+    if (err == 1) return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
+    if (err == 2) return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
+    return MNW_OK;
+}
+
+namespace {
 
 int check_desc(mnw_ctx *ctx, const mnw_float_desc *d) {
     if (!d) return fail(ctx, MNW_ERR_ARG, "float group descriptor is NULL");
@@ -145,11 +107,7 @@ int check_flags(mnw_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->L.stream));
     const int err = ctx->h_flags[0];
     if (err) CU(cudaMemsetAsync(ctx->flags.as<int>() + FLAG_ERR, 0, sizeof(int), ctx->L.stream));
-    if (err == 1)
-        return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
-    if (err == 2)
-        return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
-    return MNW_OK;
+    return mnw_report_device_error(ctx, err);
 }
 
 // Device-resident group encode.  x/out/mins/bits/offsets/out_len are device

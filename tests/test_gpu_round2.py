@@ -360,3 +360,67 @@ def test_minh_log_column_reads_back_through_device_pow(ctx, tmp_path):
     assert np.all(np.abs(np.log10(out["mass"].astype(np.float64)) - np.log10(mass.astype(np.float64))) <= 0.001 * 0.51 + 1e-6)
     assert np.allclose(out["rawlog"], raw, rtol=3e-6)
     assert np.array_equal(ctx.pow10_f32(np.array([0.0, 1.0, -1.0, 2.0], np.float32)), np.array([1.0, 10.0, 0.1, 100.0], np.float32))
+
+
+# ---------------------------------------------------------------------------------------- mnw_pipe
+@pytest.mark.parametrize("periodic", [True, False])
+def test_pipe_streams_files_like_the_synchronous_calls(ctx, periodic):
+    """mnw_pipe with more files than slots, pageable host buffers: every ticket delivers exactly what
+    mnw_minp_encode_vectors / mnw_decode_vec3_subcells return for the same file"""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    nfile, subcells, L, dx, nfiles = 64, 2, 200.0, 0.01, 7
+    n3, nb = nfile ** 3, 3 * subcells ** 3
+    if periodic:
+        files = [np.mod(rng.random((n3, 3)) * L, L).astype(np.float32) for _ in range(nfiles)]
+    else:
+        files = [(100.0 * (f + 1) * rng.standard_normal((n3, 3))).astype(np.float32) for f in range(nfiles)]
+    pipe = mb.Pipe(0, depth=3)
+    stride = 8 * n3 + 64
+    res = []
+    for f in range(nfiles):
+        r = dict(d3=(mb.FloatDesc * 3)(), mins=np.zeros(nb, np.int64), bits=np.zeros(nb, np.int64), offs=np.zeros(nb, np.int64),
+                 out=np.zeros(3 * stride, np.uint8), lens=np.zeros(3, np.int64), dec=np.zeros((n3, 3), np.float32))
+        r["t"] = pipe.encode(files[f], nfile, subcells, periodic, L if periodic else 0.0, dx if periodic else 1.0, r["d3"], r["mins"],
+                             r["bits"], r["offs"], r["out"], stride, r["lens"])
+        res.append(r)
+    jit = mb.Jitter.make(mb.JITTER_HASH, 3)
+    for f in range(nfiles):
+        r = res[f]
+        pipe.wait(r["t"])
+        r["ptrs"] = (C.c_void_p * 3)(*[r["out"].ctypes.data + k * stride for k in range(3)])
+        r["t2"] = pipe.decode(r["d3"], r["ptrs"], r["lens"], r["offs"], r["mins"], r["bits"], nfile, subcells, L if periodic else 0.0, jit, r["dec"])
+    pipe.drain()
+    for f in range(nfiles):
+        r = res[f]
+        descs, mins, bits, offs, streams = ctx.minp_encode_vectors(files[f], nfile, subcells, periodic, L if periodic else 0.0,
+                                                                  dx if periodic else 1.0)
+        assert np.array_equal(mins, r["mins"]) and np.array_equal(bits, r["bits"]) and np.array_equal(offs, r["offs"])
+        for k in range(3):
+            assert (descs[k].low, descs[k].high, descs[k].pixels) == (r["d3"][k].low, r["d3"][k].high, r["d3"][k].pixels)
+            assert r["lens"][k] == len(streams[k])
+            assert r["out"][k * stride:k * stride + len(streams[k])].tobytes() == streams[k].tobytes()
+        want = ctx.decode_vec3_subcells(descs, streams, offs, mins, bits, nfile, subcells, wrap_L=L if periodic else 0.0, jitter=jit)
+        assert r["dec"].tobytes() == want.tobytes()
+    pipe.close()
+
+
+def test_pipe_reports_capacity_error_on_wait():
+    rng = np.random.default_rng(78)
+    nfile, subcells, L = 64, 2, 200.0
+    n3, nb = nfile ** 3, 3 * subcells ** 3
+    vec = np.mod(rng.random((n3, 3)) * L, L).astype(np.float32)
+    pipe = mb.Pipe(0, depth=2)
+    d3, lens = (mb.FloatDesc * 3)(), np.zeros(3, np.int64)
+    mins, bits, offs = (np.zeros(nb, np.int64) for _ in range(3))
+    out = np.zeros(3 * 1000, np.uint8)
+    t = pipe.encode(vec, nfile, subcells, True, L, 0.01, d3, mins, bits, offs, out, 1000, lens)
+    with pytest.raises(mb.MinnowError) as e:
+        pipe.wait(t)
+    assert e.value.code == -3
+    big = np.zeros(3 * (8 * n3 + 64), np.uint8)
+    t = pipe.encode(vec, nfile, subcells, True, L, 0.01, d3, mins, bits, offs, big, 8 * n3 + 64, lens)
+    pipe.wait(t)
+    pipe.drain()
+    assert lens.min() > 0
+    pipe.close()
