@@ -210,6 +210,12 @@ def run_gpu(args):
 
     ctx = mb.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    if world > 1:   # the library's own communicator (mnw_comm_init): the id travels over the launcher's process group
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(mb.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
 
     # ---- synthetic snapshot, resident in HBM -------------------------------------------
     pos = torch.empty((NFILES, NP_FILE, 3), dtype=torch.float32, device=dev)
@@ -241,31 +247,39 @@ def run_gpu(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = []
 
+    desc_dev = {k: torch.zeros(24 * 3 * NFILES, dtype=torch.uint8, device=dev) for k in ("x", "v")}   # mnw_float_desc [3 * NFILES]
+    all_sizes = torch.zeros(world * 2 * nb, **i64)
+    all_offs = torch.zeros(world * 2 * nb, **i64)
+    all_total = torch.zeros(1, **i64)
+
     def step(record=False):
+        """One step, enqueued without a host round trip: limits, pixel counts and group constants of the velocity field
+        are derived on the device (mnw_minp_encode_vectors_dev)."""
         with torch.cuda.stream(stream):
             e = [ev() for _ in range(5)] if record else None
             if record: e[0].record(stream)
-            # bounds() of the velocity field (go/minp/minp.go:92-95) first: the call synchronises, and the host then
-            # builds the 192 group descriptors while the x encode runs
-            lo, hi = ctx.vec3_limits(vel, NFILES, dev=True)
-            ctx.encode_vec3_subcells_dev(pdescs, pos, NFILE, SUB_CELLS, NFILES, *meta["x"], packed["x"], stride, out_len["x"])
+            ctx.minp_encode_vectors_dev(pos, NFILE, SUB_CELLS, NFILES, True, L_BOX, DX_POS, desc_dev["x"], *meta["x"], packed["x"], stride,
+                                        out_len["x"])
             if record: e[1].record(stream)
-            vd = vel_descs(lo, hi)
-            state["vd"] = vd
-            ctx.encode_vec3_subcells_dev(vd, vel, NFILE, SUB_CELLS, NFILES, *meta["v"], packed["v"], stride, out_len["v"])
+            ctx.minp_encode_vectors_dev(vel, NFILE, SUB_CELLS, NFILES, False, 0.0, DV, desc_dev["v"], *meta["v"], packed["v"], stride,
+                                        out_len["v"])
             if record: e[2].record(stream)
             if world > 1:
-                # the one exchange of the sharded path: all-gather per-block packed sizes, then every
-                # rank scans them to the global byte offsets
+                # the one exchange of the sharded path, through the C ABI: NCCL all-gather of the per-block packed sizes,
+                # then the same scan on every rank -> global byte offsets of the whole snapshot (SURVEY 8e)
                 local = torch.cat([shard.packed_sizes(meta[k][1], NSUB3) for k in ("x", "v")])
-                state["global"] = shard.global_offsets(local, world * 2 * nb, SC3, ctx=ctx)
-            ctx.decode_vec3_subcells_dev(pdescs, packed["x"], stride, meta["x"][2], meta["x"][0], meta["x"][1],
-                                         NFILE, SUB_CELLS, NFILES, L_BOX, jit, decoded)
+                ctx.sharded_offsets_dev(local, 2 * nb, all_sizes, all_offs, all_total)
+            ctx.minp_decode_vectors_dev(desc_dev["x"], packed["x"], stride, meta["x"][2], meta["x"][0], meta["x"][1],
+                                        NFILE, SUB_CELLS, NFILES, True, L_BOX, jit, decoded)
             if record: e[3].record(stream)
-            ctx.decode_vec3_subcells_dev(vd, packed["v"], stride, meta["v"][2], meta["v"][0], meta["v"][1],
-                                         NFILE, SUB_CELLS, NFILES, 0.0, jit, decoded)
+            ctx.minp_decode_vectors_dev(desc_dev["v"], packed["v"], stride, meta["v"][2], meta["v"][0], meta["v"][1],
+                                        NFILE, SUB_CELLS, NFILES, False, 0.0, jit, decoded)
             if record: e[4].record(stream)
             if record: marks.append(e)
+
+    def host_descs(key):
+        a = np.frombuffer(desc_dev[key].cpu().numpy().tobytes(), np.dtype([("low", "<f4"), ("high", "<f4"), ("pixels", "<i8"), ("fl", "u1", 8)]))
+        return [mb.FloatDesc.make(float(r["low"]), float(r["high"]), int(r["pixels"])) for r in a]
 
     def barrier():
         if world > 1:
@@ -353,10 +367,21 @@ def run_gpu(args):
     verified = None
     if rank == 0:
         try:
-            verified = verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, state["vd"], packed, meta, out_len,
+            verified = verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, host_descs("v"), packed, meta, out_len,
                                         decoded, stride)
         except Exception as exc:   # a failed check is reported, it never costs the run its number
             verified = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+
+    # ---- C5: the ranks' files as ONE sharded snapshot (not timed): the global offsets are consumed ---------------------
+    c5 = None
+    if world > 1:
+        try:
+            c5 = c5_check(torch, dist, mb, ctx, stream, dev, rank, world, nb, stride, meta, out_len, packed, host_descs("x"),
+                          all_sizes, all_offs, all_total)
+        except Exception as exc:
+            c5 = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+        if verified is not None:
+            verified["c5_sharded_snapshot"] = c5
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers, copies timed) ------
     e2e = None if args.no_e2e else run_e2e(torch, mb, ctx, pos, vel, pdescs, world, args, dev)
@@ -405,6 +430,76 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+def c5_check(torch, dist, mb, ctx, stream, dev, rank, world, nb, stride, meta, out_len, packed, xdescs, all_sizes, all_offs, all_total):
+    """The snapshot-level block index of the sharded path, consumed (go/block_index.go:16-35, go/writer.go:84-86):
+    1. the global offsets every rank derived (mnw_sharded_offsets_dev: NCCL all-gather + scan) equal ONE scan of the
+       gathered sizes, and the gathered sizes equal what torch.distributed gathers;
+    2. every rank writes the packed x bytes of its file 0 into one shared snapshot file at groupOffset + base_r
+       (base_r = offset of its first block in the global index), each (file, axis) group at its global offset;
+    3. every rank reads the NEXT rank's file 0 back from those offsets, assembles a minp file around the bytes with the
+       host mirror (minp.Writer.EncodedVectors) and decodes it with minp.Reader: the particles are that rank's."""
+    import io
+    from minnow_b200 import minp, shard
+    ctx.sync()
+    sizes, offs = all_sizes.clone(), all_offs.clone()
+    local = torch.cat([shard.packed_sizes(meta[k][1], NSUB3) for k in ("x", "v")])
+    ref = torch.empty(world * 2 * nb, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(ref, local.contiguous())
+    ok_gather = bool(torch.equal(ref, sizes))
+    inc = torch.cumsum(sizes, 0)
+    ok_scan = bool(torch.equal(offs, inc - sizes)) and int(all_total.item()) == int(inc[-1].item())
+    # the metadata of file 0 (x) of every rank: 3 * SC3 (min, bits) pairs -- gathered with the library's collective too
+    m0 = torch.stack([meta["x"][0][:3 * SC3], meta["x"][1][:3 * SC3]]).reshape(-1).contiguous()
+    mall = torch.empty(world * m0.numel(), dtype=torch.int64, device=dev)
+    with torch.cuda.stream(stream):
+        ctx.allgather_sizes(m0, m0.numel(), mall)
+    ctx.sync()
+    path = "/dev/shm/minnow_b200_c5_snapshot.bin"
+    base_r = int(offs[rank * 2 * nb].item())
+    fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o600)
+    for k in range(3):                      # file 0, field x: block (k, sc) is global block rank * 2nb + k * SC3 + sc
+        g0 = rank * 2 * nb + k * SC3
+        ln = int(out_len["x"][k].item())
+        assert ln == int(sizes[g0:g0 + SC3].sum().item())
+        os.pwrite(fd, packed["x"][k * stride:k * stride + ln].cpu().numpy().tobytes(), int(offs[g0].item()))
+    os.fsync(fd)
+    dist.barrier()
+    nbr = (rank + 1) % world
+    mn = mall.view(world, 2, 3 * SC3)[nbr]
+    streams = []
+    for k in range(3):
+        g0 = nbr * 2 * nb + k * SC3
+        streams.append(os.pread(fd, int(sizes[g0:g0 + SC3].sum().item()), int(offs[g0].item())))
+    os.close(fd)
+    hd = np.zeros(1, minp.Header)
+    hd["NSide"], hd["L"] = NSIDE, L_BOX
+    cell = np.zeros(1, minp.Cell)
+    cell["FileCells"], cell["SubCells"] = FILE_CELLS, SUB_CELLS
+    buf = io.BytesIO()
+    w = minp.Create(buf, ctx)
+    w.Header(hd, b"", cell, DX_POS, True)
+    w.EncodedVectors(xdescs[:3], mn[0].cpu().numpy(), mn[1].cpu().numpy(), streams)
+    w.Close()
+    got = torch.from_numpy(minp.Open(buf.getvalue(), ctx).Vectors()).to(dev)           # CENTER jitter
+    want, _ = gen_file(torch, 0, 2 + nbr, dev)
+    d = (got - want).abs_()
+    d = torch.minimum(d, (L_BOX - d).abs_())
+    err_px = float(d.max().item()) / DX_POS
+    dist.barrier()
+    if rank == 0:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    res = torch.tensor([int(ok_gather), int(ok_scan), int(err_px <= 0.53)], dtype=torch.int64, device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    return {"ok": bool(res.min().item() == 1), "sizes_equal_torch_all_gather": bool(res[0].item()), "offsets_equal_single_scan": bool(res[1].item()),
+            "neighbour_file_read_back_through_minp_Reader": bool(res[2].item()), "max_error_pixels_rank0": err_px, "base_rank0": base_r,
+            "blocks_in_index": int(world * 2 * nb), "snapshot_bytes": int(all_total.item()),
+            "scope": "global index over all ranks' x and v blocks; file 0 (x) of every rank written at its global offsets into one "
+                     "tmpfs file and read back by the next rank"}
 
 
 def verify_roundtrip(torch, mb, ctx, stream, dev, pos, vel, pdescs, vdescs, packed, meta, out_len, decoded, stride):

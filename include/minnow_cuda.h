@@ -303,6 +303,28 @@ MNW_API int mnw_pipe_poll(mnw_pipe *pipe);                  /* advance what can 
 MNW_API int mnw_pipe_wait(mnw_pipe *pipe, int64_t ticket);  /* that ticket is complete; returns its status */
 MNW_API int mnw_pipe_drain(mnw_pipe *pipe);                 /* everything submitted is complete */
 
+/* ---- multi-GPU: one process (or thread) and one context per GPU --------------------------------------------------------
+ * Blocks are independent given the group parameters, so a file's blocks are split into contiguous ranges over the ranks;
+ * every rank packs with rank-LOCAL offsets.  The only exchange is an NCCL all-gather of the per-block packed sizes
+ * (NVLink / NVSwitch); the same scan on every rank then yields the file's global block offsets (blockIndex,
+ * go/block_index.go:16-35) and base_r = offsets[first block of rank r], where the rank's bytes go (pwrite at
+ * groupOffset + base_r).  Payload never crosses the interconnect.
+ *   mnw_comm_unique_id   rank 0 creates the NCCL id (128 bytes) and hands it to the other ranks by its own means
+ *   mnw_comm_init        every rank: joins the communicator on its context's device (collective)
+ *   mnw_allgather_sizes  local_dev [count] int64 -> all_dev [count * nranks], DEVICE pointers, on the context's stream
+ *   mnw_sharded_offsets_dev  the all-gather + the exclusive scan in one call: all_nbytes_dev / all_offsets_dev
+ *                        [count * nranks], total_dev [1]
+ * NCCL is loaded at run time (libnccl.so.2, or MNW_NCCL_LIB); a context without a communicator is a world of one. */
+typedef struct { char bytes[128]; } mnw_comm_id;
+MNW_API int mnw_comm_unique_id(mnw_comm_id *out);
+MNW_API int mnw_comm_init(mnw_ctx *ctx, const mnw_comm_id *id, int nranks, int rank);
+MNW_API int mnw_comm_destroy(mnw_ctx *ctx);
+MNW_API int mnw_comm_size(const mnw_ctx *ctx);
+MNW_API int mnw_comm_rank(const mnw_ctx *ctx);
+MNW_API int mnw_allgather_sizes(mnw_ctx *ctx, const int64_t *local_dev, int64_t count, int64_t *all_dev);
+MNW_API int mnw_sharded_offsets_dev(mnw_ctx *ctx, const int64_t *local_nbytes_dev, int64_t count, int64_t *all_nbytes_dev,
+                                    int64_t *all_offsets_dev, int64_t *total_dev);
+
 /* Per-kernel timing with CUDA events on the context's stream.  mnw_profile(ctx, 1)
  * starts recording the library's bandwidth-carrying kernels, mnw_profile(ctx, 0)
  * stops; mnw_profile_summary synchronises and writes a JSON array

@@ -89,6 +89,13 @@ SIGNATURES = {
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
     "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
+    "mnw_comm_unique_id": (_int, [_p]),
+    "mnw_comm_init": (_int, [_p, _p, _int, _int]),
+    "mnw_comm_destroy": (_int, [_p]),
+    "mnw_comm_size": (_int, [_p]),
+    "mnw_comm_rank": (_int, [_p]),
+    "mnw_allgather_sizes": (_int, [_p, _p, _i64, _p]),
+    "mnw_sharded_offsets_dev": (_int, [_p, _p, _i64, _p, _p, _p]),
     "mnw_pipe_create": (_int, [_int, _int, C.POINTER(_p)]),
     "mnw_pipe_destroy": (None, [_p]),
     "mnw_pipe_last_error": (C.c_char_p, [_p]),
@@ -257,6 +264,33 @@ class Context:
         buf = C.create_string_buffer(1 << 16)
         self._check(self.lib.mnw_profile_summary(self.h, buf, len(buf)))
         return json.loads(buf.value.decode())
+
+    # ---- multi-GPU (one context per GPU and rank) ---------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the 128-byte NCCL id to hand to the other ranks"""
+        buf = C.create_string_buffer(128)
+        lib = load_library()
+        rc = lib.mnw_comm_unique_id(buf)
+        if rc:
+            raise MinnowError(rc, lib.mnw_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, uid, nranks, rank):
+        self._check(self.lib.mnw_comm_init(self.h, C.create_string_buffer(bytes(uid), 128), nranks, rank))
+
+    def comm_destroy(self):
+        self._check(self.lib.mnw_comm_destroy(self.h))
+
+    @property
+    def comm_size(self):
+        return int(self.lib.mnw_comm_size(self.h))
+
+    def allgather_sizes(self, local, count, out):
+        self._check(self.lib.mnw_allgather_sizes(self.h, _ptr(local), count, _ptr(out)))
+
+    def sharded_offsets_dev(self, local_nbytes, count, all_nbytes, all_offsets, total):
+        self._check(self.lib.mnw_sharded_offsets_dev(self.h, _ptr(local_nbytes), count, _ptr(all_nbytes), _ptr(all_offsets), _ptr(total)))
 
     def scan_offsets_dev(self, nbytes, nblocks, base, offsets, total):
         self._check(self.lib.mnw_scan_offsets_dev(self.h, _ptr(nbytes), nblocks, base, _ptr(offsets), _ptr(total)))

@@ -476,6 +476,7 @@ int mnw_create(int device, mnw_ctx **out) {
 void mnw_destroy(mnw_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    mnw_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
                       &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws})
@@ -681,7 +682,8 @@ int mnw_scan_offsets(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, int64
     CU(ctx->meta.reserve(8 * (size_t)(2 * nblocks + 2)));
     int64_t *d_sizes = ctx->meta.as<int64_t>(), *d_off = d_sizes + nblocks, *d_total = d_off + nblocks;
     if (nblocks) CU(cudaMemcpyAsync(d_sizes, nbytes, 8 * (size_t)nblocks, cudaMemcpyHostToDevice, ctx->L.stream));
-    e = launch_scan_sizes(ctx->L, d_sizes, nblocks, base, d_off, d_total);
+    CU(ctx->aux.reserve(scan_scratch_bytes(nblocks)));
+    e = launch_scan_sizes(ctx->L, d_sizes, nblocks, base, d_off, d_total, ctx->aux.p);
     if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
     if (nblocks) CU(cudaMemcpyAsync(offsets, d_off, 8 * (size_t)nblocks, cudaMemcpyDeviceToHost, ctx->L.stream));
     int64_t t = 0;
@@ -1057,7 +1059,8 @@ int mnw_scan_offsets_dev(mnw_ctx *ctx, const int64_t *nbytes, int64_t nblocks, i
                          int64_t *total) {
     if (ctx) (void)cudaSetDevice(ctx->device);   /* a context may be used from any host thread */
     if (nblocks < 0) return fail(ctx, MNW_ERR_ARG, "negative block count");
-    cudaError_t e = launch_scan_sizes(ctx->L, nbytes, nblocks, base, offsets, total);
+    CU(ctx->aux.reserve(scan_scratch_bytes(nblocks)));
+    cudaError_t e = launch_scan_sizes(ctx->L, nbytes, nblocks, base, offsets, total, ctx->aux.p);
     if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
     return MNW_OK;
 }

@@ -40,6 +40,8 @@ struct mnw_ctx {
     void *h_stage = nullptr; // pinned staging for gathered uploads (grow-only)
     size_t h_stage_cap = 0;
     bool flags_init = false; // the device flag words have been zeroed once (the error word is sticky afterwards)
+    void *comm = nullptr;    // ncclComm_t of the sharded path (comm_api.cu); null = a world of one
+    int comm_ranks = 0, comm_rank = 0;
 };
 
 // sets the context's (or, for c == NULL, the creation) error message; returns code

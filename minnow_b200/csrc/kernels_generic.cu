@@ -1060,8 +1060,57 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_i64c(DecodeArgs A) {
     }
 }
 
+// Device-wide form for long size arrays (the gathered sizes of a sharded snapshot): every CTA scans a tile of 4096
+// sizes locally and posts its total, k_scan_sizes scans the tile totals, a last pass adds each tile's base.
+constexpr int SCAN_TILE = 4096;
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int64_t *sizes, int64_t n, int64_t *offsets, int64_t *tile_sums) {
+    __shared__ long long s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+    long long v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = i0 + k < n ? sizes[i0 + k] : 0; t += v[k]; }
+    long long incl = t;
+    for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = s_warp[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    long long excl = s_warp[warp] + incl - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i0 + k < n) offsets[i0 + k] = excl; excl += v[k]; }
+}
+__global__ void __launch_bounds__(1024) k_scan_add(int64_t *offsets, int64_t n, const int64_t *tile_offsets) {
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+    const long long base = tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (i0 + k < n) offsets[i0 + k] += base;
+}
+
+size_t scan_scratch_bytes(int64_t n) { return n > 2 * SCAN_TILE ? 16 * (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 64 : 0; }
+
 cudaError_t launch_scan_sizes(Launcher &L, const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets,
-                              int64_t *total) {
+                              int64_t *total, void *scratch) {
+    if (n > 2 * SCAN_TILE && scratch) {
+        const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+        int64_t *tile_sums = (int64_t *)scratch, *tile_offs = tile_sums + ntiles;
+        k_scan_tiles<<<(unsigned)ntiles, 1024, 0, L.stream>>>(sizes, n, offsets, tile_sums);
+        k_scan_sizes<<<1, 1024, 0, L.stream>>>(tile_sums, ntiles, base, tile_offs, total);
+        k_scan_add<<<(unsigned)ntiles, 1024, 0, L.stream>>>(offsets, n, tile_offs);
+        L.count += 3;
+        return cudaGetLastError();
+    }
     k_scan_sizes<<<1, 1024, 0, L.stream>>>(sizes, n, base, offsets, total);
     L.count++;
     return cudaGetLastError();

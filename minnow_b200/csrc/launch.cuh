@@ -99,8 +99,9 @@ void launch_init_stats(Launcher &L, const BlockDesc *descs, BlockStat *stats, in
 void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
                       const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,
                       int64_t chain_cap, int *err);
+size_t scan_scratch_bytes(int64_t n);   // scratch launch_scan_sizes wants for n sizes (0: none)
 cudaError_t launch_scan_sizes(Launcher &L, const int64_t *sizes, int64_t n, int64_t base, int64_t *offsets,
-                              int64_t *total);
+                              int64_t *total, void *scratch = nullptr);
 void launch_raw_pack(Launcher &L, BlockDesc *descs, BlockStat *stats, const void *src, int64_t n, int bits,
                      uint8_t *out);
 void launch_umax(Launcher &L, const unsigned long long *x, int64_t n, unsigned long long *out);

@@ -53,13 +53,22 @@ class Writer:
         nsub3, sc3 = (nfile // sub) ** 3, sub ** 3
         descs, mins, bits, offs, streams = self.ctx.minp_encode_vectors(vec, nfile, sub, self.periodic,
                                                                         float(self.hd["L"]), self.dx)
+        self.EncodedVectors(descs, mins, bits, streams)
+
+    def EncodedVectors(self, descs, mins, bits, streams):
+        """The three FloatGroups of one Vectors call from bytes that were encoded elsewhere -- by a device-resident
+        mnw_minp_encode_vectors_dev batch, or by another rank of a sharded snapshot (its bytes read back from
+        groupOffset + base_r): what Vectors records for them, go/minp/minp.go:112-118."""
+        nfile = NFile(self.c, int(self.hd["NSide"]))
+        sub = int(self.c["SubCells"])
+        nsub3, sc3 = (nfile // sub) ** 3, sub ** 3
         w = self.f
         for k in range(3):                   # one FloatGroup per axis, sub^3 blocks each (:112-118)
             g = minnow._Group(minnow.FloatGroup, w.blocks, nsub3)
             g.low, g.high = np.float32(descs[k].low), np.float32(descs[k].high)
             g.pixels, g.periodic = int(descs[k].pixels), 1
             w._new_group(g)
-            w.f.write(streams[k].tobytes())
+            w.f.write(bytes(streams[k]) if isinstance(streams[k], (bytes, bytearray, memoryview)) else np.asarray(streams[k]).tobytes())
             sl = slice(k * sc3, (k + 1) * sc3)
             g.mins, g.bits = [int(m) for m in mins[sl]], [int(b) for b in bits[sl]]
             g.sizes = [array_bytes(b, nsub3) for b in g.bits]

@@ -424,3 +424,30 @@ def test_pipe_reports_capacity_error_on_wait():
     pipe.drain()
     assert lens.min() > 0
     pipe.close()
+
+
+# ---------------------------------------------------------------------------------------- sharded path behind the ABI
+def test_comm_single_rank_and_device_wide_scan(ctx):
+    """mnw_comm_init (NCCL loaded at run time) with a world of one, the all-gather + scan call, and the device-wide scan
+    on an index longer than one CTA's tile"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(9)
+    n = 98304 * 2 + 123
+    sizes = torch.randint(0, 1 << 20, (n,), generator=g, device=dev, dtype=torch.int64)
+    offs, total = torch.zeros_like(sizes), torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.scan_offsets_dev(sizes, n, 17, offs, total)
+    ctx.sync()
+    inc = torch.cumsum(sizes, 0)
+    assert torch.equal(offs, inc - sizes + 17) and int(total) == int(inc[-1])
+    c2 = mb.Context(0)
+    try:
+        assert c2.comm_size == 1
+        c2.comm_init(mb.Context.comm_unique_id(), 1, 0)
+        allsz, alloff = torch.zeros_like(sizes), torch.zeros_like(sizes)
+        c2.sharded_offsets_dev(sizes, n, allsz, alloff, total)
+        c2.sync()
+        assert torch.equal(allsz, sizes) and torch.equal(alloff, inc - sizes) and int(total) == int(inc[-1])
+        c2.comm_destroy()
+    finally:
+        c2.close()
