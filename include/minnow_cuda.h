@@ -150,6 +150,28 @@ MNW_API int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column
                                    int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
                                    int64_t out_col_stride);
 
+/* ---- minh BoundaryWriter (go/minh/boundary.go): cell + ghost-layer binning and the per-cell column encode -------------
+ * mnw_boundary_coordinates = BoundaryWriter.Coordinates (:39-51): cellSizes (:93-109), indices (:54-86), hostCells
+ *   (:111-151), idxReg (:154-165) and region (:173-180) for n points (HOST x, y, z) in a periodic box of size L cut into
+ *   cells^3 cells with ghost layers of width `boundary`.  sizes [cells^3] (HOST) gets the number of points of every
+ *   cell + ghost region, total their sum.  The per-cell index lists and boundary flags -- in the reference's order -- STAY
+ *   ON THE DEVICE in the context for the column calls below; mnw_boundary_index copies them out (idx, flags: HOST
+ *   int64 [total]; flags are 0 in a point's own cell and 1 in a ghost region).  A coordinate outside [0, 2 L) is
+ *   MNW_ERR_ARG (the reference indexes outside its grid and panics).
+ * mnw_boundary_encode_{int,float}_column = the IntGroup / FloatGroup branches of BoundaryWriter.Column (:184-225): cell i
+ *   becomes block i (its own minnow group in the file) holding col[idx] of the cell's points, gathered on the device.
+ * mnw_boundary_encode_flags = boundaryColumn (:227-246).  Outputs as in mnw_encode_int_group (cells^3 blocks). */
+MNW_API int mnw_boundary_coordinates(mnw_ctx *ctx, const float *x, const float *y, const float *z, int64_t n, float L,
+                                     float boundary, int64_t cells, int64_t *sizes, int64_t *total);
+MNW_API int mnw_boundary_index(mnw_ctx *ctx, int64_t *idx, int64_t *flags);
+MNW_API int mnw_boundary_encode_int_column(mnw_ctx *ctx, const int64_t *col, int64_t ncol, int64_t *mins, int64_t *bits,
+                                           int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len);
+MNW_API int mnw_boundary_encode_float_column(mnw_ctx *ctx, const mnw_float_desc *desc, const float *col, int64_t ncol,
+                                             int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                                             int64_t out_cap, int64_t *out_len);
+MNW_API int mnw_boundary_encode_flags(mnw_ctx *ctx, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out,
+                                      int64_t out_cap, int64_t *out_len);
+
 /* Decode nsel blocks of one group.  data/offsets/mins/bits describe the whole
  * group (nblocks entries; offsets as produced above); sel lists the block ids
  * to decode (NULL = blocks 0..nsel-1); block sel[j] lands at out + j*n.

@@ -89,6 +89,11 @@ SIGNATURES = {
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
     "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
+    "mnw_boundary_coordinates": (_int, [_p, _p, _p, _p, _i64, _f32, _f32, _i64, _p, C.POINTER(_i64)]),
+    "mnw_boundary_index": (_int, [_p, _p, _p]),
+    "mnw_boundary_encode_int_column": (_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_boundary_encode_float_column": (_int, [_p, _FD, _p, _i64, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
+    "mnw_boundary_encode_flags": (_int, [_p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_comm_unique_id": (_int, [_p]),
     "mnw_comm_init": (_int, [_p, _p, _int, _int]),
     "mnw_comm_destroy": (_int, [_p]),
@@ -417,6 +422,41 @@ class Context:
                 cols[i].desc = d
             ptrs[i] = x.data_ptr() if hasattr(x, "data_ptr") else int(x)
         self._check(self.lib.mnw_encode_columns_dev(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), out_col_stride))
+
+    # ---- minh BoundaryWriter ------------------------------------------------------------------
+    def boundary_coordinates(self, x, y, z, L, boundary, cells):
+        """BoundaryWriter.Coordinates (go/minh/boundary.go:39-51) -> sizes [cells^3]; the index lists stay on the device"""
+        x, y, z = (_np(a, np.float32).reshape(-1) for a in (x, y, z))
+        sizes, total = np.zeros(cells ** 3, np.int64), _i64(0)
+        self._check(self.lib.mnw_boundary_coordinates(self.h, _ptr(x), _ptr(y), _ptr(z), len(x), float(L), float(boundary), cells,
+                                                      _ptr(sizes), C.byref(total)))
+        self._bnd_total, self._bnd_cells = total.value, cells
+        return sizes
+
+    def boundary_index(self):
+        idx, flags = np.zeros(self._bnd_total, np.int64), np.zeros(self._bnd_total, np.int64)
+        self._check(self.lib.mnw_boundary_index(self.h, _ptr(idx), _ptr(flags)))
+        return idx, flags
+
+    def _boundary_encode(self, fn, pre, col, ncol):
+        nb = self._bnd_cells ** 3
+        mins, bits, offs = (np.zeros(nb, np.int64) for _ in range(3))
+        out = np.zeros(8 * self._bnd_total + 64, np.uint8)
+        ln = _i64(0)
+        args = pre + ((_ptr(col), ncol) if col is not None else ())
+        self._check(fn(self.h, *args, _ptr(mins), _ptr(bits), _ptr(offs), _ptr(out), len(out), C.byref(ln)))
+        return mins, bits, offs, out[:ln.value].copy()
+
+    def boundary_encode_column(self, col, desc=None):
+        """BoundaryWriter.Column for an IntGroup (desc None) or FloatGroup column -> (mins, bits, offsets, data), one block per cell"""
+        if desc is None:
+            col = _np(col, np.int64).reshape(-1)
+            return self._boundary_encode(self.lib.mnw_boundary_encode_int_column, (), col, len(col))
+        col = _np(col, np.float32).reshape(-1)
+        return self._boundary_encode(self.lib.mnw_boundary_encode_float_column, (C.byref(desc),), col, len(col))
+
+    def boundary_encode_flags(self):
+        return self._boundary_encode(self.lib.mnw_boundary_encode_flags, (), None, 0)
 
     def decode_int_blocks(self, data, offsets, mins, bits, n, sel=None):
         """intGroup.readData per selected block (go/group.go:257-263)"""

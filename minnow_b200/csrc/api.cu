@@ -33,6 +33,7 @@ int mnw_fail(mnw_ctx *c, int code, const char *fmt, ...) {
 int mnw_report_device_error(mnw_ctx *ctx, int err) {
     if (err == 1) return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
     if (err == 2) return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
+    if (err == 3) return fail(ctx, MNW_ERR_ARG, "a coordinate lies outside [0, 2 L): the reference indexes outside its cell grid there");
     return MNW_OK;
 }
 
@@ -174,13 +175,15 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
 // Host-pointer group encode: stage in, run, stage out.
 int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *x, int64_t n,
                       int64_t nblocks, const int64_t *starts, int64_t *mins, int64_t *bits, int64_t *offsets,
-                      uint8_t *out, int64_t out_cap, int64_t *out_len, const int64_t *idx = nullptr, int64_t ncol = 0) {
+                      uint8_t *out, int64_t out_cap, int64_t *out_len, const int64_t *idx = nullptr, int64_t ncol = 0,
+                      const int64_t *d_idx_resident = nullptr, const void *x_dev = nullptr) {
+    // d_idx_resident: the gather index is on the device already (mnw_boundary_coordinates); x_dev: so are the elements
     if (nblocks < 0 || n < 0) return fail(ctx, MNW_ERR_ARG, "negative block count or length");
     const size_t esz = kind == KIND_I64 ? 8 : 4;
     int64_t total = starts ? starts[nblocks] - starts[0] : n * nblocks;
     if (starts && starts[0] != 0) return fail(ctx, MNW_ERR_ARG, "starts[0] must be 0");
-    const int64_t nsrc = idx ? ncol : total;   // elements to upload: the whole column for a gather
-    const int64_t *d_idx = nullptr;
+    const int64_t nsrc = (idx || d_idx_resident) ? ncol : total;   // elements to upload: the whole column for a gather
+    const int64_t *d_idx = d_idx_resident;
     if (idx) {
         if (!starts) return fail(ctx, MNW_ERR_ARG, "a gather needs starts[]");
         for (int64_t i = 0; i < total; i++)
@@ -193,7 +196,7 @@ int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const 
     CU(ctx->out.reserve(8 * (size_t)total + 64));
     int rc = reserve_batch(ctx, nblocks, 1);
     if (rc) return rc;
-    if (nsrc > 0) CU(cudaMemcpyAsync(ctx->in.p, x, esz * (size_t)nsrc, cudaMemcpyHostToDevice, ctx->L.stream));
+    if (nsrc > 0 && !x_dev) CU(cudaMemcpyAsync(ctx->in.p, x, esz * (size_t)nsrc, cudaMemcpyHostToDevice, ctx->L.stream));
 
     const int64_t *d_starts = nullptr, *d_tile0 = nullptr, *d_chunk0 = nullptr;
     int64_t total_tiles = 0, total_chunks = 0;
@@ -218,7 +221,7 @@ int encode_group_host(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const 
     }
     int64_t *d_meta = ctx->meta.as<int64_t>();
     int64_t *d_mins = d_meta, *d_bits = d_meta + nblocks, *d_offs = d_meta + 2 * nblocks, *d_len = d_meta + 3 * nblocks;
-    rc = encode_group_dev(ctx, kind, desc, ctx->in.p, n, nblocks, d_starts, d_tile0, d_chunk0, total_tiles,
+    rc = encode_group_dev(ctx, kind, desc, x_dev ? x_dev : ctx->in.p, n, nblocks, d_starts, d_tile0, d_chunk0, total_tiles,
                           total_chunks, d_mins, d_bits, d_offs, ctx->out.as<uint8_t>(), (int64_t)ctx->out.cap, d_len, d_idx);
     if (rc) return rc;
     std::vector<int64_t> h_meta(3 * (size_t)nblocks + 1);
@@ -479,7 +482,8 @@ void mnw_destroy(mnw_ctx *ctx) {
     mnw_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws})
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws,
+                      &ctx->bnd_idx, &ctx->bnd_flags, &ctx->bnd_work})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -658,6 +662,97 @@ int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, cons
     if (rc) return rc;
     if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
     return encode_group_host(ctx, KIND_F32, desc, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
+}
+
+// ---- minh BoundaryWriter (go/minh/boundary.go) ------------------------------------------------------------------------
+int mnw_boundary_coordinates(mnw_ctx *ctx, const float *x, const float *y, const float *z, int64_t n, float L, float boundary,
+                             int64_t cells, int64_t *sizes, int64_t *total) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (n < 0 || cells < 1 || cells > 1625) return fail(ctx, MNW_ERR_ARG, "mnw_boundary_coordinates: n = %lld, cells = %lld", (long long)n, (long long)cells);
+    const int64_t c3 = cells * cells * cells;
+    ctx->bnd_n = -1; ctx->bnd_m = 0;
+    CU(ctx->in.reserve(12 * (size_t)n + 64));
+    CU(ctx->bnd_work.reserve(8 * (2 * (size_t)n + (size_t)c3 + 2) + scan_scratch_bytes(n) + 64));
+    float *dx = ctx->in.as<float>(), *dy = dx + n, *dz = dy + n;
+    int64_t *d_cnt = ctx->bnd_work.as<int64_t>(), *d_eoff = d_cnt + n, *d_sizes = d_eoff + n, *d_total = d_sizes + c3;
+    void *scan_scratch = d_total + 2;
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
+    if (n > 0) {
+        CU(cudaMemcpyAsync(dx, x, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+        CU(cudaMemcpyAsync(dy, y, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+        CU(cudaMemcpyAsync(dz, z, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    }
+    launch_bnd_count(ctx->L, dx, dy, dz, n, L, boundary, cells, d_cnt, d_sizes, ctx->flags.as<int>() + FLAG_ERR);
+    CU(cudaMemsetAsync(d_total, 0, 8, ctx->L.stream));
+    if (n > 0) {
+        const cudaError_t e = launch_scan_sizes(ctx->L, d_cnt, n, 0, d_eoff, d_total, scan_scratch);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "boundary scan: %s", cudaGetErrorString(e));
+    }
+    std::vector<int64_t> h((size_t)c3 + 1);
+    CU(cudaMemcpyAsync(h.data(), d_sizes, 8 * ((size_t)c3 + 1), cudaMemcpyDeviceToHost, ctx->L.stream));   // sizes, then the total
+    int rc = check_flags(ctx);   // synchronises; a coordinate outside the grid is an argument error (the reference panics)
+    if (rc) return rc;
+    const int64_t m = h[(size_t)c3];
+    ctx->bnd_starts.assign((size_t)c3 + 1, 0);
+    for (int64_t g = 0; g < c3; g++) ctx->bnd_starts[(size_t)g + 1] = ctx->bnd_starts[(size_t)g] + h[(size_t)g];
+    if (ctx->bnd_starts[(size_t)c3] != m) return fail(ctx, MNW_ERR_CUDA, "boundary: cell sizes and entry count disagree");
+    if (sizes) memcpy(sizes, h.data(), 8 * (size_t)c3);
+    if (total) *total = m;
+    CU(ctx->bnd_idx.reserve(8 * (size_t)m + 64));
+    CU(ctx->bnd_flags.reserve(8 * (size_t)m + 64));
+    CU(ctx->out.reserve(2 * 12 * (size_t)m + bnd_sort_scratch_bytes(m) + 256));   // sort buffers: released to the next encode
+    uint8_t *w = ctx->out.as<uint8_t>();
+    int64_t *vals = (int64_t *)w, *vals2 = vals + m;
+    uint32_t *keys = (uint32_t *)(vals2 + m), *keys2 = keys + m;
+    void *scratch = (void *)(((uintptr_t)(keys2 + m) + 15) & ~(uintptr_t)15);
+    const cudaError_t e = launch_bnd_index(ctx->L, dx, dy, dz, n, L, boundary, cells, d_eoff, m, keys, vals, keys2, vals2, scratch,
+                                           ctx->bnd_idx.as<int64_t>(), ctx->bnd_flags.as<int64_t>());
+    if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "boundary index: %s", cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(ctx->L.stream));   // (ctx->out is about to be reused by the column encoders)
+    ctx->bnd_n = n; ctx->bnd_m = m;
+    return MNW_OK;
+}
+
+int mnw_boundary_index(mnw_ctx *ctx, int64_t *idx, int64_t *flags) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (ctx->bnd_n < 0) return fail(ctx, MNW_ERR_ARG, "no mnw_boundary_coordinates call on this context");
+    if (ctx->bnd_m > 0 && idx) CU(cudaMemcpyAsync(idx, ctx->bnd_idx.p, 8 * (size_t)ctx->bnd_m, cudaMemcpyDeviceToHost, ctx->L.stream));
+    if (ctx->bnd_m > 0 && flags) CU(cudaMemcpyAsync(flags, ctx->bnd_flags.p, 8 * (size_t)ctx->bnd_m, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+static int boundary_column(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const void *col, int64_t ncol, const void *x_dev,
+                           int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (ctx->bnd_n < 0) return fail(ctx, MNW_ERR_ARG, "no mnw_boundary_coordinates call on this context");
+    if (!x_dev && ncol != ctx->bnd_n) return fail(ctx, MNW_ERR_ARG, "column of %lld elements, coordinates of %lld", (long long)ncol, (long long)ctx->bnd_n);
+    const int64_t nblocks = (int64_t)ctx->bnd_starts.size() - 1;
+    if (x_dev)   // the boundary flags themselves: contiguous ragged blocks, already on the device
+        return encode_group_host(ctx, kind, desc, nullptr, 0, nblocks, ctx->bnd_starts.data(), mins, bits, offsets, out, out_cap, out_len,
+                                 nullptr, 0, nullptr, x_dev);
+    return encode_group_host(ctx, kind, desc, col, 0, nblocks, ctx->bnd_starts.data(), mins, bits, offsets, out, out_cap, out_len, nullptr,
+                             ncol, ctx->bnd_idx.as<int64_t>());
+}
+
+int mnw_boundary_encode_int_column(mnw_ctx *ctx, const int64_t *col, int64_t ncol, int64_t *mins, int64_t *bits, int64_t *offsets,
+                                   uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    return boundary_column(ctx, KIND_I64, nullptr, col, ncol, nullptr, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_boundary_encode_float_column(mnw_ctx *ctx, const mnw_float_desc *desc, const float *col, int64_t ncol, int64_t *mins,
+                                     int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+    int rc = check_desc(ctx, desc);
+    if (rc) return rc;
+    return boundary_column(ctx, KIND_F32, desc, col, ncol, nullptr, mins, bits, offsets, out, out_cap, out_len);
+}
+
+int mnw_boundary_encode_flags(mnw_ctx *ctx, int64_t *mins, int64_t *bits, int64_t *offsets, uint8_t *out, int64_t out_cap,
+                              int64_t *out_len) {
+    return boundary_column(ctx, KIND_I64, nullptr, nullptr, 0, ctx ? ctx->bnd_flags.p : nullptr, mins, bits, offsets, out, out_cap, out_len);
 }
 
 int mnw_decode_int_blocks(mnw_ctx *ctx, const uint8_t *data, int64_t data_len, const int64_t *offsets,

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/minnow_cuda.h"
 #include "engine.cuh"
@@ -40,6 +41,10 @@ struct mnw_ctx {
     void *h_stage = nullptr; // pinned staging for gathered uploads (grow-only)
     size_t h_stage_cap = 0;
     bool flags_init = false; // the device flag words have been zeroed once (the error word is sticky afterwards)
+    // minh BoundaryWriter: the per-cell index lists of the last mnw_boundary_coordinates call, resident on the device
+    DevBuf bnd_idx, bnd_flags, bnd_work;
+    std::vector<int64_t> bnd_starts;   // [cells^3 + 1], host
+    int64_t bnd_n = -1, bnd_m = 0;
     void *comm = nullptr;    // ncclComm_t of the sharded path (comm_api.cu); null = a world of one
     int comm_ranks = 0, comm_rank = 0;
 };

@@ -82,6 +82,13 @@ void launch_build_vec3(Launcher &L, BlockDesc *descs, int64_t nfiles, const floa
 // bounds() of minp.Writer.Vectors (go/minp/minp.go:291-300): keys[f*6 + k] = min, [f*6 + 3 + k] = max,
 // as order-preserving uint32 keys (decode with key_to_float on the host).
 void launch_vec3_limits(Launcher &L, const float *aos, int64_t np_per_file, int64_t nfiles, uint32_t *keys);
+// kernels_boundary.cu: minh BoundaryWriter.Coordinates (go/minh/boundary.go:39-180)
+void launch_bnd_count(Launcher &L, const float *x, const float *y, const float *z, int64_t n, float l, float boundary, int64_t cells,
+                      int64_t *cnt, int64_t *sizes, int *err);
+size_t bnd_sort_scratch_bytes(int64_t m);
+cudaError_t launch_bnd_index(Launcher &L, const float *x, const float *y, const float *z, int64_t n, float l, float boundary,
+                             int64_t cells, const int64_t *eoff, int64_t m, uint32_t *keys, int64_t *vals, uint32_t *keys2,
+                             int64_t *vals2, void *scratch, int64_t *idx, int64_t *flags);
 void launch_vec3_params(Launcher &L, const uint32_t *keys, int64_t nfiles, float dx, FloatParams *tab, void *desc_out, int *skip,
                         int *abort_flag, int need_pipe);
 void launch_params_from_desc(Launcher &L, const void *desc, int64_t n, FloatParams *tab);

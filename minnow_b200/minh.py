@@ -99,6 +99,79 @@ def Create(fname, ctx):
     return Writer(fname, ctx)
 
 
+class BoundaryWriter(Writer):
+    """minh.BoundaryWriter, go/minh/boundary.go: a catalogue split into cells^3 cells, every cell stored together with the
+    points of its ghost layers.  Coordinates bins the points on the GPU (the index lists stay on the device); Column
+    gathers and encodes every cell's values there."""
+
+    def __init__(self, fname, ctx):                                                          # CreateBoundary, :25-29
+        super().__init__(fname, ctx, boundaryFileType)
+        self.names, self.colspecs = [], []
+        self.cell_sizes = self._index = None
+
+    def Header(self, text):                                                                  # :31-33
+        self.f.Header(text.encode("ascii"))
+
+    def Block(self, cols):                                                                   # :35-37
+        raise RuntimeError("Block() cannot be called for BoundaryWriter. Use")
+
+    def Coordinates(self, x, y, z):                                                          # :39-51
+        self.cell_sizes = self.ctx.boundary_coordinates(x, y, z, self.l, self.boundary, self.cells)
+        self._index = None
+        self._encoded_column("boundary", columns([(minnow.IntGroup,)])[0], *self.ctx.boundary_encode_flags())   # boundaryColumn, :227-246
+        self.block_sizes = [int(n) for n in self.cell_sizes]
+        self.blocks = len(self.cell_sizes)
+
+    def _encoded_column(self, name, col, mins, bits, offs, data):
+        self.colspecs.append(col)
+        self.names.append(name)
+        w, t = self.f, int(col["Type"])
+        for i, N in enumerate(self.cell_sizes):
+            N = int(N)
+            if t == minnow.IntGroup:
+                w.IntGroup(N)
+            else:
+                w.FloatGroup(N, (col["Low"], col["High"]), col["Dx"])
+            w.EncodedBlock(mins[i], bits[i], data[offs[i]:offs[i] + array_bytes(int(bits[i]), N)])
+
+    def Column(self, name, col, x):                                                          # :184-225
+        if self.cell_sizes is None:
+            raise RuntimeError("Column called before Coordinates")
+        col = np.asarray(col, Column).reshape(1)[0] if not isinstance(col, np.void) else col
+        t = int(col["Type"])
+        if t == minnow.IntGroup:
+            self._encoded_column(name, col, *self.ctx.boundary_encode_column(np.asarray(x, np.int64)))
+        elif t == minnow.FloatGroup:
+            lo, hi = np.float32(col["Low"]), np.float32(col["High"])
+            d = FloatDesc.make(lo, hi, float_group_pixels(lo, hi, np.float32(col["Dx"])), 1, 1 if col["Log"] != 0 else 0, 1)
+            self._encoded_column(name, col, *self.ctx.boundary_encode_column(np.asarray(x, np.float32), d))
+        elif t in (minnow.Int64Group, minnow.Float32Group):       # fixed-size columns: a plain gather and copy, as in the format
+            if self._index is None:
+                self._index = self.ctx.boundary_index()[0]
+            x = np.asarray(x, minnow._FIXED[t])
+            self.colspecs.append(col)
+            self.names.append(name)
+            start = 0
+            for N in self.cell_sizes:
+                self.f.FixedSizeGroup(t, int(N))
+                self.f.Data(x[self._index[start:start + int(N)]])
+                start += int(N)
+        else:
+            raise ValueError("Can't write column with type flag %d" % t)
+
+    def Close(self):                                                                         # :249-256
+        self.f.Header("$".join(self.names).encode("ascii"))
+        self.f.Header(np.asarray(self.colspecs, Column).tobytes() if self.colspecs else b"")
+        self.f.Header(struct.pack("<ffq", self.l, self.boundary, self.cells))
+        self.f.Header(struct.pack("<q", self.blocks))
+        self.f.Header(np.asarray(self.block_sizes, "<i8").tobytes())
+        self.f.Close()
+
+
+def CreateBoundary(fname, ctx):
+    return BoundaryWriter(fname, ctx)
+
+
 class Reader:
     def __init__(self, fname, ctx, jitter=None):                                             # Open, :184-226
         self.f = minnow.Open(fname, ctx, jitter)

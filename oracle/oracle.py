@@ -101,6 +101,10 @@ def _declare(L):
         "orc_bench_minp_decode": (None, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _int, _f32, _int, _u64, _p, _int]),
         "orc_bench_group_encode": (_i64, [_int, _p, _i64, _i64, _f32, _f32, _i64, _int, _int, _p, _p, _p, _p, _i64, _int]),
         "orc_bench_group_decode": (None, [_int, _p, _i64, _i64, _i64, _p, _p, _p, _f32, _f32, _i64, _int, _int, _u64, _p, _int]),
+        "orc_bnd_region": (_int, [_f32, _f32, _i64, _f32, _i64, _f32]),
+        "orc_bnd_idx_reg": (None, [_f32, _f32, _i64, _f32, _p, _p, _p]),
+        "orc_bnd_host_cells": (_int, [_i64, _p, _p, _p]),
+        "orc_boundary_bin": (_i64, [_p, _p, _p, _i64, _f32, _f32, _i64, _f32, _p, _p, _p]),
         "orc_max_threads": (_int, []),
     }
     for name, (res, args) in sig.items():
@@ -472,6 +476,36 @@ def bench_group_decode(packed, stride, n, mins, bits, desc=None, sel=None, jitte
     lib().orc_bench_group_decode(kind, _ptr(packed), stride, n, nsel, _ptr(s) if s is not None else None, _ptr(mins), _ptr(bits),
                                  low, high, pixels, int(is_log), jitter_mode, seed, _ptr(out), threads)
     return out
+
+
+# ---- minh BoundaryWriter.Coordinates (go/minh/boundary.go:39-180) -----------------------------
+def bnd_region(l, boundary, cells, scaled, ix, x):
+    return int(lib().orc_bnd_region(l, boundary, cells, scaled, ix, x))
+
+
+def bnd_idx_reg(l, boundary, cells, scaled, vec):
+    v = _c(vec, np.float32)
+    idx, reg = np.zeros(3, np.int64), np.zeros(3, np.int32)
+    lib().orc_bnd_idx_reg(l, boundary, cells, scaled, _ptr(v), _ptr(idx), _ptr(reg))
+    return idx.tolist(), reg.tolist()
+
+
+def bnd_host_cells(cells, idx, reg):
+    i, r, out = _c(idx, np.int64), _c(reg, np.int32), np.zeros(8, np.int64)
+    n = lib().orc_bnd_host_cells(cells, _ptr(i), _ptr(r), _ptr(out))
+    return out[:n].tolist()
+
+
+def boundary_bin(x, y, z, l, boundary, cells, scaled=-1.0, want_index=True):
+    """-> sizes [cells^3], idx (points of every cell in insertion order, cell after cell), flags"""
+    x, y, z = _c(x, np.float32), _c(y, np.float32), _c(z, np.float32)
+    sizes = np.zeros(cells ** 3, np.int64)
+    total = lib().orc_boundary_bin(_ptr(x), _ptr(y), _ptr(z), len(x), l, boundary, cells, scaled, _ptr(sizes), None, None)
+    if not want_index:
+        return sizes, None, None
+    idx, flags = np.zeros(total, np.int64), np.zeros(total, np.int8)
+    lib().orc_boundary_bin(_ptr(x), _ptr(y), _ptr(z), len(x), l, boundary, cells, scaled, _ptr(sizes), _ptr(idx), _ptr(flags))
+    return sizes, idx, flags
 
 
 def max_threads():

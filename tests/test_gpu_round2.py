@@ -451,3 +451,102 @@ def test_comm_single_rank_and_device_wide_scan(ctx):
         c2.comm_destroy()
     finally:
         c2.close()
+
+
+# ---------------------------------------------------------------------------------------- minh BoundaryWriter
+def test_boundary_reference_kat(ctx):
+    """TestBoundary of go/minh/minh_test.go:336-404: three points, 2^3 cells of a 100 box with 20 of boundary"""
+    vecs = np.array([[25, 25, 25], [50, 50, 50], [26, 26, 95]], np.float32)
+    sizes = ctx.boundary_coordinates(vecs[:, 0], vecs[:, 1], vecs[:, 2], 100.0, 20.0, 2)
+    idx, flags = ctx.boundary_index()
+    want_ids = [[0, 1, 2], [1], [1], [1], [1, 2], [1], [1], [1]]
+    want_flags = [[0, 1, 1], [1], [1], [1], [1, 0], [1], [1], [0]]
+    assert sizes.tolist() == [len(w) for w in want_ids]
+    assert idx.tolist() == sum(want_ids, []) and flags.tolist() == sum(want_flags, [])
+
+
+@pytest.mark.parametrize("cells,bfrac,n", [(1, 0.1, 5000), (2, 0.2, 5000), (3, 0.0, 20000), (7, 0.05, 300000), (16, 0.12, 300000), (40, 0.3, 200000)])
+def test_boundary_binning_matches_oracle(ctx, orc, cells, bfrac, n):
+    rng = np.random.default_rng(cells * 1000 + n)
+    L = 250.0
+    pts = (rng.random((n, 3)) * L).astype(np.float32)
+    pts[::97] = np.float32(L) * rng.integers(0, cells + 1, (len(pts[::97]), 3)).astype(np.float32) / np.float32(cells)   # on cell faces
+    pts[pts >= L] = np.nextafter(np.float32(L), np.float32(0))
+    boundary = np.float32(bfrac * L / cells)
+    sizes = ctx.boundary_coordinates(pts[:, 0], pts[:, 1], pts[:, 2], L, boundary, cells)
+    idx, flags = ctx.boundary_index()
+    osz, oidx, ofl = orc.boundary_bin(pts[:, 0], pts[:, 1], pts[:, 2], np.float32(L), boundary, cells)
+    assert np.array_equal(sizes, osz)
+    assert np.array_equal(idx, oidx) and np.array_equal(flags, ofl.astype(np.int64))
+
+
+def test_boundary_rejects_points_outside_the_grid(ctx):
+    pts = np.array([[1.0, 2.0, 3.0], [250.0, 1.0, 1.0], [-300.0, 1.0, 1.0]], np.float32)
+    with pytest.raises(mb.MinnowError) as e:
+        ctx.boundary_coordinates(pts[:, 0], pts[:, 1], pts[:, 2], 100.0, 5.0, 4)
+    assert e.value.code == -2
+
+
+def test_boundary_writer_file_equals_reference_layout(ctx, orc, tmp_path):
+    """a boundary minh file written by the mirror (binning, gathers and encodes on the GPU) == the file assembled from the
+    oracle's binning and block encoders in BoundaryWriter's order (go/minh/boundary.go:184-256), and reads back"""
+    import struct
+    from minnow_b200 import minh, minnow
+    rng = np.random.default_rng(5)
+    n, cells, L, bnd = 30000, 3, np.float32(120.0), np.float32(9.0)
+    pts = (rng.random((n, 3)) * L).astype(np.float32)
+    ids = rng.permutation(n).astype(np.int64) + 10 ** 6
+    mass = np.power(10.0, rng.uniform(10.0, 15.0, n)).astype(np.float32)
+    cols = minh.columns([(minnow.Int64Group,), (minnow.IntGroup,), (minnow.FloatGroup, 0, 0.0, float(L), 0.01), (minnow.FloatGroup, 1, 10.0, 15.0, 0.001),
+                         (minnow.Float32Group,)])
+    names = ["id64", "id", "x", "mass", "rawx"]
+    data = [ids, ids, pts[:, 0], mass, pts[:, 0]]
+    path = str(tmp_path / "b.minh")
+    w = minh.CreateBoundary(path, ctx)
+    w.Header("text header")
+    w.Geometry(L, bnd, cells)
+    w.Coordinates(pts[:, 0], pts[:, 1], pts[:, 2])
+    for nm, c, x in zip(names, cols, data):
+        w.Column(nm, c, x)
+    w.Close()
+    got = open(path, "rb").read()
+
+    sizes, idx, flags = orc.boundary_bin(pts[:, 0], pts[:, 1], pts[:, 2], L, bnd, cells)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    ow = orc.Writer()
+    ow.header(struct.pack("<qqq", minh.Magic, minh.Version, minh.boundaryFileType))
+    ow.header(b"text header")
+    allcols = [minh.columns([(minnow.IntGroup,)])[0]] + list(cols)
+    for ci, (c, x) in enumerate(zip(allcols, [flags.astype(np.int64)] + data)):
+        t = int(c["Type"])
+        for g in range(cells ** 3):
+            sel = idx[starts[g]:starts[g + 1]]
+            blk = x[starts[g]:starts[g + 1]] if ci == 0 else x[sel]     # (the flags are per entry, the columns per point)
+            N = len(sel)
+            if t in (minnow.Int64Group, minnow.Float32Group):
+                ow.fixed_size_group(t, N)
+                ow.data(np.ascontiguousarray(blk))
+            elif t == minnow.IntGroup:
+                ow.int_group(N)
+                ow.data(np.ascontiguousarray(blk, np.int64))
+            else:
+                ow.float_group(N, (c["Low"], c["High"]), c["Dx"])
+                ow.data(orc.minh_process_float(np.ascontiguousarray(blk, np.float32), int(c["Log"]), c["Low"], c["High"]))
+    ow.header("$".join(["boundary"] + names).encode("ascii"))
+    ow.header(np.asarray(allcols, minh.Column).tobytes())
+    ow.header(struct.pack("<ffq", L, bnd, cells))
+    ow.header(struct.pack("<q", cells ** 3))
+    ow.header(np.asarray(sizes, "<i8").tobytes())
+    want = ow.close()
+    assert got == want
+
+    r = minh.Open(path, ctx)
+    assert r.Blocks == cells ** 3 and r.BlockLengths == sizes.tolist()
+    for b in (0, 13, 26):
+        sel = idx[starts[b]:starts[b + 1]]
+        ib = r.IntBlock(b, ["boundary", "id", "id64"])
+        assert np.array_equal(ib["id"], ids[sel]) and np.array_equal(ib["id64"], ids[sel])
+        assert np.array_equal(ib["boundary"], flags[starts[b]:starts[b + 1]].astype(np.int64))
+        fb = r.FloatBlock(b, ["x", "rawx"])
+        assert np.array_equal(fb["rawx"], pts[sel, 0]) and np.all(np.abs(fb["x"] - pts[sel, 0]) <= 0.0051)
+    r.Close()
