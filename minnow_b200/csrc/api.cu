@@ -877,7 +877,7 @@ static int encode_vec3_core(mnw_ctx *ctx, const FloatParams *tab, const std::vec
             CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
             coop_ws = ctx->coop_ws.p;
         }
-        const cudaError_t e = launch_fused_vec3(ctx->L, W, tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
+        const cudaError_t e = launch_fused_vec3(ctx->L, W, ctx->descs.as<BlockDesc>(), tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
                                                 ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
                                                 pipe_ok, coop_ws);
         if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));

@@ -31,7 +31,7 @@ struct FusedWork {
 // or 64, every group is periodic without minh pre-transform, and pixels < 2^30.
 bool fused_vec3_supported(const FloatParamsHost *fp, int64_t nparams, int nfile, int subcells, const void *aos);
 size_t fused_work_bytes(int64_t nblocks);
-cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams *tab, int tab_per_file,
+cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *descs, const FloatParams *tab, int tab_per_file,
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
                               int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
                               int64_t out_axis_stride, bool pipe_ok, void *coop_ws);

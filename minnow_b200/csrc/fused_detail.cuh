@@ -32,6 +32,7 @@ struct Fin {  // finalised block, identical in every CTA of the cluster
 };
 
 struct FusedArgs {
+    const BlockDesc *descs;   // the batch's block descriptors (k_build_vec3): the exact path of a unit with out-of-range values
     const float *aos;
     const FloatParams *tab;
     int tab_per_file;

@@ -270,16 +270,27 @@ __device__ __forceinline__ void slow_block(const BlockDesc &d, BlockStat *sb, in
 }
 
 // slow_block for ONE warp (all 32 lanes of the calling warp, no CTA-level barrier): the exact sequential periodicMin and
-// the min / max of bound() of a block with out-of-range pixel indices.
-__device__ __forceinline__ void slow_block_warp(const BlockDesc &d, BlockStat *sb, int *err) {
+// the min / max of bound() of a block with out-of-range pixel indices.  Values only (uniform across the warp).
+__device__ __forceinline__ void slow_block_warp_values(const BlockDesc &d, long long &pmin_out, long long &mn_out, long long &mx_out) {
     const long long P = d.pixels;
     const int lane = threadIdx.x & 31;
     long long x0 = block_value(d, 0), width = 1;
     bool returned_zero = false;
-    for (int64_t base = 0; base < d.n && !returned_zero; base += 32) {
+    for (int64_t base0 = 0; base0 < d.n && !returned_zero; base0 += 32 * 8) {
+      long long qq[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {   // 8 independent loads per lane in flight; the arc walk below is sequential
+          const int64_t i = base0 + 32 * u + lane;
+          qq[u] = i < d.n ? block_value(d, i) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (returned_zero) break;
+        const int64_t base = base0 + 32 * u;
+        if (base >= d.n) break;
         int64_t i = base + lane;
         bool valid = i < d.n;
-        long long q = valid ? block_value(d, i) : 0;
+        long long q = qq[u];
         unsigned pending = __ballot_sync(0xffffffffu, valid);
         while (pending) {
             long long x1 = (long long)((unsigned long long)x0 + (unsigned long long)width - 1ULL);
@@ -302,16 +313,33 @@ __device__ __forceinline__ void slow_block_warp(const BlockDesc &d, BlockStat *s
             if (width > P / 2) { returned_zero = true; break; }
             pending &= ~((2u << j) - 1u);  // elements up to j are done
         }
+      }
     }
     const long long pmin = returned_zero ? 0 : x0;   // uniform across the warp
     long long mn = LLONG_MAX, mx = LLONG_MIN;
-    for (int64_t i = lane; i < d.n; i += 32) {
-        long long q = bound1(block_value(d, i), pmin, P);
-        mn = q < mn ? q : mn;
-        mx = q > mx ? q : mx;
+    for (int64_t base = 0; base < d.n; base += 32 * 16) {   // 16 independent loads per lane in flight
+        long long q[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const int64_t i = base + 32 * u + lane;
+            q[u] = i < d.n ? block_value(d, i) : LLONG_MIN;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (base + 32 * u + lane < d.n) {
+                const long long qb = bound1(q[u], pmin, P);
+                mn = qb < mn ? qb : mn;
+                mx = qb > mx ? qb : mx;
+            }
+        }
     }
-    mn = warp_min_ll(mn); mx = warp_max_ll(mx);
-    if (lane == 0) {
+    pmin_out = pmin; mn_out = warp_min_ll(mn); mx_out = warp_max_ll(mx);
+}
+
+__device__ __forceinline__ void slow_block_warp(const BlockDesc &d, BlockStat *sb, int *err) {
+    long long pmin, mn, mx;
+    slow_block_warp_values(d, pmin, mn, mx);
+    if ((threadIdx.x & 31) == 0) {
         BlockStat s = *sb;
         s.pmin = pmin; s.do_bound = 1; s.min = mn;
         finish_stat(s, d.n, (unsigned long long)mx - (unsigned long long)mn, err);

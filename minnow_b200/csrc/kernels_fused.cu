@@ -830,11 +830,12 @@ static cudaError_t launch_fused_vec3_t(Launcher &L, const FusedArgs &A) {
 cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A);   // kernels_pipe.cu
 cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws, int nsub);
 
-cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const FloatParams *tab, int tab_per_file,
+cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *descs, const FloatParams *tab, int tab_per_file,
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
                               int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
                               int64_t out_axis_stride, bool pipe_ok, void *coop_ws) {
     FusedArgs A = {};
+    A.descs = descs;
     A.aos = aos; A.tab = tab; A.tab_per_file = tab_per_file; A.nfile = nfile; A.subcells = subcells;
     A.sc3 = (long long)subcells * subcells * subcells;
     A.nunits = nfiles * A.sc3;

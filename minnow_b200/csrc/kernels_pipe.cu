@@ -3,6 +3,7 @@
 #include <climits>
 
 #include "fused_detail.cuh"
+#include "group_detail.cuh"
 
 namespace mnw {
 

@@ -170,6 +170,55 @@ __device__ __noinline__ void pipe_redo_warp(unsigned bad_mask, const float4 *tba
     }
 }
 
+// The exact path of one block of a unit that raised the out-of-range flag (whole warp, from global memory).  One pass
+// classifies the block's pixel indices and takes the int64 min / max of bound(q, 0, pixels):
+//   code 0  every index lies in [0, pixels]: this AXIS was clean (the flag is per unit) -- the caller keeps its closed form;
+//   code 1  some indices are FAR outside (q >= 3 pixels or q < -2 pixels: NaN and infinities convert to the int64 minimum)
+//           and none is near: periodicMin is 0 whatever the order -- up to the first far element the walk of
+//           go/group.go:384-409 sees indices in range only (a valid arc, or it has returned 0 already), and a far element
+//           grows the arc beyond pixels / 2 in either branch -- so min and max of bound(q, 0, pixels) are the answer;
+//   code 2  anything else (an index slightly outside the range, or element 0 itself outside): the sequential walk.
+// out4 = {pmin, min, max, code}.  Out of line: it must not cost the scanner warp's hot path a register.
+__device__ __noinline__ void pipe_exact_block(const BlockDesc *dp, long long *out4) {
+    const BlockDesc d = *dp;
+    const int lane = threadIdx.x & 31;
+    const long long P = d.pixels;
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    bool near = false, far = false;
+    for (int64_t base = 0; base < d.n; base += 32 * 16) {   // 16 independent gathers per lane in flight
+        long long q[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const int64_t i = base + 32 * u + lane;
+            q[u] = i < d.n ? block_value(d, i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (base + 32 * u + lane < d.n) {
+                const long long v = q[u];
+                const bool inr = (unsigned long long)v <= (unsigned long long)P;
+                const bool isfar = v >= 3 * P || v < -2 * P;
+                far = far || isfar;
+                near = near || (!inr && !isfar);
+                const long long qb = bound1(v, 0, P);
+                mn = qb < mn ? qb : mn;
+                mx = qb > mx ? qb : mx;
+            }
+        }
+    }
+    const bool any_near = __any_sync(0xffffffffu, near), any_far = __any_sync(0xffffffffu, far);
+    const long long q0 = block_value(d, 0);
+    const bool q0_in = (unsigned long long)q0 < (unsigned long long)P;
+    if (!any_near && !any_far && q0_in) {
+        out4[3] = 0;
+    } else if (!any_near && q0_in && 2 * P > 0) {
+        out4[0] = 0; out4[1] = warp_min_ll(mn); out4[2] = warp_max_ll(mx); out4[3] = 1;
+    } else {
+        slow_block_warp_values(d, out4[0], out4[1], out4[2]);
+        out4[3] = 2;
+    }
+}
+
 // 16 fields of 2 B bits (two packed values each) -> B little-endian stream words, shifts resolved at
 // compile time (bit.BufferedArray, go/bit/bit.go:84-134, for 32 values of one lane).
 template <int B>
@@ -588,7 +637,10 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 // ---- finalise: lane k < 3 combines the cluster's statistics of axis k (every CTA, redundantly) ----
                 const int k = lane < 3 ? lane : 0;
                 const long long f_b = f * 3 * A.sc3 + k * A.sc3 + sc;   // block id in the batch
-                long long nbytes = 0;
+                long long nbytes = 0, mn = 0, pmin = 0, q0k = 0;
+                unsigned base = 0, padj = 0;
+                int bits = 0, mode = 0;
+                bool slow = false;
                 if (lane < 3) {
                     XStat x;
                     x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
@@ -612,10 +664,8 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                     }
                     const PipePar pp = s_par[par_i][k];
                     const long long Pk = (long long)pp.P, half = Pk / 2, K = Pk - half - 1;
-                    const long long q0k = pp.q0;
-                    long long mn, pmin;
+                    q0k = pp.q0;
                     unsigned long long maxoff;
-                    unsigned base, padj;
                     bool wide;
                     const unsigned long long spread = (unsigned long long)x.wmax - x.wmin + 1ULL;
                     if (spread > (unsigned long long)half) {   // arc too wide: periodicMin returns 0
@@ -629,23 +679,43 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         pmin = m; mn = m; maxoff = spread - 1ULL;
                         base = x.wmin; padj = 0;
                     }
-                    int bits = 64 - __clzll((long long)maxoff);   // bit.PrecisionNeeded (maxoff < 2^32 here)
+                    bits = 64 - __clzll((long long)maxoff);   // bit.PrecisionNeeded (maxoff < 2^32 here)
                     nbytes = array_bytes(bits, N);
-                    const bool slow = x.oob != 0 || pp.oob0 != 0;
-                    if (slow) { bits = 0; nbytes = 0; }
-                    if (rank == 0) st_relaxed(A.W.pub + f_b, PUB_AGG | (unsigned long long)nbytes);
+                    slow = x.oob != 0 || pp.oob0 != 0;
                     // staged values are the low 16 bits of w: enough when the packed value has <= 16 bits
                     // and (wide arcs) w itself fits, i.e. pixels <= 65536
-                    const int mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
+                    mode = (bits >= 1 && bits <= 16 && !(wide && Pk > 65536)) ? 1 : 0;
+                }
+                // ---- a unit that holds NaN / out-of-range values (rare): the exact sequential periodicMin and the int64
+                // statistics of its blocks, by this warp, from global memory -- the blocks then take the k_pack list like
+                // any block the staging cannot represent, and nothing else in the batch is disturbed ----
+                const unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
+                if (slow_mask) {
+#pragma unroll 1
+                    for (int kk = 0; kk < 3; kk++) {
+                        if (!((slow_mask >> kk) & 1u)) continue;
+                        const long long fb = f * 3 * A.sc3 + kk * A.sc3 + sc;
+                        long long ex[4];   // pmin, min, max, code
+                        pipe_exact_block(A.descs + fb, ex);
+                        if (lane == kk && ex[3] != 0) {
+                            pmin = ex[0]; mn = ex[1];
+                            bits = precision_needed((unsigned long long)ex[2] - (unsigned long long)ex[1]);
+                            if (bits < 0) { bits = 64; atomicExch(A.W.err, 1); }
+                            nbytes = array_bytes(bits, N);
+                            mode = 0;
+                        }
+                    }
+                }
+                if (lane < 3) {
+                    if (rank == 0) st_relaxed(A.W.pub + f_b, PUB_AGG | (unsigned long long)nbytes);
                     Fin fin;
                     fin.off = nbytes; fin.bits = bits; fin.mode = mode; fin.base = base; fin.padj = padj;
                     s_fin[k] = fin;
                     if (rank == 0) {
-                        if (!slow && bits > 0 && mode == 0) A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = f_b;
-                        if (slow) atomicExch(A.W.abort_flag, 1);
+                        if (bits > 0 && mode == 0) A.W.repack_list[atomicAdd(A.W.repack_count, 1)] = f_b;
                         BlockStat bs = {};
                         bs.pmin = pmin; bs.min = mn; bs.nbytes = nbytes; bs.out_off = 0; bs.do_bound = 1; bs.bits = bits;
-                        bs.q0 = q0k; bs.oob = slow;
+                        bs.q0 = q0k; bs.oob = slow; bs.slow = slow;
                         A.stats[f_b] = bs;
                         if (A.mins) A.mins[f_b] = mn;
                         if (A.bits) A.bits[f_b] = bits;
