@@ -150,6 +150,18 @@ MNW_API int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column
                                    int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
                                    int64_t out_col_stride);
 
+/* ---- Lagrangian re-gridding: the producer of minp.Writer.Vectors' input ------------------------------------------------
+ * vectorGrid.Insert over a batch (go/minp/snapshot/grid.go:206-211 with grid.Index :118-137, driven by xGrid / vGrid
+ * :168-204): particle j with 1-based ID ids[j] goes to cell c, slot i of a Lagrangian lattice of ncell^3 cells x nside^3
+ * particles.  grid_dev is a DEVICE array [ncell^3][nside^3][3] float32 that persists across calls (a snapshot arrives
+ * file by file) and is exactly the input layout of mnw_minp_encode_vectors_dev (nfiles = ncell^3, nfile = nside).
+ * mnw_regrid_insert takes HOST ids / vec and synchronises; the _dev form takes DEVICE pointers and only enqueues.
+ * An ID outside [1, (ncell * nside)^3] is MNW_ERR_ARG (grid.Index panics). */
+MNW_API int mnw_regrid_insert(mnw_ctx *ctx, const int64_t *ids, const float *vec, int64_t n, int64_t ncell, int64_t nside,
+                              float *grid_dev);
+MNW_API int mnw_regrid_insert_dev(mnw_ctx *ctx, const int64_t *ids, const float *vec, int64_t n, int64_t ncell,
+                                  int64_t nside, float *grid_dev);
+
 /* ---- minh BoundaryWriter (go/minh/boundary.go): cell + ghost-layer binning and the per-cell column encode -------------
  * mnw_boundary_coordinates = BoundaryWriter.Coordinates (:39-51): cellSizes (:93-109), indices (:54-86), hostCells
  *   (:111-151), idxReg (:154-165) and region (:173-180) for n points (HOST x, y, z) in a periodic box of size L cut into

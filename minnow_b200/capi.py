@@ -89,6 +89,8 @@ SIGNATURES = {
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
     "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
+    "mnw_regrid_insert": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
+    "mnw_regrid_insert_dev": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "mnw_boundary_coordinates": (_int, [_p, _p, _p, _p, _i64, _f32, _f32, _i64, _p, C.POINTER(_i64)]),
     "mnw_boundary_index": (_int, [_p, _p, _p]),
     "mnw_boundary_encode_int_column": (_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
@@ -422,6 +424,15 @@ class Context:
                 cols[i].desc = d
             ptrs[i] = x.data_ptr() if hasattr(x, "data_ptr") else int(x)
         self._check(self.lib.mnw_encode_columns_dev(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), out_col_stride))
+
+    # ---- Lagrangian re-gridding ---------------------------------------------------------------
+    def regrid_insert(self, ids, vec, ncell, nside, grid_dev, dev=False):
+        """vectorGrid.Insert over a batch (go/minp/snapshot/grid.go:118-137,206-211) into the device grid [ncell^3][nside^3][3]"""
+        if dev:
+            self._check(self.lib.mnw_regrid_insert_dev(self.h, _ptr(ids), _ptr(vec), ids.numel(), ncell, nside, _ptr(grid_dev)))
+        else:
+            ids, vec = _np(ids, np.int64).reshape(-1), _np(vec, np.float32).reshape(-1)
+            self._check(self.lib.mnw_regrid_insert(self.h, _ptr(ids), _ptr(vec), len(ids), ncell, nside, _ptr(grid_dev)))
 
     # ---- minh BoundaryWriter ------------------------------------------------------------------
     def boundary_coordinates(self, x, y, z, L, boundary, cells):

@@ -34,6 +34,7 @@ int mnw_report_device_error(mnw_ctx *ctx, int err) {
     if (err == 1) return fail(ctx, MNW_ERR_ARG, "block value range is 2^64-1: bit.PrecisionNeeded is undefined there");
     if (err == 2) return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
     if (err == 3) return fail(ctx, MNW_ERR_ARG, "a coordinate lies outside [0, 2 L): the reference indexes outside its cell grid there");
+    if (err == 4) return fail(ctx, MNW_ERR_ARG, "a particle ID is not valid for this NCell and NSide (grid.Index panics)");
     return MNW_OK;
 }
 
@@ -662,6 +663,34 @@ int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, cons
     if (rc) return rc;
     if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
     return encode_group_host(ctx, KIND_F32, desc, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
+}
+
+// ---- Lagrangian re-gridding (go/minp/snapshot/grid.go) -----------------------------------------------------------------
+int mnw_regrid_insert_dev(mnw_ctx *ctx, const int64_t *ids, const float *vec, int64_t n, int64_t ncell, int64_t nside, float *grid) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (n < 0 || ncell < 1 || nside < 1 || ncell * nside > 2097151) return fail(ctx, MNW_ERR_ARG, "regrid: n = %lld, ncell = %lld, nside = %lld", (long long)n, (long long)ncell, (long long)nside);
+    CU(ctx->flags.reserve(64));
+    if (!ctx->flags_init) { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
+    launch_regrid_insert(ctx->L, ids, vec, n, ncell, nside, grid, ctx->flags.as<int>() + FLAG_ERR);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+int mnw_regrid_insert(mnw_ctx *ctx, const int64_t *ids, const float *vec, int64_t n, int64_t ncell, int64_t nside, float *grid_dev) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (n < 0) return fail(ctx, MNW_ERR_ARG, "negative length");
+    CU(ctx->in.reserve(20 * (size_t)n + 64));
+    int64_t *d_ids = ctx->in.as<int64_t>();
+    float *d_vec = (float *)(d_ids + n);
+    if (n > 0) {
+        CU(cudaMemcpyAsync(d_ids, ids, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+        CU(cudaMemcpyAsync(d_vec, vec, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->L.stream));
+    }
+    int rc = mnw_regrid_insert_dev(ctx, d_ids, d_vec, n, ncell, nside, grid_dev);
+    if (rc) return rc;
+    return check_flags(ctx);   // synchronises; an invalid ID is an argument error, as in the reference
 }
 
 // ---- minh BoundaryWriter (go/minh/boundary.go) ------------------------------------------------------------------------

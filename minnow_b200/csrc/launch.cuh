@@ -89,6 +89,8 @@ size_t bnd_sort_scratch_bytes(int64_t m);
 cudaError_t launch_bnd_index(Launcher &L, const float *x, const float *y, const float *z, int64_t n, float l, float boundary,
                              int64_t cells, const int64_t *eoff, int64_t m, uint32_t *keys, int64_t *vals, uint32_t *keys2,
                              int64_t *vals2, void *scratch, int64_t *idx, int64_t *flags);
+// kernels_regrid.cu: vectorGrid.Insert over a batch (go/minp/snapshot/grid.go:118-137,206-211)
+void launch_regrid_insert(Launcher &L, const int64_t *ids, const float *vec, int64_t n, int64_t ncell, int64_t nside, float *grid, int *err);
 void launch_vec3_params(Launcher &L, const uint32_t *keys, int64_t nfiles, float dx, FloatParams *tab, void *desc_out, int *skip,
                         int *abort_flag, int need_pipe);
 void launch_params_from_desc(Launcher &L, const void *desc, int64_t n, FloatParams *tab);

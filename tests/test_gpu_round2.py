@@ -602,3 +602,55 @@ def test_one_bad_value_does_not_redo_the_batch(ctx, orc):
     print("clean %.3f ms, one NaN %.3f ms" % (t_clean, t_bad))
     assert t_bad < 40.0   # the exact path of ONE unit is a constant (~15 ms: three one-warp passes), whatever the batch size;
                           # the whole-batch generic redo it replaces costs ~50 ms on the 4096-unit benchmark batch and grows with it
+
+
+# ---------------------------------------------------------------------------------------- Lagrangian re-gridding
+def grid_index(ids0, ncell, nside):
+    """grid.Index, go/minp/snapshot/grid.go:118-137 (numpy restatement for the test)"""
+    nall = ncell * nside
+    idx, idy, idz = ids0 % nall, (ids0 // nall) % nall, ids0 // (nall * nall)
+    i = idx % nside + (idy % nside) * nside + (idz % nside) * nside * nside
+    c = idx // nside + (idy // nside) * ncell + (idz // nside) * ncell * ncell
+    return c, i
+
+
+def test_regrid_then_encode_on_the_device(ctx, orc):
+    """a snapshot arriving as 4 unordered files of (ID, position): vectorGrid.Insert on the GPU, then minp.Writer.Vectors of
+    every Lagrangian cell from the same device grid == the oracle on the numpy re-grid"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    ncell, nside, L, dx = 2, 64, 100.0, 0.01
+    nall = ncell * nside
+    ntot = nall ** 3
+    ids = rng.permutation(ntot).astype(np.int64) + 1
+    pos = (rng.random((ntot, 3)) * L).astype(np.float32)
+    grid = torch.zeros((ncell ** 3, nside ** 3, 3), dtype=torch.float32, device=dev)
+    for part in np.array_split(np.arange(ntot), 4):
+        ctx.regrid_insert(ids[part], pos[part], ncell, nside, grid)
+    c, i = grid_index(ids - 1, ncell, nside)
+    want = np.zeros((ncell ** 3, nside ** 3, 3), np.float32)
+    want[c, i] = pos
+    assert grid.cpu().numpy().tobytes() == want.tobytes()
+    with pytest.raises(mb.MinnowError):
+        ctx.regrid_insert(np.array([0], np.int64), np.zeros(3, np.float32), ncell, nside, grid)
+    # straight into the encoder
+    subcells, nfiles = 2, ncell ** 3
+    sc3, nb = subcells ** 3, nfiles * 3 * subcells ** 3
+    stride = 8 * nside ** 3 + 256
+    i64 = dict(dtype=torch.int64, device=dev)
+    mins, bits, offs = (torch.zeros(nb, **i64) for _ in range(3))
+    out_len = torch.zeros(3 * nfiles, **i64)
+    out = torch.zeros(3 * nfiles * stride, dtype=torch.uint8, device=dev)
+    desc_dev = torch.zeros(24 * 3 * nfiles, dtype=torch.uint8, device=dev)
+    ctx.minp_encode_vectors_dev(grid, nside, subcells, nfiles, True, L, dx, desc_dev, mins, bits, offs, out, stride, out_len)
+    ctx.sync()
+    px = mb.float_group_pixels(0.0, L, dx)
+    m, b, ln = mins.cpu().numpy(), bits.cpu().numpy(), out_len.cpu().numpy()
+    for f in range(nfiles):
+        om, ob, onb, packed, ostride, _ = orc.bench_minp_encode(want[f], nside, subcells, [0.0] * 3, [L] * 3, [px] * 3)
+        sl = slice(f * 3 * sc3, (f + 1) * 3 * sc3)
+        assert np.array_equal(m[sl], om) and np.array_equal(b[sl], ob)
+        for k in range(3):
+            w = b"".join(packed[t * ostride:t * ostride + onb[t]].tobytes() for t in range(k * sc3, (k + 1) * sc3))
+            assert out[(3 * f + k) * stride:(3 * f + k) * stride + ln[3 * f + k]].cpu().numpy().tobytes() == w
