@@ -150,6 +150,22 @@ MNW_API int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column
                                    int64_t n, int64_t *mins, int64_t *bits, int64_t *nbytes, uint8_t *out,
                                    int64_t out_col_stride);
 
+/* ---- text -> typed columns: the producer of minh.Writer.Block's input (scripts/text_to_minh.go:166-214) ------------------
+ * mnw_text_parse_block = the body of text.Reader.Block (go/text/text.go:181-200) for one block of bytes (HOST buf): split at
+ * '\n', uncomment, trim, fields (go/text/parse.go:16-79,175-211), then strconv.Atoi of the n_icols columns icols[] and
+ * float32(strconv.ParseFloat(.., 64)) of the n_fcols columns fcols[] (ascending column numbers, at most 64 each; :81-172).
+ * The parsed columns STAY ON THE DEVICE as row-major matrices [n_icols][nrows] int64 and [n_fcols][nrows] float32 --
+ * mnw_text_columns_dev hands out their device addresses (for mnw_encode_columns_dev: text to minh without the columns
+ * ever visiting the host), mnw_text_columns copies them to HOST arrays.  Decimal -> float64 is correctly rounded (exact
+ * fast path, else Eisel-Lemire with Go's own power-of-ten table); the rare fields that path cannot decide are returned
+ * in `fallback` as triples (row, index into fcols, byte offset | length << 40) with 0 written in their place, for the
+ * caller to convert with the host language's parser (*nfallback of them).  Where the reference panics (a field that is
+ * not a number, a line with another column count, a requested column beyond the data) the call fails. */
+MNW_API int mnw_text_parse_block(mnw_ctx *ctx, const char *buf, int64_t len, char sep, char comment, int n_icols,
+                                 const int *icols, int n_fcols, const int *fcols, int64_t *nrows, int64_t *nfallback);
+MNW_API int mnw_text_columns(mnw_ctx *ctx, int64_t *iout, float *fout, int64_t *fallback);
+MNW_API int mnw_text_columns_dev(mnw_ctx *ctx, const int64_t **icols_dev, const float **fcols_dev);
+
 /* ---- Lagrangian re-gridding: the producer of minp.Writer.Vectors' input ------------------------------------------------
  * vectorGrid.Insert over a batch (go/minp/snapshot/grid.go:206-211 with grid.Index :118-137, driven by xGrid / vGrid
  * :168-204): particle j with 1-based ID ids[j] goes to cell c, slot i of a Lagrangian lattice of ncell^3 cells x nside^3

@@ -89,6 +89,9 @@ SIGNATURES = {
     "mnw_decode_vec3_subcells_dev": (_int, [_p, _FD, _int, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _f32, _JT, _p]),
     "mnw_minp_encode_vectors_dev": (_int, [_p, _p, _i64, _i64, _i64, _int, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "mnw_minp_decode_vectors_dev": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _f32, _JT, _p]),
+    "mnw_text_parse_block": (_int, [_p, _p, _i64, C.c_char, C.c_char, _int, _p, _int, _p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "mnw_text_columns": (_int, [_p, _p, _p, _p]),
+    "mnw_text_columns_dev": (_int, [_p, C.POINTER(_p), C.POINTER(_p)]),
     "mnw_regrid_insert": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "mnw_regrid_insert_dev": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "mnw_boundary_coordinates": (_int, [_p, _p, _p, _p, _i64, _f32, _f32, _i64, _p, C.POINTER(_i64)]),
@@ -160,6 +163,17 @@ def float_group_pixels(lo, hi, dx):
 
 def jitter_hash32(seed, block, i):
     return int(load_library().mnw_jitter_hash32(seed, block, i))
+
+
+def _go_parse_float(tok):
+    """strconv.ParseFloat(tok, 64) for the fields mnw_text_parse_block leaves to the host: half-way cases, subnormals,
+    more than 19 digits on a rounding boundary (Python's float() is correctly rounded too), hexadecimal floats."""
+    t = tok.decode("ascii")
+    if "_" in t:
+        raise ValueError("strconv.ParseFloat: parsing %r: invalid syntax" % t)
+    if t.lower().lstrip("+-").startswith("0x"):
+        return float.fromhex(t)
+    return float(t)
 
 
 def _np(a, dtype):
@@ -424,6 +438,31 @@ class Context:
                 cols[i].desc = d
             ptrs[i] = x.data_ptr() if hasattr(x, "data_ptr") else int(x)
         self._check(self.lib.mnw_encode_columns_dev(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), out_col_stride))
+
+    # ---- text -> columns ------------------------------------------------------------------------
+    def text_parse_block(self, buf, icols, fcols, sep=b" ", comment=b"#"):
+        """text.Reader.Block for one block of bytes (go/text/text.go:181-200): -> (int64 [len(icols), rows],
+        float32 [len(fcols), rows]); icols / fcols: column numbers in any order.  The few floats the device leaves to
+        the host's parser (see the header) are converted here with Python's float()."""
+        buf = bytes(buf)
+        io_, fo_ = np.argsort(icols, kind="stable"), np.argsort(fcols, kind="stable")
+        ic = np.ascontiguousarray(np.asarray(icols, np.int32)[io_]) if len(icols) else np.zeros(0, np.int32)
+        fc = np.ascontiguousarray(np.asarray(fcols, np.int32)[fo_]) if len(fcols) else np.zeros(0, np.int32)
+        rows, nfb = _i64(0), _i64(0)
+        self._check(self.lib.mnw_text_parse_block(self.h, buf, len(buf), sep, comment, len(ic), _ptr(ic), len(fc), _ptr(fc),
+                                                  C.byref(rows), C.byref(nfb)))
+        iout, fout = np.zeros((len(ic), rows.value), np.int64), np.zeros((len(fc), rows.value), np.float32)
+        fb = np.zeros((nfb.value, 3), np.int64)
+        self._check(self.lib.mnw_text_columns(self.h, _ptr(iout), _ptr(fout), _ptr(fb)))
+        for r, c, where in fb:
+            off, ln = int(where) & ((1 << 40) - 1), int(where) >> 40
+            try:
+                fout[c, r] = np.float32(_go_parse_float(buf[off:off + ln]))
+            except ValueError as exc:                     # the reference panics with strconv's error
+                raise MinnowError(-4, "text: %s" % exc)
+        inv_i, inv_f = np.empty_like(io_), np.empty_like(fo_)
+        inv_i[io_], inv_f[fo_] = np.arange(len(io_)), np.arange(len(fo_))
+        return iout[inv_i], fout[inv_f]
 
     # ---- Lagrangian re-gridding ---------------------------------------------------------------
     def regrid_insert(self, ids, vec, ncell, nside, grid_dev, dev=False):

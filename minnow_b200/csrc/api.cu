@@ -35,6 +35,9 @@ int mnw_report_device_error(mnw_ctx *ctx, int err) {
     if (err == 2) return fail(ctx, MNW_ERR_CAPACITY, "packed output does not fit the output buffer");
     if (err == 3) return fail(ctx, MNW_ERR_ARG, "a coordinate lies outside [0, 2 L): the reference indexes outside its cell grid there");
     if (err == 4) return fail(ctx, MNW_ERR_ARG, "a particle ID is not valid for this NCell and NSide (grid.Index panics)");
+    if (err == 5) return fail(ctx, MNW_ERR_ARG, "text: a requested column does not exist in the data");
+    if (err == 6) return fail(ctx, MNW_ERR_FORMAT, "text: a field does not parse as a number (strconv.Atoi / ParseFloat error)");
+    if (err == 7) return fail(ctx, MNW_ERR_FORMAT, "text: a line has a different number of columns than the first one");
     return MNW_OK;
 }
 
@@ -484,7 +487,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
                       &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws,
-                      &ctx->bnd_idx, &ctx->bnd_flags, &ctx->bnd_work})
+                      &ctx->bnd_idx, &ctx->bnd_flags, &ctx->bnd_work, &ctx->txt_work, &ctx->txt_i, &ctx->txt_f, &ctx->txt_fb})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -663,6 +666,93 @@ int mnw_encode_float_group_gather(mnw_ctx *ctx, const mnw_float_desc *desc, cons
     if (rc) return rc;
     if (ncol < 0 || !starts) return fail(ctx, MNW_ERR_ARG, "gather: bad column length or no starts[]");
     return encode_group_host(ctx, KIND_F32, desc, col, 0, nblocks, starts, mins, bits, offsets, out, out_cap, out_len, idx, ncol);
+}
+
+// ---- text.Reader.Block (go/text/text.go:181-200, go/text/parse.go) ---------------------------------------------------------
+int mnw_text_parse_block(mnw_ctx *ctx, const char *buf, int64_t len, char sep, char comment, int n_icols, const int *icols,
+                         int n_fcols, const int *fcols, int64_t *nrows, int64_t *nfallback) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (len < 0 || n_icols < 0 || n_fcols < 0 || n_icols > 64 || n_fcols > 64) return fail(ctx, MNW_ERR_ARG, "mnw_text_parse_block: bad argument");
+    for (int k = 0; k + 1 < n_icols; k++) if (icols[k] >= icols[k + 1] || icols[k] < 0) return fail(ctx, MNW_ERR_ARG, "text: column numbers must ascend");
+    for (int k = 0; k + 1 < n_fcols; k++) if (fcols[k] >= fcols[k + 1] || fcols[k] < 0) return fail(ctx, MNW_ERR_ARG, "text: column numbers must ascend");
+    ctx->txt_rows = -1; ctx->txt_nfb = 0; ctx->txt_ni = n_icols; ctx->txt_nf = n_fcols;
+    const int64_t ntiles = (int64_t)text_tiles(len);
+    CU(ctx->in.reserve((size_t)len + 64));
+    CU(ctx->aux.reserve(8 * (2 * (size_t)ntiles + 8) + scan_scratch_bytes(ntiles) + 64));
+    { const int rcf = reset_flags(ctx); if (rcf) return rcf; }
+    unsigned char *d_buf = ctx->in.as<unsigned char>();
+    if (len > 0) CU(cudaMemcpyAsync(d_buf, buf, (size_t)len, cudaMemcpyHostToDevice, ctx->L.stream));
+    int64_t *tile_nl = ctx->aux.as<int64_t>(), *tile_off = tile_nl + ntiles, *d_tot = tile_off + ntiles;
+    CU(cudaMemsetAsync(d_tot, 0, 64, ctx->L.stream));
+    launch_text_count(ctx->L, d_buf, len, tile_nl);
+    if (ntiles > 0) {
+        const cudaError_t e = launch_scan_sizes(ctx->L, tile_nl, ntiles, 0, tile_off, d_tot, d_tot + 8);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "text scan: %s", cudaGetErrorString(e));
+    }
+    int64_t nl = 0;
+    CU(cudaMemcpyAsync(&nl, d_tot, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    const int64_t nlines = nl + 1;   // split(): n separators -> n + 1 lines (go/text/parse.go:23-35)
+    // per line: start, end, keep, row; then the totals and the column count
+    CU(ctx->txt_work.reserve(8 * (4 * (size_t)nlines + 16) + scan_scratch_bytes(nlines) + 64));
+    int64_t *line_start = ctx->txt_work.as<int64_t>(), *line_end = line_start + nlines + 1, *keep = line_end + nlines, *row_of = keep + nlines;
+    int64_t *d_rows = row_of + nlines;
+    int *d_ncols = (int *)(d_rows + 1), *d_fbcount = d_ncols + 1;
+    long long *d_errline = (long long *)(d_rows + 2);
+    void *scan2 = d_rows + 4;
+    CU(cudaMemsetAsync(d_rows, 0, 32, ctx->L.stream));
+    launch_text_starts(ctx->L, d_buf, len, tile_off, line_start);
+    launch_text_lines(ctx->L, d_buf, len, nlines, line_start, (unsigned char)sep, (unsigned char)comment, line_end, keep, d_ncols);
+    {
+        const cudaError_t e = launch_scan_sizes(ctx->L, keep, nlines, 0, row_of, d_rows, scan2);
+        if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "text scan: %s", cudaGetErrorString(e));
+    }
+    int64_t rows = 0;
+    CU(cudaMemcpyAsync(&rows, d_rows, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    const int fb_cap = 1 << 16;
+    CU(ctx->txt_i.reserve(8 * (size_t)n_icols * (size_t)rows + 64));
+    CU(ctx->txt_f.reserve(4 * (size_t)n_fcols * (size_t)rows + 64));
+    CU(ctx->txt_fb.reserve(24 * (size_t)fb_cap));
+    if (rows > 0 && n_icols + n_fcols > 0)
+        launch_text_parse(ctx->L, d_buf, nlines, line_start, line_end, keep, row_of, (unsigned char)sep, n_icols, icols, n_fcols, fcols,
+                          d_ncols, rows, ctx->txt_i.as<int64_t>(), ctx->txt_f.as<float>(), ctx->txt_fb.as<int64_t>(), fb_cap, d_fbcount,
+                          ctx->flags.as<int>() + FLAG_ERR, d_errline);
+    CU(cudaGetLastError());
+    int nfb = 0;
+    long long errline = 0;
+    CU(cudaMemcpyAsync(&nfb, d_fbcount, 4, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaMemcpyAsync(&errline, d_errline, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    int rc = check_flags(ctx);   // synchronises
+    if (rc) {
+        if (ctx->err.find("text:") != std::string::npos && rc == MNW_ERR_FORMAT) ctx->err += " (line " + std::to_string(errline + 1) + " of the block)";
+        return rc;
+    }
+    if (nfb > fb_cap) return fail(ctx, MNW_ERR_CAPACITY, "text: more than %d fields need the host's parser", fb_cap);
+    ctx->txt_rows = rows; ctx->txt_nfb = nfb;
+    if (nrows) *nrows = rows;
+    if (nfallback) *nfallback = nfb;
+    return MNW_OK;
+}
+
+int mnw_text_columns(mnw_ctx *ctx, int64_t *iout, float *fout, int64_t *fallback) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (ctx->txt_rows < 0) return fail(ctx, MNW_ERR_ARG, "no mnw_text_parse_block call on this context");
+    const size_t r = (size_t)ctx->txt_rows;
+    if (iout && ctx->txt_ni && r) CU(cudaMemcpyAsync(iout, ctx->txt_i.p, 8 * r * (size_t)ctx->txt_ni, cudaMemcpyDeviceToHost, ctx->L.stream));
+    if (fout && ctx->txt_nf && r) CU(cudaMemcpyAsync(fout, ctx->txt_f.p, 4 * r * (size_t)ctx->txt_nf, cudaMemcpyDeviceToHost, ctx->L.stream));
+    if (fallback && ctx->txt_nfb) CU(cudaMemcpyAsync(fallback, ctx->txt_fb.p, 24 * (size_t)ctx->txt_nfb, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    return MNW_OK;
+}
+
+int mnw_text_columns_dev(mnw_ctx *ctx, const int64_t **icols_dev, const float **fcols_dev) {
+    if (!ctx || ctx->txt_rows < 0) return ctx ? fail(ctx, MNW_ERR_ARG, "no mnw_text_parse_block call on this context") : MNW_ERR_ARG;
+    if (icols_dev) *icols_dev = ctx->txt_i.as<int64_t>();
+    if (fcols_dev) *fcols_dev = ctx->txt_f.as<float>();
+    return MNW_OK;
 }
 
 // ---- Lagrangian re-gridding (go/minp/snapshot/grid.go) -----------------------------------------------------------------

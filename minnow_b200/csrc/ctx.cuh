@@ -45,6 +45,10 @@ struct mnw_ctx {
     DevBuf bnd_idx, bnd_flags, bnd_work;
     std::vector<int64_t> bnd_starts;   // [cells^3 + 1], host
     int64_t bnd_n = -1, bnd_m = 0;
+    // text.Reader.Block: the parsed columns of the last mnw_text_parse_block call, resident on the device
+    DevBuf txt_work, txt_i, txt_f, txt_fb;
+    int64_t txt_rows = -1, txt_nfb = 0;
+    int txt_ni = 0, txt_nf = 0;
     void *comm = nullptr;    // ncclComm_t of the sharded path (comm_api.cu); null = a world of one
     int comm_ranks = 0, comm_rank = 0;
 };

@@ -89,6 +89,16 @@ size_t bnd_sort_scratch_bytes(int64_t m);
 cudaError_t launch_bnd_index(Launcher &L, const float *x, const float *y, const float *z, int64_t n, float l, float boundary,
                              int64_t cells, const int64_t *eoff, int64_t m, uint32_t *keys, int64_t *vals, uint32_t *keys2,
                              int64_t *vals2, void *scratch, int64_t *idx, int64_t *flags);
+// kernels_text.cu: text.Reader.Block on the device (go/text/text.go:181-200, go/text/parse.go)
+size_t text_tiles(int64_t len);
+void launch_text_count(Launcher &L, const unsigned char *buf, int64_t len, int64_t *tile_nl);
+void launch_text_starts(Launcher &L, const unsigned char *buf, int64_t len, const int64_t *tile_off, int64_t *line_start);
+void launch_text_lines(Launcher &L, const unsigned char *buf, int64_t len, int64_t nlines, const int64_t *line_start, unsigned char sep,
+                       unsigned char comm, int64_t *line_end, int64_t *keep, int *ncols);
+void launch_text_parse(Launcher &L, const unsigned char *buf, int64_t nlines, const int64_t *line_start, const int64_t *line_end,
+                       const int64_t *keep, const int64_t *row_of, unsigned char sep, int n_i, const int *icol, int n_f, const int *fcol,
+                       const int *ncols, int64_t nrows, int64_t *iout, float *fout, int64_t *fb_list, int fb_cap, int *fb_count,
+                       int *err, long long *err_line);
 // kernels_regrid.cu: vectorGrid.Insert over a batch (go/minp/snapshot/grid.go:118-137,206-211)
 void launch_regrid_insert(Launcher &L, const int64_t *ids, const float *vec, int64_t n, int64_t ncell, int64_t nside, float *grid, int *err);
 void launch_vec3_params(Launcher &L, const uint32_t *keys, int64_t nfiles, float dx, FloatParams *tab, void *desc_out, int *skip,
