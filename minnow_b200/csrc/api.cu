@@ -996,9 +996,10 @@ static int encode_vec3_core(mnw_ctx *ctx, const FloatParams *tab, const std::vec
             CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
             coop_ws = ctx->coop_ws.p;
         }
+        bool ran_pipe = false;
         const cudaError_t e = launch_fused_vec3(ctx->L, W, ctx->descs.as<BlockDesc>(), tab, desc_per_file, aos, (int)nfile, (int)subcells, nfiles,
                                                 ctx->stats.as<BlockStat>(), mins, bits, offsets, out_len, out, out_axis_stride,
-                                                pipe_ok, coop_ws);
+                                                pipe_ok, coop_ws, &ran_pipe);
         if (e != cudaSuccess && e != cudaErrorNotSupported) return fail(ctx, MNW_ERR_CUDA, "fused vec3 encode: %s", cudaGetErrorString(e));
         if (e == cudaErrorNotSupported) {   // no fused kernel for this shape on this device after all: the generic kernels
             ctx->last_path = 0;
@@ -1011,10 +1012,13 @@ static int encode_vec3_core(mnw_ctx *ctx, const FloatParams *tab, const std::vec
         // blocks wider than 16 bits: packed from global memory with the fused kernel's (min, bits, offset)
         launch_pack_list(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, W.repack_list, W.repack_count,
                          out, out_axis_stride, out_axis_stride, d_flags + FLAG_ERR);
-        // blocks that need the exact sequential periodicMin: the whole call again, generically
-        launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
-                              ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
-                              out_axis_stride, out_axis_stride, W.abort_flag);
+        // The generic kernels, gated on the abort flag, redo the whole call when (a) k_fused_vec3 met a block that needs
+        // the exact sequential periodicMin, or (b) k_vec3_params found derived parameters outside the fused kernels'
+        // domain.  k_pipe_vec3 with parameters the host has checked raises neither: it resolves such blocks itself.
+        if (!(fp && ran_pipe))
+            launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh,
+                                  ctx->slow.as<int64_t>(), d_flags, d_flags + FLAG_ERR, mins, bits, offsets, out_len, out,
+                                  out_axis_stride, out_axis_stride, W.abort_flag);
         CU(cudaGetLastError());
         return MNW_OK;
     }

@@ -180,7 +180,7 @@ __device__ __forceinline__ bool finalize_block(const BlockDesc &d, BlockStat &s,
     } else if (d.kind == KIND_I64 || !(d.flags & F_PERIODIC)) {
         s.min = s.qmin;
         finish_stat(s, d.n, (unsigned long long)s.qmax - (unsigned long long)s.qmin, err);
-    } else if (s.oob) {
+    } else if (s.oob & 1u) {   // (bit 1 of oob only says that some thread took the checked quantiser: k_group_fused)
         s.slow = 1;
         return true;
     } else {

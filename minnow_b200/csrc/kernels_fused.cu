@@ -833,7 +833,8 @@ cudaError_t launch_pipe_vec3_coop(Launcher &L, FusedArgs A, void *ws, int nsub);
 cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *descs, const FloatParams *tab, int tab_per_file,
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
                               int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
-                              int64_t out_axis_stride, bool pipe_ok, void *coop_ws) {
+                              int64_t out_axis_stride, bool pipe_ok, void *coop_ws, bool *ran_pipe) {
+    if (ran_pipe) *ran_pipe = false;
     FusedArgs A = {};
     A.descs = descs;
     A.aos = aos; A.tab = tab; A.tab_per_file = tab_per_file; A.nfile = nfile; A.subcells = subcells;
@@ -861,10 +862,10 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *
                 static const bool coop = !(getenv("MNW_PIPE") && !strcmp(getenv("MNW_PIPE"), "cluster"));
                 if (pipe_ok && coop && coop_ws) {
                     const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 64);
-                    if (e == cudaSuccess) return e;
+                    if (e == cudaSuccess) { if (ran_pipe) *ran_pipe = true; return e; }
                     (void)cudaGetLastError();
                 }
-                if (pipe_ok) return launch_pipe_vec3(L, A);
+                if (pipe_ok) { if (ran_pipe) *ran_pipe = true; return launch_pipe_vec3(L, A); }
                 return launch_fused_vec3_t<64, 8, 384, 4, 1, true>(L, A);
             }
             if (variant == 0) {
@@ -882,7 +883,7 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *
             static const bool pipe32 = !(getenv("MNW_PIPE") && !strcmp(getenv("MNW_PIPE"), "cluster"));
             if (pipe_ok && pipe32 && coop_ws) {
                 const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 32);
-                if (e == cudaSuccess) return e;
+                if (e == cudaSuccess) { if (ran_pipe) *ran_pipe = true; return e; }
                 (void)cudaGetLastError();
             }
             return launch_fused_vec3_t<32, 1, 768, 4, 1, false>(L, A);
@@ -890,7 +891,7 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *
         case 128: {   // 64 CTAs per unit: the cooperative pipeline or nothing (the caller then takes the generic kernels)
             if (pipe_ok && coop_ws) {
                 const cudaError_t e = launch_pipe_vec3_coop(L, A, coop_ws, 128);
-                if (e == cudaSuccess) return e;
+                if (e == cudaSuccess) { if (ran_pipe) *ran_pipe = true; return e; }
                 (void)cudaGetLastError();
             }
             return cudaErrorNotSupported;

@@ -48,7 +48,8 @@ struct GroupFusedArgs {
     int wave_tiles;            // tiles per wave: a whole number of blocks
     int sup;                   // tiles per ticket
     int lag;                   // the pack pass of wave g follows the statistics pass of wave g + lag
-    int dry;                   // diagnostics: 1 = consumers skip the pack work, 2 = and the statistics work (ring + TMA only)
+    int dry;                   // diagnostics: 1 = consumers skip the pack work, 2 = and the statistics work (ring + TMA only),
+                               // 3 = full work without the pack pass's "sure" shortcut
 };
 
 constexpr int GF_CW = 4;                          // consumer warps = quarters of a tile
@@ -68,7 +69,9 @@ struct __align__(16) GProto {
     unsigned P, C;
     int flags, fast;     // fast: the unchecked quantiser applies
     long long pmin, min;
-    int slow, do_bound, bits, pad;
+    int slow, do_bound, bits;
+    int sure;            // pack pass: every value of the block passed the unchecked quantiser in the statistics pass and
+                         // no pixel index needs the + pixels of bound(): v = bits + constant, no range test
 };
 constexpr int GF_NP = 8;   // GProto ring: more than any ring of job slots
 
@@ -157,9 +160,9 @@ __device__ __forceinline__ void pack_group_warp(const unsigned (&v)[32], unsigne
 struct WarpAcc {
     unsigned wmin, wmax, qmin, qmax;
     long long mn, mx;
-    bool oob;
+    bool oob, fell;   // fell: some value went through the checked quantiser
     int n;   // tile quarters accumulated
-    __device__ __forceinline__ void reset() { wmin = ~0u; wmax = 0u; qmin = ~0u; qmax = 0u; mn = LLONG_MAX; mx = LLONG_MIN; oob = false; n = 0; }
+    __device__ __forceinline__ void reset() { wmin = ~0u; wmax = 0u; qmin = ~0u; qmax = 0u; mn = LLONG_MAX; mx = LLONG_MIN; oob = false; fell = false; n = 0; }
 };
 
 }  // namespace
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                     proto_dirty = true;
                     proto.low = gd->low; proto.high = gd->high; proto.dx = gd->dx; proto.hi_clamp = gd->hi_clamp;
                     proto.P = (unsigned)gd->pixels; proto.flags = gd->flags;
-                    proto.C = 0; proto.fast = 0; proto.bits = 0; proto.do_bound = 0; proto.slow = 0;
+                    proto.C = 0; proto.fast = 0; proto.bits = 0; proto.do_bound = 0; proto.slow = 0; proto.sure = 0;
                     if (cur_kind == KIND_F32) {
                         const QuantP qp = job_quant(proto);
                         if (!pack) {
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                         const long long nbytes = __ldcg(&gs->nbytes);
                         cur_off = __ldcg(&gs->out_off);
                         if (cur_kind == KIND_F32) proto.fast = proto.fast && !proto.slow && proto.do_bound;
+                        proto.sure = A.dry != 3 && proto.fast && !(__ldcg(&gs->oob) & 2u) && __ldcg(&gs->qmin) >= proto.pmin;
                         if (proto.bits >= 1 && proto.bits <= 32 && cur_off + nbytes > A.chain_cap) {   // never write past the caller's buffer
                             atomicExch(A.err, 2);
                             proto.bits = 0;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
         const long long b = j.b;
         if (A.dry == 2 && (kind == J_STAT_F32 || kind == J_STAT_I64)) {
             acc.n++;
-        } else if (A.dry && (kind == J_PACK_F32 || kind == J_PACK_I64)) {
+        } else if ((A.dry == 1 || A.dry == 2) && (kind == J_PACK_F32 || kind == J_PACK_I64)) {
         } else if (kind == J_STAT_F32) {
             const QuantP qp = job_quant(j);
             const unsigned C = j.C;
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                     acc.wmin = min(acc.wmin, fwmin); acc.wmax = max(acc.wmax, fwmax);
                     acc.qmin = min(acc.qmin, bmin - FQ_MAGIC); acc.qmax = max(acc.qmax, bmax - FQ_MAGIC);
                 } else {   // log10 columns, pixels > 2^22, or (rare) a value the unchecked quantiser does not vouch for: checked
+                    acc.fell = true;
 #pragma unroll 1
                     for (int i = 0; i < 8; i++) {
                         const float4 vv = s4[lane + 32 * i];   // (read again: no dynamic indexing of v[])
@@ -424,6 +429,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                 }
             } else {   // partial tile: element-wise from global memory
                 const float *gp = (const float *)jb.src + warp * 1024;
+                acc.fell = true;
 #pragma unroll 1
                 for (int el = lane; el < wcount; el += 32) {
                     const unsigned q = quant_elem(__ldcg(gp + el), qp, acc.oob, nullptr);
@@ -487,6 +493,27 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                     const unsigned dsub = 0u - FQ_MAGIC - (unsigned)pmin, cadd = (unsigned)(pmin - mn);
                     // step i: the warp reads the four 128-byte rows 4i .. 4i+3 of its quarter and stages their values into
                     // the same rows (the chunk rotation stays within a row): in place, one __syncwarp per step
+                    if (j.sure) {   // the statistics pass vouches for every value and bound() adds nothing: v = bits + constant
+                        const unsigned cst = dsub + cadd;
+#pragma unroll 2
+                        for (int i = 0; i < 8; i++) {
+                            const float4 xx = s4[lane + 32 * i];
+                            __syncwarp();
+                            float x0 = xx.x, x1 = xx.y, x2 = xx.z, x3 = xx.w;
+                            if (islog) { x0 = go_log10_f32(x0); x1 = go_log10_f32(x1); x2 = go_log10_f32(x2); x3 = go_log10_f32(x3); }
+                            if (clamp) {
+                                x0 = x0 < qp.low ? qp.low : x0; x0 = x0 >= qp.high ? qp.hi_clamp : x0;
+                                x1 = x1 < qp.low ? qp.low : x1; x1 = x1 >= qp.high ? qp.hi_clamp : x1;
+                                x2 = x2 < qp.low ? qp.low : x2; x2 = x2 >= qp.high ? qp.hi_clamp : x2;
+                                x3 = x3 < qp.low ? qp.low : x3; x3 = x3 >= qp.high ? qp.hi_clamp : x3;
+                            }
+                            unsigned b0, b1, b2, b3;
+                            f2_bits(quantize2(f2_pack(x0, x1), LOW2, RCP2, NDX2), b0, b1);
+                            f2_bits(quantize2(f2_pack(x2, x3), LOW2, RCP2, NDX2), b2, b3);
+                            const int iv = lane + 32 * i, L = iv >> 3;
+                            *(uint4 *)&region[(L << 5) + (((iv & 7) ^ (L & 7)) << 2)] = make_uint4(b0 + cst, b1 + cst, b2 + cst, b3 + cst);
+                        }
+                    } else
 #pragma unroll 2
                     for (int i = 0; i < 8; i++) {
                         const float4 xx = s4[lane + 32 * i];
@@ -568,14 +595,14 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
             if (kind == J_STAT_F32) {
                 const unsigned wmin = __reduce_min_sync(0xffffffffu, acc.wmin), wmax = __reduce_max_sync(0xffffffffu, acc.wmax);
                 const unsigned qmin = __reduce_min_sync(0xffffffffu, acc.qmin), qmax = __reduce_max_sync(0xffffffffu, acc.qmax);
-                const unsigned ob = __any_sync(0xffffffffu, acc.oob);
+                const unsigned ob = (__any_sync(0xffffffffu, acc.oob) ? 1u : 0u) | (__any_sync(0xffffffffu, acc.fell) ? 2u : 0u);
                 if (lane == 0) {
                     pr0 = pr1 = 0; pr2 = pr3 = 0; pr4 = 0;
                     if (wmin <= wmax) {
                         pr0 = atomicMin(&sb->wmin, (unsigned long long)wmin); pr1 = atomicMax(&sb->wmax, (unsigned long long)wmax);
                         pr2 = atomicMin(&sb->qmin, (long long)qmin); pr3 = atomicMax(&sb->qmax, (long long)qmax);
                     }
-                    if (ob) pr4 = atomicOr(&sb->oob, 1u);
+                    if (ob) pr4 = atomicOr(&sb->oob, ob);
                 }
             } else {
                 const long long mn = warp_min_ll(acc.mn), mx = warp_max_ll(acc.mx);

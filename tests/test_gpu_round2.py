@@ -746,7 +746,7 @@ def test_text_to_minh_block_without_leaving_the_device(ctx, orc):
     mnw_encode_columns_dev): the bytes are those of the oracle on the host-parsed columns"""
     import ctypes as C
     rng = np.random.default_rng(14)
-    rows = 4096 * 3 + 77
+    rows = 4096 * 3 + 76
     ids = rng.permutation(rows).astype(np.int64) + 10 ** 9
     xs = (rng.random(rows) * 125.0).astype(np.float32)
     ms = np.power(10.0, rng.uniform(10, 15, rows))
