@@ -394,6 +394,9 @@ MNW_API int mnw_selftest_fastdiv(mnw_ctx *ctx, const mnw_float_desc *desc, uint3
  * an exact fallback (device_math.cuh go_log10_f32).  This compares it with the restated Go algorithm on every float32
  * bit pattern in [first_bits, first_bits + count) and reports how many results differ (must be 0). */
 MNW_API int mnw_selftest_log10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64_t *mismatches);
+/* The same for the read side's float32(pow(10, float64 x)): exp2 form with an exact fallback against the restated Go
+ * math.Pow, on every float32 bit pattern in the range (must be 0). */
+MNW_API int mnw_selftest_pow10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64_t *mismatches);
 
 /* out[i] = float32(math.Pow(10, float64(x[i]))): the read side of a minh Log column that is stored raw (Float32Group),
  * go/minh/minh.go:315-319.  FloatGroup Log columns get it inside mnw_decode_float_blocks (desc.log10).  HOST pointers.

@@ -120,6 +120,7 @@ SIGNATURES = {
     "mnw_profile": (_int, [_p, _int]),
     "mnw_profile_summary": (_int, [_p, C.c_char_p, _i64]),
     "mnw_selftest_log10": (_int, [_p, C.c_uint32, _u64, C.POINTER(_u64)]),
+    "mnw_selftest_pow10": (_int, [_p, C.c_uint32, _u64, C.POINTER(_u64)]),
     "mnw_pow10_f32": (_int, [_p, _p, _i64, _p]),
     "mnw_last_path": (_int, [_p]),
     "mnw_force_generic": (None, [_p, _int]),
@@ -326,6 +327,11 @@ class Context:
         """-> mismatches of go_log10_f32 against the restated Go math.Log10 over float32 bit patterns"""
         bad = _u64(0)
         self._check(self.lib.mnw_selftest_log10(self.h, first_bits, count, C.byref(bad)))
+        return bad.value
+
+    def selftest_pow10(self, first_bits=0, count=1 << 32):
+        bad = _u64(0)
+        self._check(self.lib.mnw_selftest_pow10(self.h, first_bits, count, C.byref(bad)))
         return bad.value
 
     def pow10_f32(self, x):

@@ -1314,6 +1314,20 @@ int mnw_selftest_log10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64
     return MNW_OK;
 }
 
+int mnw_selftest_pow10(mnw_ctx *ctx, uint32_t first_bits, uint64_t count, uint64_t *mismatches) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if ((uint64_t)first_bits + count > (1ULL << 32)) return fail(ctx, MNW_ERR_ARG, "bit pattern range exceeds 2^32");
+    CU(ctx->meta.reserve(64));
+    launch_selftest_log10(ctx->L, first_bits, count, ctx->meta.as<unsigned long long>(), 1);
+    CU(cudaGetLastError());
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, ctx->meta.p, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CU(cudaStreamSynchronize(ctx->L.stream));
+    if (mismatches) *mismatches = h;
+    return MNW_OK;
+}
+
 int mnw_pow10_f32(mnw_ctx *ctx, const float *x, int64_t n, float *out) {
     if (!ctx) return MNW_ERR_ARG;
     (void)cudaSetDevice(ctx->device);

@@ -213,6 +213,37 @@ MNW_D float go_log10_f32(float x) {
     return __double2float_rn(go_log10((double)x));
 }
 
+// float32(math.Pow(10, float64(x))), go/minh/minh.go:315-319, at a fraction of the FP64 work of go_pow10:
+// 10^x = 2^k 2^f with k + f = x log2(10), |f| <= 1/2, and 2^f = exp(f ln 2) by a degree-13 Taylor polynomial (relative
+// error < 2^-48 including the 2^-53-relative error of the product x log2(10), |x| < 50).  go_pow10's own relative error is
+// a few units in 2^-53 (one exp, one log and at most six multiplications of the square-and-multiply loop).  The float32
+// rounding of both is therefore the same number unless a rounding boundary lies within 2^-40 (relative) of the value: then,
+// and outside the range where the result is a normal float32 well inside its range, go_pow10 decides.
+MNW_D float go_pow10_f32(float x) {
+    if (x > -37.0f && x < 38.0f) {
+        const double y = (double)x * 3.3219280948873622;   // log2(10)
+        const double k = rint(y), f = (y - k) * 0.69314718055994529;   // f ln 2, |.| <= 0.3466
+        double p = 1.6059043836821613e-10;                 // 1/13!
+        p = fma(p, f, 2.08767569878681e-09);               // 1/12!
+        p = fma(p, f, 2.505210838544172e-08);
+        p = fma(p, f, 2.755731922398589e-07);
+        p = fma(p, f, 2.7557319223985893e-06);
+        p = fma(p, f, 2.48015873015873e-05);
+        p = fma(p, f, 0.0001984126984126984);
+        p = fma(p, f, 0.001388888888888889);
+        p = fma(p, f, 0.008333333333333333);
+        p = fma(p, f, 0.041666666666666664);
+        p = fma(p, f, 0.16666666666666666);
+        p = fma(p, f, 0.5);
+        p = fma(p, f, 1.0);
+        p = fma(p, f, 1.0);
+        const double v = __longlong_as_double(__double_as_longlong(p) + (long long)k * (1LL << 52));   // p 2^k (p in [0.7, 1.42])
+        const float lo = __double2float_rn(v * (1.0 - 0x1p-40)), hi = __double2float_rn(v * (1.0 + 0x1p-40));
+        if (lo == hi) return lo;
+    }
+    return __double2float_rn(go_pow10((double)x));
+}
+
 // minh processFloatGroup, go/minh/minh.go:141-149 (hi_clamp = Nextafter32(High, -Inf)).
 MNW_D float minh_pre(float v, bool is_log, bool clamp, float low, float high, float hi_clamp) {
     if (is_log) v = go_log10_f32(v);

@@ -48,7 +48,7 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
 void launch_selftest_fastdiv(Launcher &L, const FloatParamsHost &fp, unsigned long long first,
                              unsigned long long count, unsigned long long *d_out2);
 
-void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out);
+void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out, int pow10 = 0);
 void launch_pow10_f32(Launcher &L, const float *x, long long n, float *out);
 
 }  // namespace mnw

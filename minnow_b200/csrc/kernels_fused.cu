@@ -742,28 +742,29 @@ void launch_selftest_fastdiv(Launcher &L, const FloatParamsHost &fp, unsigned lo
 }
 
 // go_log10_f32 (table + series, exact fallback) against float32(go_log10(float64 x)) over float bit patterns
-__global__ void k_selftest_log10(unsigned long long first, unsigned long long count, unsigned long long *mismatches) {
+__global__ void k_selftest_log10(unsigned long long first, unsigned long long count, unsigned long long *mismatches, int pow10) {
     unsigned long long bad = 0;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned)(first + i));
-        const unsigned a = __float_as_uint(go_log10_f32(x)), b = __float_as_uint(__double2float_rn(go_log10((double)x)));
+        const unsigned a = __float_as_uint(pow10 ? go_pow10_f32(x) : go_log10_f32(x));
+        const unsigned b = __float_as_uint(__double2float_rn(pow10 ? go_pow10((double)x) : go_log10((double)x)));
         if (a != b && !((a & 0x7fffffffu) > 0x7f800000u && (b & 0x7fffffffu) > 0x7f800000u)) bad++;   // (any NaN equals any NaN)
     }
     for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
-void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out) {
+void launch_selftest_log10(Launcher &L, unsigned long long first, unsigned long long count, unsigned long long *d_out, int pow10) {
     cudaMemsetAsync(d_out, 0, 8, L.stream);
     if (count == 0) return;
-    k_selftest_log10<<<148 * 8, 256, 0, L.stream>>>(first, count, d_out);
+    k_selftest_log10<<<148 * 8, 256, 0, L.stream>>>(first, count, d_out, pow10);
     L.count++;
 }
 
 // float32(math.Pow(10, float64(x))) of a raw float32 column (minh Log columns stored as Float32Group, go/minh/minh.go:315-319)
 __global__ void k_pow10_f32(const float *x, long long n, float *out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = __double2float_rn(go_pow10((double)x[i]));
+        out[i] = go_pow10_f32(x[i]);
 }
 void launch_pow10_f32(Launcher &L, const float *x, long long n, float *out) {
     if (n == 0) return;

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
         float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));  // go/group.go:308
         float o = __fadd_rn(__fmul_rn(dx, t), low);
         if (A.mode == 1) {
-            if (islog) o = __double2float_rn(go_pow10((double)o));   // minh Log column, go/minh/minh.go:315-319
+            if (islog) o = go_pow10_f32(o);   // minh Log column, go/minh/minh.go:315-319
             ((float *)A.out)[j * A.n + i] = o;
         } else {
             if (A.wrap_L > 0.0f) {                               // go/minp/minp.go:195-203
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
                     t = __fadd_rn((float)q, 0.5f);
                 }
                 o[c] = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);                            // :308
-                if (islog) o[c] = __double2float_rn(go_pow10((double)o[c]));             // go/minh/minh.go:315-319
+                if (islog) o[c] = go_pow10_f32(o[c]);             // go/minh/minh.go:315-319
             }
             if (vec_ok && e4 + 4 <= count) {
                 __stcs((float4 *)(outp + e4), make_float4(o[0], o[1], o[2], o[3]));
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
             if (A.jmode == 1) u = (double)(jitter_hash_keyed(key, (uint32_t)i) >> 8) * 0x1p-24;
             const float t = __double2float_rn(__dadd_rn(__ll2double_rn(q), u));
             float o = __fadd_rn(__fmul_rn(fp.dx, t), fp.low);
-            if (islog) o = __double2float_rn(go_pow10((double)o));
+            if (islog) o = go_pow10_f32(o);
             outp[el] = o;
         }
     }

@@ -643,7 +643,6 @@ static cudaError_t launch_group_fused_t(Launcher &L, GroupFusedArgs &A, int64_t 
     // tuning knobs: MNW_GROUP_SUP tiles per ticket, MNW_GROUP_WAVE_MB megabytes of input per wave
     static const int sup_knob = getenv("MNW_GROUP_SUP") ? atoi(getenv("MNW_GROUP_SUP")) : 0;
     static const int wave_knob = getenv("MNW_GROUP_WAVE_MB") ? atoi(getenv("MNW_GROUP_WAVE_MB")) : 0;
-    A.sup = sup_knob > 0 ? sup_knob : 4;
     static const int dry_knob = getenv("MNW_GROUP_DRY") ? atoi(getenv("MNW_GROUP_DRY")) : 0;
     A.dry = dry_knob;
     // a wave is a whole number of blocks: every statistics tile of a block then has a smaller ticket than any of the
@@ -653,6 +652,11 @@ static cudaError_t launch_group_fused_t(Launcher &L, GroupFusedArgs &A, int64_t 
     wave = (wave + tpb - 1) / tpb * tpb;
     if (wave > sh.total_tiles) wave = sh.total_tiles;
     A.wave_tiles = (int)wave;
+    // tiles per ticket: 4 amortise the ticket and the flush for a large batch; a small batch (fewer tickets than
+    // co-resident CTAs) is spread over more CTAs instead (measured on 16 blocks of 2^16: 0.052 -> 0.043 ms)
+    A.sup = 4;
+    while (A.sup > 1 && wave / A.sup < dc.a) A.sup >>= 1;
+    if (sup_knob > 0) A.sup = sup_knob;
     const long long nsw = (wave + A.sup - 1) / A.sup, nwaves = (sh.total_tiles + wave - 1) / wave;
     static const int lag_knob = getenv("MNW_GROUP_LAG") ? atoi(getenv("MNW_GROUP_LAG")) : 0;
     A.lag = lag_knob > 0 ? lag_knob : 1;

@@ -122,6 +122,11 @@ def test_log10_float32_fast_form_is_exact(ctx):
     assert ctx.selftest_log10(0, 1 << 32) == 0
 
 
+def test_pow10_float32_fast_form_is_exact(ctx):
+    """go_pow10_f32 (exp2 form + exact fallback) == float32(restated Go math.Pow(10, x)) on EVERY float32 bit pattern"""
+    assert ctx.selftest_pow10(0, 1 << 32) == 0
+
+
 def test_log10_float32_against_numpy(ctx, orc):
     """and the restated Go math.Log10 itself is a correct log10: within one float32 ulp of numpy's on random inputs
     (a tolerance test, as the reference's own is: go/minh/minh_test.go:110-113)"""
