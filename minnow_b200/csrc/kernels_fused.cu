@@ -454,6 +454,7 @@ struct DecVec3Args {
     int nfile, subcells;
     long long sc3, nslabs;
     float *out;
+    int sync_mode;          // tuning knob MNW_DEC_SYNC: 1 = CTA barrier per slab, 0 = per-stage empty barriers
 };
 
 // What a CTA needs to know about one axis block of the slab it is about to decode
@@ -525,11 +526,12 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
     constexpr int STAGE_BYTES = SLAB * 3 + 32;   // up to 24 bits per value, + alignment slack
     static_assert(NT % R4 == 0, "threads tile the rows exactly");
     extern __shared__ __align__(128) unsigned char dsm[];   // [2][3][STAGE_BYTES]
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar[2], s_empty[2];
     __shared__ SlabAxis s_hdr[2][3];
     __shared__ SlabInfo s_info[2];
 
-    const int tid = threadIdx.x;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned S = (unsigned)A.subcells, nfile = (unsigned)A.nfile, sc3 = (unsigned)A.sc3;
     const unsigned row4 = 3u * nfile / 4u, plane4 = row4 * nfile;
     const int col4 = tid % R4, rsub = tid / R4, a0 = col4 % 3;
@@ -540,23 +542,24 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_empty[0])), "r"(NW));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_empty[1])), "r"(NW));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // producer: describe slab g and start the copies of its packed bytes into stage st
+    // producer (one whole warp calls it; lane k < 3 describes axis k, so the dependent global loads of the three axes
+    // overlap): describe slab g and start the copies of its packed bytes into stage st
     auto issue = [&](int st, unsigned g) {
         const unsigned unit = g / SLABS, slab = g % SLABS;
         const unsigned f = unit / sc3, sc = unit % sc3;
-        const FloatParams *tab = A.tab + (A.tab_per_file ? 3 * f : 0);
-        unsigned bytes[3] = {0, 0, 0};
-        const uint8_t *src[3] = {nullptr, nullptr, nullptr};
-        unsigned total = 0;
-        int all_fast = 1;
-#pragma unroll 1
-        for (int k = 0; k < 3; k++) {
+        unsigned nbytes = 0;
+        const uint8_t *src = nullptr;
+        int fast = 1;
+        if (lane < 3) {
+            const int k = lane;
             const long long b = ((long long)f * 3 + k) * sc3 + sc;
-            const FloatParams fp = tab[k];
+            const FloatParams fp = A.tab[(A.tab_per_file ? 3 * f : 0) + k];
             SlabAxis h;
             h.mn = A.mins[b]; h.bits = (int)A.bits[b]; h.pixels = fp.pixels; h.low = fp.low; h.dx = fp.dx;
             h.periodic = (fp.flags & F_PERIODIC) ? 1 : 0;
@@ -570,41 +573,58 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
             if (h.fast && h.bits > 0) {
                 const uint8_t *p = h.gsrc + (((long long)slab * SLAB * h.bits) >> 3);
                 const unsigned a16 = (unsigned)((uintptr_t)p & 15);
-                src[k] = p - a16;
-                bytes[k] = (a16 + (unsigned)(SLAB * h.bits / 8) + 15u) & ~15u;
+                src = p - a16;
+                nbytes = (a16 + (unsigned)(SLAB * h.bits / 8) + 15u) & ~15u;
                 h.shift = 8 * (int)a16;
-                total += bytes[k];
             }
-            all_fast &= h.fast;
+            fast = h.fast;
             s_hdr[st][k] = h;
         }
-        SlabInfo info;
-        const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
-        const unsigned row0 = slab * ROWS;   // first sub-cell row of the slab
-        info.out4 = (long long)f * ((long long)plane4 * nfile) +
-                    (long long)(3u * ix0 / 4u) + (long long)(iy0 + row0 % NSUB) * row4 + (long long)(iz0 + row0 / NSUB) * plane4;
-        info.e0 = slab * SLAB;
-        info.fast = all_fast;
-        s_info[st] = info;
+        const unsigned total = nbytes + __shfl_down_sync(0xffffffffu, nbytes, 1) + __shfl_down_sync(0xffffffffu, nbytes, 2);   // (lane 0's)
+        const int all_fast = __all_sync(0xffffffffu, fast);
         const unsigned bar = smem_u32(&s_bar[st]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            if (bytes[k])
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(dsm + (st * 3 + k) * STAGE_BYTES)), "l"(src[k]), "r"(bytes[k]), "r"(bar) : "memory");
+        if (lane == 0) {
+            SlabInfo info;
+            const unsigned ix0 = NSUB * (sc % S), iy0 = NSUB * ((sc / S) % S), iz0 = NSUB * (sc / (S * S));
+            const unsigned row0 = slab * ROWS;   // first sub-cell row of the slab
+            info.out4 = (long long)f * ((long long)plane4 * nfile) +
+                        (long long)(3u * ix0 / 4u) + (long long)(iy0 + row0 % NSUB) * row4 + (long long)(iz0 + row0 / NSUB) * plane4;
+            info.e0 = slab * SLAB;
+            info.fast = all_fast;
+            s_info[st] = info;
+        }
+        __syncwarp();   // the headers of lanes 1 and 2 are ordered before lane 0's arrival, which publishes them
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+        __syncwarp();
+        if (nbytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dsm + (st * 3 + lane) * STAGE_BYTES)), "l"(src), "r"(nbytes), "r"(bar) : "memory");
     };
 
     const unsigned nslabs = (unsigned)A.nslabs;
-    if (tid == 0 && blockIdx.x < nslabs) issue(0, blockIdx.x);
+    if (warp == 0 && blockIdx.x < nslabs) issue(0, blockIdx.x);
     __syncthreads();
 
     // rows of the slab handled by this thread are rl = rsub + RPP*i: offset of row rl from the slab's row 0
     // (a slab is one z-plane of the sub-cell when NSUB = 64, several planes otherwise)
+    // No CTA-wide barrier in the loop: a stage is handed back through s_empty (one arrival per warp), and the warp whose
+    // turn it is to fetch the next slab (a different one every iteration: describing a slab costs a few dependent global
+    // loads) is the only one that waits for the others -- for the iteration BEFORE the one they are working on.
     int it = 0;
     for (unsigned g = blockIdx.x; g < nslabs; g += gridDim.x, it++) {
         const int st = it & 1;
-        if (tid == 0 && g + gridDim.x < nslabs) issue(st ^ 1, g + gridDim.x);
+        if (A.sync_mode) {
+            if (warp == 0 && g + gridDim.x < nslabs) issue(st ^ 1, g + gridDim.x);
+        } else if (g + gridDim.x < nslabs && warp == it % NW) {
+            if (it >= 1) {   // stage st ^ 1 was read in iteration it - 1: phase (it - 1) / 2 of its empty barrier
+                const unsigned bar = smem_u32(&s_empty[st ^ 1]), parity = ((it - 1) >> 1) & 1;
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            }
+            issue(st ^ 1, g + gridDim.x);
+        }
         {   // wait for this slab's bytes
             const unsigned bar = smem_u32(&s_bar[st]), parity = (it >> 1) & 1;
             unsigned done = 0;
@@ -668,6 +688,7 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
                     } else {
                         t = __fadd_rn((float)q, 0.5f);   // q < 2^23: exact
                     }
+                    // (scalar on purpose: the packed f32x2 forms cost as many register moves as they save)
                     float x = __fadd_rn(__fmul_rn(dx[j], t), low[j]);
                     if constexpr (WRAP == 1) {                                       // go/minp/minp.go:195-203
                         const float xp = __fadd_rn(x, A.wrap_L), xm = __fsub_rn(x, A.wrap_L);
@@ -691,7 +712,12 @@ __global__ void __launch_bounds__(NT, MINB) k_decode_vec3(const DecVec3Args A) {
                 __stcs(pbase + ((unsigned)(rl / NSUB) * plane4 + (unsigned)(rl % NSUB) * row4), make_float4(o[0], o[1], o[2], o[3]));
             }
         }
-        __syncthreads();   // stage st and its header may be refilled from the next iteration on
+        if (A.sync_mode) {
+            __syncthreads();
+        } else {
+            __syncwarp();      // stage st and its header may be refilled once every warp has said so
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
+        }
     }
 }
 
@@ -964,6 +990,8 @@ cudaError_t launch_fused_decode_vec3(Launcher &L, const DecodeHost &h, int64_t n
     A.block_id0 = h.block_id0; A.nfile = h.nfile; A.subcells = h.subcells;
     A.sc3 = (long long)h.subcells * h.subcells * h.subcells;
     A.out = (float *)h.out;
+    static const int sync_knob = getenv("MNW_DEC_SYNC") ? atoi(getenv("MNW_DEC_SYNC")) : 0;
+    A.sync_mode = sync_knob;
     const long long units = nfiles * A.sc3;
     if (units == 0) return cudaSuccess;
     const int nsub = h.nfile / h.subcells;
