@@ -160,12 +160,16 @@ int encode_group_dev(mnw_ctx *ctx, int kind, const mnw_float_desc *desc, const v
     const bool aligned = ((uintptr_t)x & 15) == 0 && (nblocks == 1 || (n * (kind == KIND_I64 ? 8 : 4)) % 16 == 0);
     const bool fused = (f32c || i64c) && !d_starts && n > 0 && aligned && !twopass;
     if (fused) CU(ctx->group_ws.reserve(group_fused_ws_bytes(nblocks)));
+    // log10 columns: the statistics pass leaves float32(log10 x) for the pack pass (one logarithm per value)
+    const bool logcol = fused && kind == KIND_F32 && (fp.flags & F_LOG10);
+    if (logcol) CU(ctx->group_log.reserve(4 * (size_t)nblocks * (size_t)n + 64));
     launch_build_contig(ctx->L, ctx->descs.as<BlockDesc>(), nblocks, kind, x, n, d_starts, d_tile0, d_chunk0, fp, nblocks, d_idx,
                         fused ? ctx->stats.as<BlockStat>() : nullptr, fused ? ctx->group_ws.p : nullptr);
     if (fused) {
         ctx->last_path = 2;
         const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, mins, bits,
-                                                  offsets, out_len, out, 0, out_cap, ctx->group_ws.p, kind == KIND_I64, true);
+                                                  offsets, out_len, out, 0, out_cap, ctx->group_ws.p, kind == KIND_I64, true,
+                                                  logcol ? ctx->group_log.p : nullptr);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused group encode: %s", cudaGetErrorString(e));
         return MNW_OK;
     }
@@ -256,6 +260,7 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
     std::vector<size_t> off((size_t)ncols);
     size_t tot = 0;
     bool any_f = false, any_i = false, degenerate = false;
+    int64_t log_hi = 0;   // columns below this index may be log10 columns (scratch of the fused encoder)
     for (int64_t c = 0; c < ncols; c++) {
         off[(size_t)c] = tot;
         tot += ((size_t)(cols[c].is_float ? 4 : 8) * (size_t)n + 15) & ~(size_t)15;
@@ -269,6 +274,7 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
             // group through its int64 arithmetic; so do the exact kernels (as encode_group_dev does)
             if (cols[c].desc.pixels < 1) degenerate = true;
             any_f = true;
+            if (cols[c].desc.log10) log_hi = c + 1;
         } else {
             any_i = true;
         }
@@ -308,10 +314,11 @@ int encode_columns_host(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, con
     static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
     if (fast && n > 0 && !twopass) {   // every column is one uniform contiguous block of its own chain: the fused single-read kernel
         CU(ctx->group_ws.reserve(group_fused_ws_bytes(ncols)));
+        if (log_hi) CU(ctx->group_log.reserve(4 * (size_t)log_hi * (size_t)n + 64));
         ctx->last_path = 2;
         const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, d_mins,
                                                   d_bits, d_offs, d_len, ctx->out.as<uint8_t>(), (int64_t)dstride, (int64_t)dstride,
-                                                  ctx->group_ws.p, any_i);
+                                                  ctx->group_ws.p, any_i, false, log_hi ? ctx->group_log.p : nullptr);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused column encode: %s", cudaGetErrorString(e));
     } else {
         launch_generic_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, ctx->slow.as<int64_t>(),
@@ -486,7 +493,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     mnw_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws,
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws, &ctx->group_log,
                       &ctx->bnd_idx, &ctx->bnd_flags, &ctx->bnd_work, &ctx->txt_work, &ctx->txt_i, &ctx->txt_f, &ctx->txt_fb})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -598,6 +605,7 @@ int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, 
     const int64_t tpb = (n + PACK_TILE - 1) / PACK_TILE, cpb = (n + STATS_CHUNK - 1) / STATS_CHUNK;
     if (ncols * tpb >= (1LL << 31)) return fail(ctx, MNW_ERR_ARG, "batch too large for one launch");
     bool any_f = false, any_i = false, degenerate = false, aligned = true;
+    int64_t log_hi = 0;
     std::vector<BlockDesc> hd((size_t)ncols);
     for (int64_t c = 0; c < ncols; c++) {
         if (!data_dev[c] && n > 0) return fail(ctx, MNW_ERR_ARG, "column %lld has no data", (long long)c);
@@ -614,6 +622,7 @@ int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, 
             d.kind = KIND_F32; d.flags = fp.flags;
             d.low = fp.low; d.high = fp.high; d.dx = fp.dx; d.hi_clamp = fp.hi_clamp; d.pixels = fp.pixels;
             any_f = true;
+            if (cols[c].desc.log10) log_hi = c + 1;
         } else {
             d.kind = KIND_I64;
             any_i = true;
@@ -634,9 +643,11 @@ int mnw_encode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, 
     static const bool twopass = getenv("MNW_GROUP") && !strcmp(getenv("MNW_GROUP"), "twopass");
     if (fast && n > 0 && aligned && !twopass) {
         CU(ctx->group_ws.reserve(group_fused_ws_bytes(ncols)));
+        if (log_hi) CU(ctx->group_log.reserve(4 * (size_t)log_hi * (size_t)n + 64));
         ctx->last_path = 2;
         const cudaError_t e = launch_group_encode(ctx->L, ctx->descs.as<BlockDesc>(), ctx->stats.as<BlockStat>(), sh, d_flags, mins, bits,
-                                                  d_offs, nbytes, out, out_col_stride, out_col_stride, ctx->group_ws.p, any_i);
+                                                  d_offs, nbytes, out, out_col_stride, out_col_stride, ctx->group_ws.p, any_i, false,
+                                                  log_hi ? ctx->group_log.p : nullptr);
         if (e != cudaSuccess) return fail(ctx, MNW_ERR_CUDA, "fused column encode: %s", cudaGetErrorString(e));
     } else {
         ctx->last_path = 0;

@@ -45,6 +45,7 @@ struct GroupFusedArgs {
     int64_t *wide_list;        // blocks wider than 32 bits, for k_pack
     int *wide_count;
     int *err;
+    float *logws;              // [nblocks][uniform_n] float32(log10 x) of the log10 columns' whole tiles, or null
     int wave_tiles;            // tiles per wave: a whole number of blocks
     int sup;                   // tiles per ticket
     int lag;                   // the pack pass of wave g follows the statistics pass of wave g + lag
@@ -59,7 +60,9 @@ enum : int { J_STAT_F32 = 0, J_STAT_I64, J_PACK_F32, J_PACK_I64, J_SKIP, J_END }
 // A job = one tile of one pass, in a ring slot.  The fields that only depend on (block, pass) live in a GProto.
 struct __align__(16) GJob {
     int kind, flush, count, whole;   // whole: a full tile, fetched into the slot by TMA
-    int pi, pad0, pad1, pad2;        // which GProto
+    int pi, pad0;                    // which GProto
+    float *aux;                      // log10 column, whole tile: where the statistics pass leaves float32(log10 x) (clamped)
+                                     // for the pack pass, so that the logarithm is taken once per value; else null
     const void *src;                 // global address of the tile's first element
     uint8_t *dst;                    // pack: where the tile's packed bytes start
 };
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
         int cur_pack = -1;
         GProto proto = {};   // the fields of a job that only depend on (block, pass)
         const char *cur_src = nullptr;
+        float *cur_aux = nullptr;
         unsigned pi = 0;
         bool proto_dirty = false;
         int esz = 4, job_kind = J_SKIP;
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                     proto.b = b;
                     cur_src = (const char *)gd->src;
                     esz = cur_kind == KIND_F32 ? 4 : 8;
+                    cur_aux = (A.logws && cur_kind == KIND_F32 && (gd->flags & F_LOG10)) ? A.logws + (long long)b * A.sh.uniform_n : nullptr;
                     proto_dirty = true;
                     proto.low = gd->low; proto.high = gd->high; proto.dx = gd->dx; proto.hi_clamp = gd->hi_clamp;
                     proto.P = (unsigned)gd->pixels; proto.flags = gd->flags;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                     }
                     if (pack) {
                         while ((ld_acquire_u64(A.pub + b) >> 62) != 2) __nanosleep(64);
+                        if (cur_aux) asm volatile("fence.proxy.async.global;" ::: "memory");   // the TMA reads what other CTAs stored
                         const BlockStat *gs = &A.stats[b];
                         proto.slow = __ldcg(&gs->slow); proto.pmin = __ldcg(&gs->pmin); proto.min = __ldcg(&gs->min);
                         proto.do_bound = __ldcg(&gs->do_bound); proto.bits = __ldcg(&gs->bits);
@@ -282,11 +288,16 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
                 j.count = (int)(first + PACK_TILE <= cur_n ? PACK_TILE : cur_n - first);
                 j.flush = !pack && ((tib == tpb - 1) || (tile == tend - 1 && !next_same));
                 j.whole = j.count == PACK_TILE && job_kind != J_SKIP;
-                j.pi = (int)pi; j.pad0 = j.pad1 = j.pad2 = 0;
+                j.pi = (int)pi; j.pad0 = 0;
                 j.src = cur_src + first * esz;
+                j.aux = nullptr;
+                if (cur_aux && j.whole) {
+                    float *ap = cur_aux + first;
+                    if (((uintptr_t)ap & 15) == 0) j.aux = ap;
+                }
                 j.dst = A.out + (long long)cur_chain * A.chain_stride + cur_off + ((first * proto.bits) >> 3);
                 jobs[slot] = j;
-                if (j.whole) tma_fetch(slots + (size_t)slot * SLOT_BYTES, j.src, (unsigned)(PACK_TILE * esz), &full[slot]);
+                if (j.whole) tma_fetch(slots + (size_t)slot * SLOT_BYTES, (pack && j.aux) ? (const void *)j.aux : j.src, (unsigned)(PACK_TILE * esz), &full[slot]);
                 else gmbar_arrive(&full[slot]);
                 s++;
             }
@@ -301,6 +312,7 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
     // ---------------------------------------------------------------------- consumers
     WarpAcc acc;
     acc.reset();
+    bool aux_stored = false;      // this warp has stored log10 values since its last post
     int pend = 0;                 // stage of the post in flight (warp-uniform)
     long long pend_b = 0;
     unsigned pend_n = 0, pend_prev = 0, pr4 = 0;
@@ -377,9 +389,30 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
             acc.n++;
         } else if ((A.dry == 1 || A.dry == 2) && (kind == J_PACK_F32 || kind == J_PACK_I64)) {
         } else if (kind == J_STAT_F32) {
-            const QuantP qp = job_quant(j);
+            QuantP qp = job_quant(j);
             const unsigned C = j.C;
             if (!j.do_bound) acc.oob = true;   // element 0 of the block is out of range
+            if (jb.whole && jb.aux) {
+                // log10 column: the logarithm (and the clamp) once per value -- in place in the slot, and a copy for the
+                // pack pass (go/minh/minh.go:141-149); from here on the tile is a plain float tile
+                float4 *w4 = (float4 *)(tilep + warp * 4096), *a4 = (float4 *)(jb.aux + warp * 1024);
+                const bool clamp = qp.flags & F_CLAMP;
+#pragma unroll 2
+                for (int i = 0; i < 8; i++) {
+                    float4 vv = w4[lane + 32 * i];
+                    vv.x = go_log10_f32(vv.x); vv.y = go_log10_f32(vv.y); vv.z = go_log10_f32(vv.z); vv.w = go_log10_f32(vv.w);
+                    if (clamp) {
+                        vv.x = vv.x < qp.low ? qp.low : vv.x; vv.x = vv.x >= qp.high ? qp.hi_clamp : vv.x;
+                        vv.y = vv.y < qp.low ? qp.low : vv.y; vv.y = vv.y >= qp.high ? qp.hi_clamp : vv.y;
+                        vv.z = vv.z < qp.low ? qp.low : vv.z; vv.z = vv.z >= qp.high ? qp.hi_clamp : vv.z;
+                        vv.w = vv.w < qp.low ? qp.low : vv.w; vv.w = vv.w >= qp.high ? qp.hi_clamp : vv.w;
+                    }
+                    w4[lane + 32 * i] = vv;
+                    __stcg(a4 + lane + 32 * i, vv);
+                }
+                qp.flags &= ~(unsigned)(F_LOG10 | F_CLAMP);
+                aux_stored = true;
+            }
             if (jb.whole) {
                 const float4 *s4 = (const float4 *)(tilep + warp * 4096);
                 const bool clamp = qp.flags & F_CLAMP, islog = qp.flags & F_LOG10;
@@ -468,7 +501,8 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
             uint8_t *dst = jb.dst + (((long long)warp * 1024 * bits) >> 3);
             unsigned v[32];
             if (kind == J_PACK_F32) {
-                const QuantP qp = job_quant(j);
+                QuantP qp = job_quant(j);
+                if (jb.whole && jb.aux) qp.flags &= ~(unsigned)(F_LOG10 | F_CLAMP);   // the tile came from the statistics pass's copy
                 const long long pmin = j.pmin, mn = j.min;
                 const int slow = j.slow, do_bound = j.do_bound;
                 const unsigned mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
@@ -590,6 +624,12 @@ __global__ void __launch_bounds__(GF_THREADS, NS * SLOT_BYTES <= 32768 ? 6 : (NS
         // stage 2 = the block's counter, stage 3 = "was this the last post of the block?"
         advance();
         if (flush) {
+            if (aux_stored) {   // the stored logarithms are performed (and visible to the async proxy) before this post counts
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncwarp();
+                aux_stored = false;
+            }
             while (pend) advance();   // consecutive posts (short tickets, block ends): finish the earlier one first
             BlockStat *sb = &A.stats[b];
             if (kind == J_STAT_F32) {
@@ -654,7 +694,7 @@ static cudaError_t launch_group_fused_t(Launcher &L, GroupFusedArgs &A, int64_t 
     A.wave_tiles = (int)wave;
     // tiles per ticket: 4 amortise the ticket and the flush for a large batch; a small batch (fewer tickets than
     // co-resident CTAs) is spread over more CTAs instead (measured on 16 blocks of 2^16: 0.052 -> 0.043 ms)
-    A.sup = 4;
+    A.sup = A.logws ? 1 : 4;   // (log10 columns: a tile is ~3x the work, single-tile tickets balance better: 0.53 -> 0.48 ms)
     while (A.sup > 1 && wave / A.sup < dc.a) A.sup >>= 1;
     if (sup_knob > 0) A.sup = sup_knob;
     const long long nsw = (wave + A.sup - 1) / A.sup, nwaves = (sh.total_tiles + wave - 1) / wave;
@@ -674,7 +714,7 @@ static cudaError_t launch_group_fused_t(Launcher &L, GroupFusedArgs &A, int64_t 
 // 1 <= pixels < 2^31; every block 16-byte aligned).  descs are ready on the stream.  ws: group_fused_ws_bytes(nblocks).
 cudaError_t launch_group_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh, int *flags,
                                 int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
-                                int64_t chain_stride, int64_t chain_cap, void *ws, bool has_i64, bool prepared) {
+                                int64_t chain_stride, int64_t chain_cap, void *ws, bool has_i64, bool prepared, void *logws) {
     if (sh.nblocks == 0 || sh.total_tiles == 0) return cudaSuccess;
     // prepared: the descriptor kernel has initialised the statistics records and zeroed ws already
     if (!prepared) launch_init_stats(L, descs, stats, sh.nblocks);
@@ -682,6 +722,7 @@ cudaError_t launch_group_encode(Launcher &L, const BlockDesc *descs, BlockStat *
     A.descs = descs; A.stats = stats; A.sh = sh;
     A.mins = mins; A.bits = bits; A.offsets = offsets; A.out_len = out_len; A.out = out;
     A.chain_stride = chain_stride; A.chain_cap = chain_cap;
+    A.logws = (float *)logws;
     A.pub = (unsigned long long *)ws;
     A.wide_list = (int64_t *)(A.pub + sh.nblocks);
     A.done = (unsigned *)(A.wide_list + sh.nblocks);

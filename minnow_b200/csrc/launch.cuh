@@ -113,7 +113,8 @@ void launch_generic_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats
 size_t group_fused_ws_bytes(int64_t nblocks);
 cudaError_t launch_group_encode(Launcher &L, const BlockDesc *descs, BlockStat *stats, const BatchShape &sh, int *flags,
                                 int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
-                                int64_t chain_stride, int64_t chain_cap, void *ws, bool has_i64, bool prepared = false);
+                                int64_t chain_stride, int64_t chain_cap, void *ws, bool has_i64, bool prepared = false,
+                                void *logws = nullptr);   // logws: 4 * uniform_n bytes per block up to the last log10 block, or null
 void launch_init_stats(Launcher &L, const BlockDesc *descs, BlockStat *stats, int64_t nb);
 void launch_pack_list(Launcher &L, const BlockDesc *descs, const BlockStat *stats, const BatchShape &sh,
                       const int64_t *list, const int *list_count, uint8_t *out, int64_t chain_stride,

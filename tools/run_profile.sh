@@ -18,7 +18,7 @@ python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-configs > /dev/null 
 ncu --set full --clock-control none --import-source on -k "regex:k_pipe_vec3|k_decode_vec3" -c 4 -o gpurun_out/full_$tag -f \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-configs > gpurun_out/ncu_full_$tag.log 2>&1
 summarise full_$tag
-for c in f32 i64; do
+for c in f32 i64 log; do
   python tools/prof_groups.py $c 3 > /dev/null 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:k_group_fused -s 1 -c 1 -o gpurun_out/full_group_${c}_$tag -f \
       python tools/prof_groups.py $c 3 > gpurun_out/ncu_group_${c}_$tag.log 2>&1
