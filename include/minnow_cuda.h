@@ -286,6 +286,17 @@ MNW_API int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc
                                         int64_t data_len, const int64_t *offsets, const int64_t *mins,
                                         const int64_t *bits, int64_t n, int64_t nsel,
                                         const int64_t *sel, const mnw_jitter *jitter, float *out);
+
+/* The read side of the same block: every IntGroup / FloatGroup column in two launches (the per-column loop of
+ * minh.Reader.Block, go/minh/minh.go:296-323; Log columns come back through 10^x).  Column c is block 0 of its own group,
+ * packed at data + offsets[c] (mnw_encode_columns_dev's layout: offsets[c] = c * out_col_stride), with mins[c], bits[c];
+ * its n values go to out_dev[c] (int64 or float32).  data (data_len readable bytes), offsets, mins, bits: DEVICE pointers; out_dev: a HOST array of
+ * ncols DEVICE pointers.  jitter: CENTER or HASH (column c hashes with block id jitter->block_id0 + c).  Enqueued on the
+ * context's stream without synchronising. */
+MNW_API int mnw_decode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const uint8_t *data, int64_t data_len,
+                                   const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n,
+                                   const mnw_jitter *jitter, void *const *out_dev);
+
 /* nfiles cubes back to back in aos (each nfile^3 particles); outputs are
  * [nfiles][3*subcells^3]; file f / axis k bytes at out + (3*f + k)*out_axis_stride,
  * lengths in out_len[3*f + k].  desc (HOST) holds 3 entries shared by all files

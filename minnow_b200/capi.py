@@ -66,6 +66,7 @@ SIGNATURES = {
     "mnw_encode_int_group_gather": (_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_encode_columns": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64]),
     "mnw_encode_columns_dev": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64]),
+    "mnw_decode_columns_dev": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
     "mnw_encode_float_group_gather": (_int, [_p, _FD, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, C.POINTER(_i64)]),
     "mnw_precision_needed": (_int, [_u64]),
     "mnw_array_bytes": (_i64, [_int, _i64]),
@@ -444,6 +445,19 @@ class Context:
                 cols[i].desc = d
             ptrs[i] = x.data_ptr() if hasattr(x, "data_ptr") else int(x)
         self._check(self.lib.mnw_encode_columns_dev(self.h, nc, cols, ptrs, n, _ptr(mins), _ptr(bits), _ptr(nbytes), _ptr(out), out_col_stride))
+
+    def decode_columns_dev(self, descs, data, offsets, mins, bits, n, jitter, outs):
+        """mnw_decode_columns_dev: descs = [FloatDesc or None per column], outs = [device tensor per column]"""
+        nc = len(descs)
+        cols = (Column * max(nc, 1))()
+        ptrs = (C.c_void_p * max(nc, 1))()
+        for i, d in enumerate(descs):
+            cols[i].is_float = 0 if d is None else 1
+            if d is not None:
+                cols[i].desc = d
+            ptrs[i] = outs[i].data_ptr() if hasattr(outs[i], "data_ptr") else int(outs[i])
+        self._check(self.lib.mnw_decode_columns_dev(self.h, nc, cols, _ptr(data), int(data.numel()), _ptr(offsets), _ptr(mins), _ptr(bits), n,
+                                                    C.byref(jitter) if jitter is not None else None, ptrs))
 
     # ---- text -> columns ------------------------------------------------------------------------
     def text_parse_block(self, buf, icols, fcols, sep=b" ", comment=b"#"):

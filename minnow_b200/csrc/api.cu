@@ -493,7 +493,7 @@ void mnw_destroy(mnw_ctx *ctx) {
     mnw_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->L.stream);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->descs, &ctx->stats, &ctx->slow, &ctx->flags, &ctx->meta,
-                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws, &ctx->group_log,
+                      &ctx->aux, &ctx->dec_out, &ctx->ustream, &ctx->fused_ws, &ctx->params, &ctx->coop_ws, &ctx->group_ws, &ctx->group_log, &ctx->dec_cols,
                       &ctx->bnd_idx, &ctx->bnd_flags, &ctx->bnd_work, &ctx->txt_work, &ctx->txt_i, &ctx->txt_f, &ctx->txt_fb})
         b->release();
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -958,6 +958,59 @@ int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const 
     h.data = data; h.stream_len = data_len; h.offsets = offsets; h.mins = mins; h.bits = bits;
     h.sel = sel; h.n = n; h.nsel = nsel; h.out = out;
     launch_decode(ctx->L, h);
+    CU(cudaGetLastError());
+    return MNW_OK;
+}
+
+// Every IntGroup / FloatGroup column of one minh block in two launches (minh.Reader.Block's per-column loop,
+// go/minh/minh.go:296-323): column c is block 0 of its own group, packed at data + offsets[c].
+int mnw_decode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const uint8_t *data, int64_t data_len,
+                           const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n, const mnw_jitter *jitter,
+                           void *const *out_dev) {
+    if (!ctx) return MNW_ERR_ARG;
+    (void)cudaSetDevice(ctx->device);
+    if (ncols < 0 || n < 0 || data_len < 0) return fail(ctx, MNW_ERR_ARG, "negative length");
+    if (ncols == 0 || n == 0) return MNW_OK;
+    if (!cols || !out_dev || !data || !offsets || !mins || !bits) return fail(ctx, MNW_ERR_ARG, "null argument");
+    if (jitter && (jitter->mode < 0 || jitter->mode > 1))
+        return fail(ctx, MNW_ERR_ARG, "mnw_decode_columns_dev takes MNW_JITTER_CENTER or MNW_JITTER_HASH");
+    std::vector<FloatParams> tab((size_t)ncols);
+    std::vector<int64_t> sel_f, sel_i;
+    std::vector<void *> out_f, out_i;
+    for (int64_t c = 0; c < ncols; c++) {
+        if (!out_dev[c]) return fail(ctx, MNW_ERR_ARG, "column %lld has no output", (long long)c);
+        if (cols[c].is_float) {
+            int rc = check_desc(ctx, &cols[c].desc);
+            if (rc) return rc;
+            tab[(size_t)c] = to_params(cols[c].desc);
+            sel_f.push_back(c); out_f.push_back(out_dev[c]);
+        } else {
+            tab[(size_t)c] = FloatParams{};
+            sel_i.push_back(c); out_i.push_back(out_dev[c]);
+        }
+    }
+    // one upload: [tab | sel_f | sel_i | out_f | out_i]
+    const size_t tab_b = sizeof(FloatParams) * (size_t)ncols, o_sf = (tab_b + 15) & ~(size_t)15, o_si = o_sf + 8 * sel_f.size(),
+                 o_of = o_si + 8 * sel_i.size(), o_oi = o_of + 8 * out_f.size(), total = o_oi + 8 * out_i.size();
+    std::vector<unsigned char> blob(total);
+    memcpy(blob.data(), tab.data(), tab_b);
+    if (!sel_f.empty()) { memcpy(blob.data() + o_sf, sel_f.data(), 8 * sel_f.size()); memcpy(blob.data() + o_of, out_f.data(), 8 * out_f.size()); }
+    if (!sel_i.empty()) { memcpy(blob.data() + o_si, sel_i.data(), 8 * sel_i.size()); memcpy(blob.data() + o_oi, out_i.data(), 8 * out_i.size()); }
+    CU(ctx->dec_cols.reserve(total + 16));
+    CU(cudaMemcpyAsync(ctx->dec_cols.p, blob.data(), total, cudaMemcpyHostToDevice, ctx->L.stream));   // pageable: staged before return
+    unsigned char *d = (unsigned char *)ctx->dec_cols.p;
+    DecodeHost h;
+    h.data = data; h.stream_len = data_len; h.offsets = offsets; h.mins = mins; h.bits = bits; h.n = n;
+    h.tab = (const FloatParams *)d; h.tab_per_file = 1;
+    if (jitter) { h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0; }
+    if (!sel_f.empty()) {
+        h.mode = 1; h.sel = (const int64_t *)(d + o_sf); h.nsel = (int64_t)sel_f.size(); h.outs = (void *const *)(d + o_of);
+        launch_decode(ctx->L, h);
+    }
+    if (!sel_i.empty()) {
+        h.mode = 0; h.sel = (const int64_t *)(d + o_si); h.nsel = (int64_t)sel_i.size(); h.outs = (void *const *)(d + o_oi);
+        launch_decode(ctx->L, h);
+    }
     CU(cudaGetLastError());
     return MNW_OK;
 }

@@ -36,7 +36,7 @@ struct mnw_ctx {
     std::string err;
     int last_path = 0;
     int force_generic = 0;
-    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws, group_ws, group_log;
+    DevBuf in, out, descs, stats, slow, flags, meta, aux, dec_out, ustream, fused_ws, params, coop_ws, group_ws, group_log, dec_cols;
     int *h_flags = nullptr;  // pinned: [slow_count, err]
     void *h_stage = nullptr; // pinned staging for gathered uploads (grow-only)
     size_t h_stage_cap = 0;

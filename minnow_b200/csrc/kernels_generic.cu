@@ -482,6 +482,7 @@ struct DecodeArgs {
     int32_t nfile, nsub, subcells;
     int64_t sc3;
     void *out;
+    void *const *outs;        // contiguous decoders: output of selected block j (else out + j * n elements)
 };
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(DecodeArgs A) {
@@ -802,14 +803,14 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
     const int64_t b = A.sel ? A.sel[j] : j;
     const long long mn = A.mins[b];
     const int bits = (int)A.bits[b];
-    const FloatParams fp = A.tab[0];
+    const FloatParams fp = A.tab[A.tab_per_file ? b : 0];   // (a batch of columns: one group per block)
     const long long P = fp.pixels;
     const bool periodic = fp.flags & F_PERIODIC, islog = fp.flags & F_LOG10;
     const int64_t first = tile * DEC_CHUNK;
     const int count = (int)(first + DEC_CHUNK <= A.n ? DEC_CHUNK : A.n - first);
     const unsigned long long bid = A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b);
     const unsigned key = jitter_key(A.seed, bid);
-    float *outp = (float *)A.out + j * A.n + first;
+    float *outp = (A.outs ? (float *)A.outs[j] : (float *)A.out + j * A.n) + first;
     const unsigned mask = (bits >= 1 && bits <= 32) ? (0xffffffffu >> (32 - bits)) : 0u;
     // 32-bit path: q = mn + v lies in [0, 2*pixels) (periodic) or [0, 2^23), and float32 holds it exactly
     const bool fast = bits <= 32 && mn >= 0 && P > 0 && P < (1LL << 23) &&
@@ -1022,7 +1023,7 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_i64c(DecodeArgs A) {
     const int bits = (int)A.bits[b];
     const int64_t first = tile * DEC_CHUNK;
     const int count = (int)(first + DEC_CHUNK <= A.n ? DEC_CHUNK : A.n - first);
-    long long *outp = (long long *)A.out + j * A.n + first;
+    long long *outp = (A.outs ? (long long *)A.outs[j] : (long long *)A.out + j * A.n) + first;
     if (bits <= 32) {
         const unsigned mask = bits >= 1 ? (0xffffffffu >> (32 - bits)) : 0u;
         unsigned shift0 = 0;
@@ -1126,7 +1127,7 @@ void launch_decode(Launcher &L, const DecodeHost &h) {
     A.wrap_L = h.wrap_L; A.jmode = h.jmode; A.seed = h.seed; A.block_id0 = h.block_id0; A.u = h.u;
     A.nfile = h.nfile; A.nsub = h.subcells ? h.nfile / h.subcells : 0; A.subcells = h.subcells;
     A.sc3 = (int64_t)h.subcells * h.subcells * h.subcells;
-    A.out = h.out;
+    A.out = h.out; A.outs = h.outs;
     int64_t cpb = (h.n + DEC_CHUNK - 1) / DEC_CHUNK;
     if (h.mode == 1 && h.jmode != 2) {   // contiguous float32 blocks: staged, vectorised decode
         L.begin("k_decode_f32c");

@@ -70,6 +70,7 @@ struct DecodeHost {
     const double *u = nullptr;
     int32_t nfile = 0, subcells = 0;
     void *out = nullptr;
+    void *const *outs = nullptr;   // device array: output pointer of every selected block (contiguous group decoders)
 };
 
 // kernels_generic.cu

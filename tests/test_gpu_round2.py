@@ -784,3 +784,52 @@ def test_text_to_minh_block_without_leaving_the_device(ctx, orc):
             om, ob, od = orc.float_block_encode(orc.minh_process_float(a.copy(), d.log10, d.low, d.high), d.low, d.high, d.pixels)
         assert (int(mins[c]), int(bits[c]), int(lens[c])) == (om, ob, len(od))
         assert out[c * stride:c * stride + len(od)].cpu().numpy().tobytes() == od.tobytes()
+
+
+def test_decode_columns_dev_matches_per_column_decode(ctx, orc):
+    """mnw_decode_columns_dev (two launches for a whole block of columns) == the per-column decoders with block id c, and the
+    oracle's decode of the same bytes (minh.Reader.Block, go/minh/minh.go:296-323), Log column included"""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 3 * 4096 + 100
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    dlin = mb.FloatDesc.make(0.0, 125.0, mb.float_group_pixels(0.0, 125.0, 0.001), 1, 0, 1)
+    dlog = mb.FloatDesc.make(10.0, 15.0, mb.float_group_pixels(10.0, 15.0, 0.01), 1, 1, 1)
+    cols = [(torch.randint(-5000, 5000, (n,), generator=g, device=dev, dtype=torch.int64), None),
+            (torch.rand(n, generator=g, device=dev, dtype=torch.float32) * 125.0, dlin),
+            (torch.pow(10.0, 10.0 + 5.0 * torch.rand(n, generator=g, device=dev, dtype=torch.float32)), dlog),
+            (torch.randint(0, 1 << 40, (n,), generator=g, device=dev, dtype=torch.int64), None),
+            (torch.rand(n, generator=g, device=dev, dtype=torch.float32) * 125.0, dlin)]
+    nc = len(cols)
+    i64 = dict(dtype=torch.int64, device=dev)
+    stride = 8 * n + 256
+    out = torch.zeros(nc * stride, dtype=torch.uint8, device=dev)
+    mins, bits, lens = (torch.zeros(nc, **i64) for _ in range(3))
+    ctx.encode_columns_dev(cols, n, mins, bits, lens, out, stride)
+    offs = torch.arange(nc, **i64) * stride
+    for mode in (mb.JITTER_CENTER, mb.JITTER_HASH):
+        jit = mb.Jitter.make(mode, 5)
+        outs = [torch.zeros(n, **i64) if d is None else torch.zeros(n, dtype=torch.float32, device=dev) for _, d in cols]
+        ctx.decode_columns_dev([d for _, d in cols], out, offs, mins, bits, n, jit, outs)
+        ctx.sync()
+        zero = torch.zeros(1, **i64)
+        for c, (x, d) in enumerate(cols):
+            pk = out[c * stride:(c + 1) * stride]
+            if d is None:
+                ref = torch.zeros(n, **i64)
+                ctx.decode_int_blocks_dev(pk, pk.numel(), zero, mins[c:c + 1], bits[c:c + 1], n, 1, None, ref)
+                ctx.sync()
+                assert torch.equal(ref, outs[c]) and torch.equal(ref, x)
+            else:
+                ref = torch.zeros(n, dtype=torch.float32, device=dev)
+                jc = mb.Jitter.make(mode, 5, block_id0=c)
+                ctx.decode_float_blocks_dev(d, pk, pk.numel(), zero, mins[c:c + 1], bits[c:c + 1], n, 1, None, jc, ref)
+                ctx.sync()
+                assert torch.equal(ref.view(torch.int32), outs[c].view(torch.int32)), (mode, c)
+                # the oracle's decode of the same bytes (HASH: block id c), then 10^x for the Log column (numpy float64
+                # pow == Go's math.Pow here is NOT assumed: only the linear column is compared bit for bit)
+                if not d.log10:
+                    nb = int(lens[c])
+                    want = orc.float_block_decode(pk[:nb].cpu().numpy(), n, int(mins[c]), int(bits[c]), d.low, d.high, int(d.pixels), 1,
+                                                  mode, 5, c)
+                    assert np.array_equal(want.view(np.int32), outs[c].cpu().numpy().view(np.int32)), (mode, c)
