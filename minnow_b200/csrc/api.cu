@@ -1057,7 +1057,7 @@ static int encode_vec3_core(mnw_ctx *ctx, const FloatParams *tab, const std::vec
         void *coop_ws = nullptr;
         const char *cmin = getenv("MNW_PIPE_COOP_MIN");   // tuning / test knob: smallest batch (in units) that goes cooperative
         if (nfiles * sc3 >= (cmin ? atoll(cmin) : 256) || nsub == 32 || nsub == 128) {   // 32^3 and 128^3: k_pipe_vec3 has no cluster schedule
-            CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3)));
+            CU(ctx->coop_ws.reserve(pipe_coop_ws_bytes(nfiles * sc3, (int)nsub)));
             coop_ws = ctx->coop_ws.p;
         }
         bool ran_pipe = false;

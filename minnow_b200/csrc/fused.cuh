@@ -35,7 +35,7 @@ cudaError_t launch_fused_vec3(Launcher &L, const FusedWork &W, const BlockDesc *
                               const float *aos, int nfile, int subcells, int64_t nfiles, BlockStat *stats,
                               int64_t *mins, int64_t *bits, int64_t *offsets, int64_t *out_len, uint8_t *out,
                               int64_t out_axis_stride, bool pipe_ok, void *coop_ws, bool *ran_pipe = nullptr);
-size_t pipe_coop_ws_bytes(int64_t nunits);   // workspace of the cooperative k_pipe_vec3 schedule
+size_t pipe_coop_ws_bytes(int64_t nunits, int nsub);   // workspace of the cooperative k_pipe_vec3 schedule
 // k_pipe_vec3 (the warp-specialised 64^3 encode) applies when every group has pixels <= 2^22.
 bool pipe_vec3_supported(const FloatParamsHost *fp, int64_t nparams);
 

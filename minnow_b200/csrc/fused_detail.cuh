@@ -44,7 +44,7 @@ struct FusedArgs {
     long long axis_stride;
     int prefetch;   // pull the next unit's rows into L2 during the pack phase
     int ticket_chunk;  // k_fused_vec3: consecutive sub-cells per step of the round-robin ticket order (claim_unit)
-    unsigned *ustat;   // k_pipe_vec3<COOP>: [nunits][16] statistics records in global memory (zeroed before the launch)
+    unsigned *ustat;   // k_pipe_vec3<COOP>: [nunits][parts][16] u64 statistics records in global memory (zeroed before the launch)
     FusedWork W;
 };
 

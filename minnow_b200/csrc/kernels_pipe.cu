@@ -58,7 +58,9 @@ cudaError_t launch_pipe_vec3(Launcher &L, const FusedArgs &A) {
 // parts of a unit are always items of the same round), statistics records in `ustat` (16 words per unit, zeroed
 // here).  Returns cudaErrorCooperativeLaunchTooLarge / NotSupported when the device cannot hold the grid; the
 // caller then takes the cluster kernel.
-size_t pipe_coop_ws_bytes(int64_t nunits) { return (size_t)nunits * 64; }
+// one 128-byte record per (unit, part): 13 words {tag 1 | statistic}, written once by the part's CTA, polled by all of the unit's
+// (128^3 sub-cells, 64 parts: one 64-byte record per unit, combined by atomics)
+size_t pipe_coop_ws_bytes(int64_t nunits, int nsub) { return (size_t)nunits * (size_t)(nsub == 64 ? 8 * 128 : 64); }
 
 template <int NSUB>
 static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
@@ -87,7 +89,7 @@ static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
     const long long items = PARTS * A.nunits;
     const unsigned grid = (unsigned)(items < grid_max ? items : grid_max);   // >= PARTS: no CTA ever holds two parts of a unit
     A.ustat = (unsigned *)ws;
-    e = cudaMemsetAsync(ws, 0, pipe_coop_ws_bytes(A.nunits), L.stream);
+    e = cudaMemsetAsync(ws, 0, pipe_coop_ws_bytes(A.nunits, NSUB), L.stream);
     if (e != cudaSuccess) return e;
     void *args[] = {(void *)&A};
     L.begin("k_pipe_vec3");

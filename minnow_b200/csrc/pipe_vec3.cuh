@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
     constexpr int LT = 32 * PIPE_LW, PT = 32 * (PIPE_PW + 1);   // loader threads; packer + scanner threads
     constexpr int NGROUPS = 3 * (CHUNK / 1024);   // pack groups per CTA and unit
     constexpr int UM = PIPE_USLOTS - 1;
+    // COOP, a handful of parts per unit: one tagged record per (unit, part), polled by every CTA of the unit; many parts
+    // (128^3 sub-cells: 64): one record per unit, combined by atomics, with a counter
+    constexpr bool REC = COOP && PARTS > 1 && PARTS <= 16;
     if (A.W.skip && *A.W.skip) return;   // uniform over the grid: written before the launch
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -574,21 +577,32 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 // this CTA holds the whole unit: its statistics are the unit's, the scanner reads them from s_cta
                 if (tid == 0) mbar_arrive(&bar_stats[it & 1]);
             } else if constexpr (COOP) {
-                // the unit's record in global memory: [4 k + {0, 1, 2, 3}] = ~wmin, wmax, ~qmin, qmax of axis k (atomicMax
-                // from zero), [12] oob, [13] parts arrived
-                unsigned *us = A.ustat + 16 * unit;
-                if (tid < 13) {
-                    const unsigned m = s_cta[tid];
-                    if (tid < 12) {
-                        const unsigned v = (tid & 2) ? m - FMAGIC : m;
-                        atomicMax(us + tid, (tid & 1) ? v : ~v);
-                    } else if (m) {
-                        atomicOr(us + 12, 1u);
+                // this part's record in global memory: word s = tag 1 << 32 | statistic s ([4 k + {0, 1, 2, 3}] = wmin, wmax, qmin,
+                // qmax of axis k, [12] oob).  One relaxed 64-bit store per word and nothing else: value and tag arrive together,
+                // so the readers need neither an atomic, nor a fence, nor a counter (three dependent round trips less per part)
+                if constexpr (REC) {
+                    if (tid < 13) {
+                        const unsigned m = s_cta[tid];
+                        const unsigned v = tid < 12 ? ((tid & 2) ? m - FMAGIC : m) : (m ? 1u : 0u);
+                        st_relaxed((unsigned long long *)A.ustat + ((size_t)unit * PARTS + rank) * 16 + tid, (1ULL << 32) | v);
                     }
-                    __threadfence();
+                } else {
+                    // one record per unit: [4 k + {0, 1, 2, 3}] = ~wmin, wmax, ~qmin, qmax of axis k (atomicMax from zero),
+                    // [12] oob, [13] parts arrived
+                    unsigned *us = A.ustat + 16 * unit;
+                    if (tid < 13) {
+                        const unsigned m = s_cta[tid];
+                        if (tid < 12) {
+                            const unsigned v = (tid & 2) ? m - FMAGIC : m;
+                            atomicMax(us + tid, (tid & 1) ? v : ~v);
+                        } else if (m) {
+                            atomicOr(us + 12, 1u);
+                        }
+                        __threadfence();
+                    }
+                    __syncwarp();
+                    if (tid == 0) atomicAdd(us + 13, 1u);
                 }
-                __syncwarp();
-                if (tid == 0) atomicAdd(us + 13, 1u);
             } else if (tid < CS) {   // post this CTA's statistics to CTA `tid` and tell it
                 const int par_i = it & 1;
 #pragma unroll
@@ -621,15 +635,32 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
             const long long f = unit / A.sc3, sc = unit - f * A.sc3;
             const int par_i = it & 1;
             if (scanner) {
+                unsigned ured = 0;   // COOP, several parts: statistic `lane` of the unit
                 if constexpr (PARTS == 1) {
                     mbar_wait(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
-                } else if constexpr (COOP) {   // all parts of the unit have posted their statistics
-                    const unsigned *cnt = A.ustat + 16 * unit + 13;
+                } else if constexpr (COOP && !REC) {   // all parts of the unit have posted their statistics
+                    const unsigned *us = A.ustat + 16 * unit;
                     unsigned c;
                     do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(cnt) : "memory");
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(us + 13) : "memory");
                         if (c < (unsigned)PARTS) __nanosleep(64);
                     } while (c < (unsigned)PARTS);
+                    if (lane < 13) { const unsigned v = __ldcg(us + lane); ured = (lane & 1) || lane == 12 ? v : ~v; }
+                } else if constexpr (COOP) {   // all parts of the unit have posted their statistics: lane s < 13 combines word s
+                    const unsigned long long *rec = (const unsigned long long *)A.ustat + (size_t)unit * PARTS * 16 + (lane < 13 ? lane : 0);
+                    for (;;) {
+                        bool all = true;
+                        unsigned mnv = ~0u, mxv = 0u;
+#pragma unroll 8
+                        for (int r = 0; r < PARTS; r++) {
+                            const unsigned long long v = ld_relaxed(rec + r * 16);
+                            all = all && (v >> 32) != 0;
+                            mnv = min(mnv, (unsigned)v); mxv = max(mxv, (unsigned)v);
+                        }
+                        ured = (lane & 1) || lane == 12 ? mxv : mnv;   // (oob: the maximum of 0 / 1 is the OR)
+                        if (__all_sync(0xffffffffu, all)) break;
+                        __nanosleep(32);
+                    }
                 } else {
                     mbar_wait_cluster(&bar_stats[par_i], (unsigned)(it >> 1) & 1u);
                 }
@@ -641,6 +672,9 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                 unsigned base = 0, padj = 0;
                 int bits = 0, mode = 0;
                 bool slow = false;
+                const unsigned u_wmin = __shfl_sync(0xffffffffu, ured, 4 * k), u_wmax = __shfl_sync(0xffffffffu, ured, 4 * k + 1);
+                const unsigned u_qmin = __shfl_sync(0xffffffffu, ured, 4 * k + 2), u_qmax = __shfl_sync(0xffffffffu, ured, 4 * k + 3);
+                const unsigned u_oob = __shfl_sync(0xffffffffu, ured, 12);
                 if (lane < 3) {
                     XStat x;
                     x.wmin = ~0u; x.wmax = 0u; x.qmin = INT_MAX; x.qmax = INT_MIN; x.oob = 0;
@@ -649,10 +683,7 @@ __global__ void __launch_bounds__(PIPE_NT, 1) k_pipe_vec3(const FusedArgs A) {
                         x.qmin = (int)(s_cta[4 * k + 2] - FMAGIC); x.qmax = (int)(s_cta[4 * k + 3] - FMAGIC);
                         x.oob = s_cta[12];
                     } else if constexpr (COOP) {
-                        const unsigned *us = A.ustat + 16 * unit;
-                        x.wmin = ~__ldcg(us + 4 * k); x.wmax = __ldcg(us + 4 * k + 1);
-                        x.qmin = (int)~__ldcg(us + 4 * k + 2); x.qmax = (int)__ldcg(us + 4 * k + 3);
-                        x.oob = __ldcg(us + 12);
+                        x.wmin = u_wmin; x.wmax = u_wmax; x.qmin = (int)u_qmin; x.qmax = (int)u_qmax; x.oob = u_oob;
                     } else {
 #pragma unroll
                         for (int r = 0; r < CS; r++) {

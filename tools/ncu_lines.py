@@ -10,7 +10,7 @@ def main(path, top=40):
     rows = list(csv.reader(open(path)))
     fname, hdr, agg = "?", None, {}
     for r in rows:
-        if r and r[0] == "File Name":
+        if r and r[0] in ("File Name", "File Path"):
             fname = r[1].split("/")[-1]
         elif r and r[0] == "Line No":
             hdr = r
