@@ -96,6 +96,20 @@ static cudaError_t launch_pipe_vec3_coop_t(Launcher &L, FusedArgs A, void *ws) {
     e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(PIPE_NT), args, smem, L.stream);
     L.end();
     L.count++;
+#ifdef MNW_PIPE_DBG
+    if (getenv("MNW_PIPE_DBG")) {   // per-part timeline of CTAs 0, 56, 112 (%globaltimer stamps, microseconds; build with MNW_DEFINES=MNW_PIPE_DBG)
+        cudaDeviceSynchronize();
+        static unsigned long long h[32 * 64 * 8];
+        cudaMemcpyFromSymbol(h, g_pipe_dbg, sizeof(h));
+        for (int c = 0; c < 15; c += 7)
+            for (int it = 2; it < 14; it++) {
+                const unsigned long long *r = h + (c * 64 + it) * 8, t0 = h[(c * 64) * 8];
+                fprintf(stderr, "c%d it%2d top %7.1f | load %5.1f | stats +%5.1f | fin +%5.1f | off +%5.1f | pre +%5.1f | packed +%5.1f\n", c, it,
+                        (r[0] - t0) / 1e3, (r[1] - r[0]) / 1e3, (r[2] - r[1]) / 1e3, (r[3] - r[2]) / 1e3, (r[4] - r[3]) / 1e3,
+                        (r[6] - r[4]) / 1e3, (r[7] - r[6]) / 1e3);
+            }
+    }
+#endif
     return e;
 }
 
