@@ -688,7 +688,7 @@ static cudaError_t launch_group_fused_t(Launcher &L, GroupFusedArgs &A, int64_t 
     // a wave is a whole number of blocks: every statistics tile of a block then has a smaller ticket than any of the
     // block's pack tiles (a pack job only ever waits for smaller tickets)
     const long long tpb = (sh.uniform_n + PACK_TILE - 1) / PACK_TILE;
-    long long wave = (long long)(wave_knob > 0 ? wave_knob : 64) * (1 << 20) / tile_bytes;
+    long long wave = (long long)(wave_knob > 0 ? wave_knob : 128) * (1 << 20) / tile_bytes;
     wave = (wave + tpb - 1) / tpb * tpb;
     if (wave > sh.total_tiles) wave = sh.total_tiles;
     A.wave_tiles = (int)wave;
