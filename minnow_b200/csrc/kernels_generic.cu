@@ -794,7 +794,7 @@ k_pack_i64c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
 // Decode of contiguous float32 blocks: one CTA per 4096-element tile of a selected block.  The
 // tile's packed bytes are staged in shared memory with 128-bit loads, every thread then extracts
 // four consecutive values, dequantises them and stores one float4.
-constexpr int FDEC_THREADS = 256;
+constexpr int FDEC_THREADS = 128;
 __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
     __shared__ __align__(16) unsigned spk[DEC_CHUNK + 16];
     const int64_t tpb = (A.n + DEC_CHUNK - 1) / DEC_CHUNK;
