@@ -287,7 +287,7 @@ MNW_API int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc
                                         const int64_t *bits, int64_t n, int64_t nsel,
                                         const int64_t *sel, const mnw_jitter *jitter, float *out);
 
-/* The read side of the same block: every IntGroup / FloatGroup column in two launches (the per-column loop of
+/* The read side of the same block: every IntGroup / FloatGroup column in at most three launches (plain float, Log, int: the per-column loop of
  * minh.Reader.Block, go/minh/minh.go:296-323; Log columns come back through 10^x).  Column c is block 0 of its own group,
  * packed at data + offsets[c] (mnw_encode_columns_dev's layout: offsets[c] = c * out_col_stride), with mins[c], bits[c];
  * its n values go to out_dev[c] (int64 or float32).  data (data_len readable bytes), offsets, mins, bits: DEVICE pointers; out_dev: a HOST array of

@@ -350,7 +350,11 @@ int fill_decode_float(mnw_ctx *ctx, DecodeHost &h, const mnw_float_desc *desc, i
     rc = upload_params(ctx, desc, ndesc, host, &h.tab);
     if (rc) return rc;
     h.low_nonneg = true;   // every decoded value dx * t + low is then >= +0: the periodic wrap needs one test only
-    for (const FloatParams &p : host) h.low_nonneg = h.low_nonneg && p.low >= 0.0f && p.dx > 0.0f;
+    h.any_log = false;
+    for (const FloatParams &p : host) {
+        h.low_nonneg = h.low_nonneg && p.low >= 0.0f && p.dx > 0.0f;
+        h.any_log = h.any_log || (p.flags & F_LOG10);
+    }
     if (jitter) {
         if (jitter->mode < 0 || jitter->mode > 2) return fail(ctx, MNW_ERR_ARG, "unknown jitter mode %d", jitter->mode);
         h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0;
@@ -962,7 +966,7 @@ int mnw_decode_float_blocks_dev(mnw_ctx *ctx, const mnw_float_desc *desc, const 
     return MNW_OK;
 }
 
-// Every IntGroup / FloatGroup column of one minh block in two launches (minh.Reader.Block's per-column loop,
+// Every IntGroup / FloatGroup column of one minh block in at most three launches (plain float, Log, int) (minh.Reader.Block's per-column loop,
 // go/minh/minh.go:296-323): column c is block 0 of its own group, packed at data + offsets[c].
 int mnw_decode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, const uint8_t *data, int64_t data_len,
                            const int64_t *offsets, const int64_t *mins, const int64_t *bits, int64_t n, const mnw_jitter *jitter,
@@ -975,26 +979,29 @@ int mnw_decode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, 
     if (jitter && (jitter->mode < 0 || jitter->mode > 1))
         return fail(ctx, MNW_ERR_ARG, "mnw_decode_columns_dev takes MNW_JITTER_CENTER or MNW_JITTER_HASH");
     std::vector<FloatParams> tab((size_t)ncols);
-    std::vector<int64_t> sel_f, sel_i;
-    std::vector<void *> out_f, out_i;
+    std::vector<int64_t> sel_f, sel_l, sel_i;   // plain float columns, Log columns (their kernel carries 10^x), int columns
+    std::vector<void *> out_f, out_l, out_i;
     for (int64_t c = 0; c < ncols; c++) {
         if (!out_dev[c]) return fail(ctx, MNW_ERR_ARG, "column %lld has no output", (long long)c);
         if (cols[c].is_float) {
             int rc = check_desc(ctx, &cols[c].desc);
             if (rc) return rc;
             tab[(size_t)c] = to_params(cols[c].desc);
-            sel_f.push_back(c); out_f.push_back(out_dev[c]);
+            if (cols[c].desc.log10) { sel_l.push_back(c); out_l.push_back(out_dev[c]); }
+            else { sel_f.push_back(c); out_f.push_back(out_dev[c]); }
         } else {
             tab[(size_t)c] = FloatParams{};
             sel_i.push_back(c); out_i.push_back(out_dev[c]);
         }
     }
-    // one upload: [tab | sel_f | sel_i | out_f | out_i]
-    const size_t tab_b = sizeof(FloatParams) * (size_t)ncols, o_sf = (tab_b + 15) & ~(size_t)15, o_si = o_sf + 8 * sel_f.size(),
-                 o_of = o_si + 8 * sel_i.size(), o_oi = o_of + 8 * out_f.size(), total = o_oi + 8 * out_i.size();
+    // one upload: [tab | sel_f | sel_l | sel_i | out_f | out_l | out_i]
+    const size_t tab_b = sizeof(FloatParams) * (size_t)ncols, o_sf = (tab_b + 15) & ~(size_t)15, o_sl = o_sf + 8 * sel_f.size(),
+                 o_si = o_sl + 8 * sel_l.size(), o_of = o_si + 8 * sel_i.size(), o_ol = o_of + 8 * out_f.size(),
+                 o_oi = o_ol + 8 * out_l.size(), total = o_oi + 8 * out_i.size();
     std::vector<unsigned char> blob(total);
     memcpy(blob.data(), tab.data(), tab_b);
     if (!sel_f.empty()) { memcpy(blob.data() + o_sf, sel_f.data(), 8 * sel_f.size()); memcpy(blob.data() + o_of, out_f.data(), 8 * out_f.size()); }
+    if (!sel_l.empty()) { memcpy(blob.data() + o_sl, sel_l.data(), 8 * sel_l.size()); memcpy(blob.data() + o_ol, out_l.data(), 8 * out_l.size()); }
     if (!sel_i.empty()) { memcpy(blob.data() + o_si, sel_i.data(), 8 * sel_i.size()); memcpy(blob.data() + o_oi, out_i.data(), 8 * out_i.size()); }
     CU(ctx->dec_cols.reserve(total + 16));
     CU(cudaMemcpyAsync(ctx->dec_cols.p, blob.data(), total, cudaMemcpyHostToDevice, ctx->L.stream));   // pageable: staged before return
@@ -1004,7 +1011,13 @@ int mnw_decode_columns_dev(mnw_ctx *ctx, int64_t ncols, const mnw_column *cols, 
     h.tab = (const FloatParams *)d; h.tab_per_file = 1;
     if (jitter) { h.jmode = jitter->mode; h.seed = jitter->seed; h.block_id0 = jitter->block_id0; }
     if (!sel_f.empty()) {
-        h.mode = 1; h.sel = (const int64_t *)(d + o_sf); h.nsel = (int64_t)sel_f.size(); h.outs = (void *const *)(d + o_of);
+        h.mode = 1; h.any_log = false;
+        h.sel = (const int64_t *)(d + o_sf); h.nsel = (int64_t)sel_f.size(); h.outs = (void *const *)(d + o_of);
+        launch_decode(ctx->L, h);
+    }
+    if (!sel_l.empty()) {
+        h.mode = 1; h.any_log = true;
+        h.sel = (const int64_t *)(d + o_sl); h.nsel = (int64_t)sel_l.size(); h.outs = (void *const *)(d + o_ol);
         launch_decode(ctx->L, h);
     }
     if (!sel_i.empty()) {

@@ -795,6 +795,9 @@ k_pack_i64c(const BlockDesc *__restrict__ descs, const BlockStat *__restrict__ s
 // tile's packed bytes are staged in shared memory with 128-bit loads, every thread then extracts
 // four consecutive values, dequantises them and stores one float4.
 constexpr int FDEC_THREADS = 128;
+// LOG: some group of the batch is a minh Log column (10^x after the dequantisation).  The plain instantiation does not carry
+// the FP64 registers of go_pow10_f32 (63 -> ~40 registers: 12 CTAs per SM instead of 8).
+template <bool LOG>
 __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
     __shared__ __align__(16) unsigned spk[DEC_CHUNK + 16];
     const int64_t tpb = (A.n + DEC_CHUNK - 1) / DEC_CHUNK;
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(FDEC_THREADS) k_decode_f32c(DecodeArgs A) {
     const int bits = (int)A.bits[b];
     const FloatParams fp = A.tab[A.tab_per_file ? b : 0];   // (a batch of columns: one group per block)
     const long long P = fp.pixels;
-    const bool periodic = fp.flags & F_PERIODIC, islog = fp.flags & F_LOG10;
+    const bool periodic = fp.flags & F_PERIODIC, islog = LOG && (fp.flags & F_LOG10);
     const int64_t first = tile * DEC_CHUNK;
     const int count = (int)(first + DEC_CHUNK <= A.n ? DEC_CHUNK : A.n - first);
     const unsigned long long bid = A.block_id0 + (unsigned long long)(A.jitter_ids ? A.jitter_ids[j] : b);
@@ -1131,7 +1134,8 @@ void launch_decode(Launcher &L, const DecodeHost &h) {
     int64_t cpb = (h.n + DEC_CHUNK - 1) / DEC_CHUNK;
     if (h.mode == 1 && h.jmode != 2) {   // contiguous float32 blocks: staged, vectorised decode
         L.begin("k_decode_f32c");
-        k_decode_f32c<<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
+        if (h.any_log) k_decode_f32c<true><<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
+        else k_decode_f32c<false><<<(unsigned)(h.nsel * cpb), FDEC_THREADS, 0, L.stream>>>(A);
         L.end();
         L.count++;
         return;

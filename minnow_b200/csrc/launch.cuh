@@ -71,6 +71,7 @@ struct DecodeHost {
     int32_t nfile = 0, subcells = 0;
     void *out = nullptr;
     void *const *outs = nullptr;   // device array: output pointer of every selected block (contiguous group decoders)
+    bool any_log = true;           // some group of the table is a Log column (false: the kernel without 10^x is enough)
 };
 
 // kernels_generic.cu
